@@ -1,0 +1,138 @@
+/* include/s3dmst.h — C ABI of the B200-native Stereo3DMST hot path.
+ *
+ * This is the drop-in boundary for the reference's
+ *     extern "C" void stereo3dmst(std::string, std::string, cv::Mat&, cv::Mat&, cv::Mat&, cv::Mat&,
+ *                                 std::string, int)            (include/Stereo3DMST.h:7)
+ * and the host functions it is made of (src/Stereo3DMST.cpp).  The reference signature passes
+ * C++ objects, so it is not an ABI; what a maintainer binds instead is this header (plain
+ * pointers and sizes, no C++/torch types).  A header-compatible C++ shim that forwards
+ * stereo3dmst(cv::Mat...) to these entry points lives in stereomatch_b200/csrc/stereo3dmst_shim.cpp;
+ * INTEGRATION.md shows the call-site change.
+ *
+ * Conventions: every function returns 0 on success or a negative S3DMST_E_* code;
+ * s3dmst_last_error() gives the message.  No exceptions cross the ABI.  All buffers are
+ * caller-owned; unless a name ends in _dev they are HOST pointers and the call synchronises
+ * the context's stream before returning.  One context per GPU; a context is not thread-safe.
+ * "view": 0 = left, 1 = right.  Pixels are raster order p = y*W + x.  Volumes handed across the
+ * ABI are the reference's layout float[D][H][W] (Stereo3DMST.cpp:117, :769-773).
+ * There is NO CPU fallback: every entry point fails with S3DMST_E_CUDA if no device is usable.
+ */
+#ifndef S3DMST_H_
+#define S3DMST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s3dmst_ctx s3dmst_ctx;
+
+enum {
+    S3DMST_OK = 0,
+    S3DMST_E_ARG = -1,   /* bad argument / call order */
+    S3DMST_E_CUDA = -2,  /* CUDA runtime error (message has the detail) */
+    S3DMST_E_STATE = -3, /* required stage has not run */
+    S3DMST_E_LIMIT = -4  /* internal iteration cap hit (forest kernels) */
+};
+
+/* The literals of src/Stereo3DMST.cpp lifted into one struct (reference values are the defaults). */
+typedef struct s3dmst_params {
+    float fh_c;         /* 5000      Stereo3DMST.cpp:831   FH threshold constant                     */
+    int min_cc_size;    /* 200       :832                  min-size merge bound (max(2, .) applied)  */
+    float gamma;        /* 1/12      :830                  edge weight = exp(-w*gamma)               */
+    int median;         /* 3         :214                  0 disables the 3x3 median                 */
+    float cost_cap;     /* 0.5       :789-801              ingest: NaN -> cap, else min(cap, v)      */
+    float cost_offset;  /* 0         :792 (commented)      ingest: v = (c + offset) * scale          */
+    float cost_scale;   /* 1                                                                       */
+    float oob_cost;     /* 0.5       :115                  label cost outside [0, Dmax)              */
+    int num_iter;       /* 100       :854                                                         */
+    float refine_floor; /* 0.1       :600                                                         */
+    int exact;          /* 1: fp64, reference association order (bit-exact); 0: fp32 fast path      */
+    int keep_aggregated;/* 1: s3dmst_aggregate_dense keeps the final aggregated volume for dumps    */
+    int agg_threads;    /* 0 = auto; threads per CTA of the aggregation kernels (multiple of 32)    */
+    int agg_cache_nodes;/* 0 = auto; nodes of a tree level cached in shared memory per CTA          */
+} s3dmst_params;
+
+void s3dmst_default_params(s3dmst_params* p);
+
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to own one. */
+int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream);
+void s3dmst_destroy(s3dmst_ctx* ctx);
+const char* s3dmst_last_error(const s3dmst_ctx* ctx);
+int s3dmst_sync(s3dmst_ctx* ctx);
+
+/* a1 inputs: two interleaved BGR u8 images (cv::Mat CV_8UC3), row stride in bytes.  H2D copy. */
+int s3dmst_set_images(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H,
+                      int stride_bytes);
+
+/* a3,a4,a5,a7 (Stereo3DMST.cpp:226-307, :342-384, :434-522; segment-graph.h:54-89): median, edge
+ * weights, FH forest (level-synchronous Boruvka), min-size merge, tree ids, BFS re-indexing. */
+int s3dmst_build_forest(s3dmst_ctx* ctx, int view);
+int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth, int* adj_size);
+/* Parity dump; any pointer may be NULL.  edge_weight/edge_mask are [2N] by canonical edge id
+ * (2p = right neighbour, 2p+1 = down neighbour; mask 1 = FH edge, 2 = min-size-merge edge);
+ * tree_start [T+1]; per node (tree-major, BFS order): node_pixel, parent, child_begin,
+ * child_count, parent_weight (integer edge weight to the parent), level;  tree_id [N] by pixel;
+ * tree adjacency CSR adj_ptr [T+1], adj [adj_size] (ascending = boost setS order). */
+int s3dmst_get_forest(s3dmst_ctx* ctx, int view, uint16_t* edge_weight, uint8_t* edge_mask, int32_t* tree_id,
+                      int32_t* tree_start, int32_t* node_pixel, int32_t* parent, int32_t* child_begin,
+                      int32_t* child_count, uint16_t* parent_weight, int32_t* level, int32_t* adj_ptr, int32_t* adj);
+/* Upload an externally built forest instead (tests: isolates the aggregation kernels). */
+int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int num_trees, const int32_t* tree_start,
+                      const int32_t* node_pixel, const int32_t* parent, const uint16_t* parent_weight);
+
+/* a2': truncated colour + gradient absolute-difference volume for both views, D labels
+ * (PatchMatchStereoGPU.cu:1482-1550), written straight into the node-major device layout;
+ * then the a2 ingest (Stereo3DMST.cpp:785-803) if apply_ingest != 0.  Needs both forests. */
+int s3dmst_build_cost_volume(s3dmst_ctx* ctx, int D, int apply_ingest);
+/* a2: external volume in the mc-cnn file layout float[D][H][W] (left.bin / right.bin), ingested. */
+int s3dmst_set_cost_volume(s3dmst_ctx* ctx, int view, const float* vol_dmajor, int D, int apply_ingest);
+int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol_dmajor);
+
+/* a9,a10 + WTA, dense-label mode: labels [d0,d1), two-pass tree filter, strict '<'
+ * so the lowest d wins ties.  disp [N] int32 and best_cost [N] double by pixel (NULL = leave on device). */
+int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* disp, double* best_cost);
+/* Final aggregated volume of the last dense call, double[D][H][W] (needs params.keep_aggregated). */
+int s3dmst_get_aggregated(s3dmst_ctx* ctx, int view, double* agg_dmajor);
+/* Device pointers of the dense result (pixel order) for collectives: best cost f64 [N], disparity i32 [N]. */
+int s3dmst_dense_result_dev(s3dmst_ctx* ctx, int view, double** best_cost_dev, int32_t** disp_dev);
+/* After an all-reduce(MIN) of best cost into global_min_dev: disp := INT32_MAX where the local cost is not
+ * the global minimum, so that a second all-reduce(MIN) on disp yields the lowest d attaining the minimum. */
+int s3dmst_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
+/* Dense disparity (int) -> float disparity map used by the LR check. */
+int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view);
+
+/* a6/a11/a12 PatchMatch state: labels abc [N][3] fp32 and min_cost [N] fp64 (init DBL_MAX). */
+int s3dmst_set_labels(s3dmst_ctx* ctx, int view, const float* abc);
+int s3dmst_get_labels(s3dmst_ctx* ctx, int view, float* abc);
+int s3dmst_reset_min_cost(s3dmst_ctx* ctx, int view);
+int s3dmst_get_min_cost(s3dmst_ctx* ctx, int view, double* min_cost);
+/* Injected proposals, applied in order (MSTCostAggregationAndLabelUpdate, :160-186): proposal i tests
+ * label labels[3i..3i+2] on tree tree_ids[i]. */
+int s3dmst_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* tree_ids, const float* labels, size_t n);
+/* a13 LabelToDisp (:189-201) followed by the *(Dmax-1) of :900-902. */
+int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view);
+
+int s3dmst_set_disparity(s3dmst_ctx* ctx, int view, const float* disp);
+int s3dmst_get_disparity(s3dmst_ctx* ctx, int view, float* disp);
+/* a14 leftRightConsistencyCheck (:632-710): invalid left pixels -> 0; fill != 0 runs the scan-line fill. */
+int s3dmst_lr_check(s3dmst_ctx* ctx, int fill);
+
+/* Whole dense pipeline on the current images: forests, cost volume, aggregation + WTA for both views,
+ * LR check (+fill).  Outputs float[H][W] (NULL = leave on device). */
+int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp);
+
+/* Per-stage device time of the most recent call, in ms (CUDA events on the context's stream). */
+enum {
+    S3DMST_T_FOREST = 0, S3DMST_T_COST = 1, S3DMST_T_AGG = 2, S3DMST_T_POST = 3, S3DMST_T_PMS = 4, S3DMST_T_COUNT = 5
+};
+double s3dmst_stage_ms(s3dmst_ctx* ctx, int stage);
+/* Number of kernels this library has launched on the context since creation. */
+long long s3dmst_launch_count(const s3dmst_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3DMST_H_ */

@@ -1,0 +1,509 @@
+// stereomatch_b200/csrc/api.cu — the C ABI declared in include/s3dmst.h: context, buffers, staging copies
+// and the stage orchestration of stereo3dmst() (src/Stereo3DMST.cpp:714-912).  Device work only; the few
+// host-side loops here are metadata (tree order, uploaded-forest bookkeeping, parity dumps).
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "internal.h"
+
+int s3_fail(s3dmst_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+static thread_local std::string g_create_err;
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t n) {
+    return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+}
+#define DFREE(p)          \
+    do {                  \
+        if (p) cudaFree(p); \
+        p = nullptr;      \
+    } while (0)
+
+static void free_view(View& V) {
+    DFREE(V.bgr); DFREE(V.raw4); DFREE(V.med); DFREE(V.gray); DFREE(V.ew);
+    DFREE(V.uf_parent); DFREE(V.uf_size); DFREE(V.uf_lastw); DFREE(V.uf_best); DFREE(V.uf_resv);
+    DFREE(V.mask); DFREE(V.elist); DFREE(V.e_ra); DFREE(V.e_rb); DFREE(V.e_flag);
+    DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
+    DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
+    DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up);
+    DFREE(V.lvl_start);
+    DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
+    DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
+    V.forest_ready = V.cost_ready = V.agg_ready = V.labels_ready = false;
+    V.T = 0; V.D = V.Dp = 0;
+}
+
+static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
+    const size_t n = N;
+    S3_CUDA(dalloc(&V.bgr, 3 * n)); S3_CUDA(dalloc(&V.raw4, n)); S3_CUDA(dalloc(&V.med, n)); S3_CUDA(dalloc(&V.gray, n));
+    S3_CUDA(dalloc(&V.ew, 2 * n));
+    S3_CUDA(dalloc(&V.uf_parent, n)); S3_CUDA(dalloc(&V.uf_size, n)); S3_CUDA(dalloc(&V.uf_lastw, n));
+    S3_CUDA(dalloc(&V.uf_best, n)); S3_CUDA(dalloc(&V.uf_resv, n));
+    S3_CUDA(dalloc(&V.mask, 2 * n)); S3_CUDA(dalloc(&V.elist, 2 * n)); S3_CUDA(dalloc(&V.e_ra, 2 * n));
+    S3_CUDA(dalloc(&V.e_rb, 2 * n)); S3_CUDA(dalloc(&V.e_flag, 2 * n));
+    S3_CUDA(dalloc(&V.hist, S3_NUM_W)); S3_CUDA(dalloc(&V.lvl_off, S3_NUM_W + 1)); S3_CUDA(dalloc(&V.lvl_cursor, S3_NUM_W));
+    S3_CUDA(dalloc(&V.counters, S3_MAX_ROUNDS));
+    S3_CUDA(dalloc(&V.minpix, n)); S3_CUDA(dalloc(&V.scan_tmp, n + 4096)); S3_CUDA(dalloc(&V.tree_id, n));
+    S3_CUDA(dalloc(&V.tree_size, n)); S3_CUDA(dalloc(&V.tree_rootpix, n));
+    S3_CUDA(dalloc(&V.tree_start, n + 1)); S3_CUDA(dalloc(&V.tree_depth, n)); S3_CUDA(dalloc(&V.unit_tree, n));
+    S3_CUDA(dalloc(&V.node_pixel, n)); S3_CUDA(dalloc(&V.pixel_node, n)); S3_CUDA(dalloc(&V.parent, n));
+    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n));
+    S3_CUDA(dalloc(&V.lvl_start, 2 * n + 2));
+    S3_CUDA(dalloc(&V.disp_i, n)); S3_CUDA(dalloc(&V.best, n)); S3_CUDA(dalloc(&V.abc, 3 * n)); S3_CUDA(dalloc(&V.min_cost, n));
+    S3_CUDA(dalloc(&V.disp_f, n)); S3_CUDA(dalloc(&V.lr_mask, n));
+    return 0;
+}
+
+static int set_size(s3dmst_ctx* ctx, int W, int H) {
+    if (W < 1 || H < 1 || (long long)W * H > (1ll << 27)) return s3_fail(ctx, S3DMST_E_ARG, "image size %dx%d unsupported", W, H);
+    if (ctx->W == W && ctx->H == H) return 0;
+    for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
+    ctx->W = W; ctx->H = H; ctx->N = W * H;
+    for (int i = 0; i < 2; i++) S3_TRY(alloc_view(ctx, ctx->v[i], ctx->N));
+    return 0;
+}
+
+extern "C" {
+
+void s3dmst_default_params(s3dmst_params* p) {
+    p->fh_c = 5000.0f;
+    p->min_cc_size = 200;
+    p->gamma = 1.0f / 12.f;
+    p->median = 3;
+    p->cost_cap = 0.5f;
+    p->cost_offset = 0.0f;
+    p->cost_scale = 1.0f;
+    p->oob_cost = 0.5f;
+    p->num_iter = 100;
+    p->refine_floor = 0.1f;
+    p->exact = 1;
+    p->keep_aggregated = 0;
+    p->agg_threads = 0;
+    p->agg_cache_nodes = 0;
+}
+
+int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream) {
+    if (!out) return S3DMST_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_err = std::string("s3dmst_create: no usable CUDA device (") + cudaGetErrorString(e) + ")";
+        return S3DMST_E_CUDA;  // no CPU fallback
+    }
+    s3dmst_ctx* ctx = new s3dmst_ctx;
+    ctx->device = device;
+    if (params) ctx->P = *params; else s3dmst_default_params(&ctx->P);
+    memset(ctx->ev, 0, sizeof ctx->ev);
+    memset(ctx->ev_set, 0, sizeof ctx->ev_set);
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    cudaDeviceProp prop;
+    ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok) ctx->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else if (ok) {
+        ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+        ctx->own_stream = ok;
+    }
+    for (int i = 0; ok && i < S3DMST_T_COUNT * 4; i++) ok = cudaEventCreate(&ctx->ev[i / 4][(i / 2) & 1][i & 1]) == cudaSuccess;
+    if (ok) {
+        // weights (Stereo3DMST.cpp:444, :513): exp(-w*gamma) in double with gamma promoted from float
+        std::vector<double> w(S3_NUM_W), w2(S3_NUM_W);
+        std::vector<float> wf(S3_NUM_W), w2f(S3_NUM_W);
+        for (int i = 0; i < S3_NUM_W; i++) {
+            w[i] = exp(-(double)i * ctx->P.gamma);
+            w2[i] = 1.0f - w[i] * w[i];
+            wf[i] = (float)w[i];
+            w2f[i] = (float)w2[i];
+        }
+        ok = dalloc(&ctx->lut_w, S3_NUM_W) == cudaSuccess && dalloc(&ctx->lut_w2, S3_NUM_W) == cudaSuccess &&
+             dalloc(&ctx->lut_wf, S3_NUM_W) == cudaSuccess && dalloc(&ctx->lut_w2f, S3_NUM_W) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->lut_w, w.data(), sizeof(double) * S3_NUM_W, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->lut_w2, w2.data(), sizeof(double) * S3_NUM_W, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->lut_wf, wf.data(), sizeof(float) * S3_NUM_W, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->lut_w2f, w2f.data(), sizeof(float) * S3_NUM_W, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        g_create_err = std::string("s3dmst_create: ") + cudaGetErrorString(cudaGetLastError());
+        s3dmst_destroy(ctx);
+        return S3DMST_E_CUDA;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void s3dmst_destroy(s3dmst_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
+    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch);
+    for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
+        if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* s3dmst_last_error(const s3dmst_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int s3dmst_sync(s3dmst_ctx* ctx) {
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+long long s3dmst_launch_count(const s3dmst_ctx* ctx) { return ctx->launches; }
+
+double s3dmst_stage_ms(s3dmst_ctx* ctx, int stage) {
+    if (stage < 0 || stage >= S3DMST_T_COUNT) return -1.0;
+    double total = 0.0;
+    for (int view = 0; view < 2; view++) {
+        if (!ctx->ev_set[stage][view]) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->ev[stage][view][1]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+        if (cudaEventElapsedTime(&ms, ctx->ev[stage][view][0], ctx->ev[stage][view][1]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+        total += ms;
+    }
+    return total;
+}
+
+int s3dmst_set_images(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride) {
+    if (!left_bgr || !right_bgr || stride < 3 * W) return s3_fail(ctx, S3DMST_E_ARG, "set_images: bad pointers/stride");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(set_size(ctx, W, H));
+    const uint8_t* src[2] = {left_bgr, right_bgr};
+    for (int i = 0; i < 2; i++) {
+        S3_CUDA(cudaMemcpy2DAsync(ctx->v[i].bgr, 3 * (size_t)W, src[i], stride, 3 * (size_t)W, H, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+        ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
+    }
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
+    return 0;
+}
+
+int s3dmst_build_forest(s3dmst_ctx* ctx, int view) {
+    if (view < 0 || view > 1 || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "build_forest: bad view or no images");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_EV_BEGIN(S3DMST_T_FOREST, view);
+    S3_TRY(s3_image_stage(ctx, view));
+    S3_TRY(s3_forest_stage(ctx, view));
+    S3_EV_END(S3DMST_T_FOREST, view);
+    return 0;
+}
+
+int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth, int* adj_size);
+
+// host-side tree adjacency for dumps (Stereo3DMST.cpp:377-384): unique neighbours, ascending
+static int host_adjacency(s3dmst_ctx* ctx, int view, std::vector<int>& adj_ptr, std::vector<int>& adj) {
+    View& V = ctx->v[view];
+    const int N = ctx->N, W = ctx->W, H = ctx->H;
+    std::vector<int> tid(N);
+    S3_CUDA(cudaMemcpyAsync(tid.data(), V.tree_id, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::vector<int>> nb(V.T);
+    for (int p = 0; p < N; p++) {
+        const int x = p % W, y = p / W;
+        if (x < W - 1 && tid[p] != tid[p + 1]) { nb[tid[p]].push_back(tid[p + 1]); nb[tid[p + 1]].push_back(tid[p]); }
+        if (y < H - 1 && tid[p] != tid[p + W]) { nb[tid[p]].push_back(tid[p + W]); nb[tid[p + W]].push_back(tid[p]); }
+    }
+    adj_ptr.assign(V.T + 1, 0);
+    adj.clear();
+    for (int t = 0; t < V.T; t++) {
+        std::sort(nb[t].begin(), nb[t].end());
+        nb[t].erase(std::unique(nb[t].begin(), nb[t].end()), nb[t].end());
+        adj.insert(adj.end(), nb[t].begin(), nb[t].end());
+        adj_ptr[t + 1] = (int)adj.size();
+    }
+    return 0;
+}
+
+int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth, int* adj_size) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    View& V = ctx->v[view];
+    if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "forest_info: no forest");
+    if (num_trees) *num_trees = V.T;
+    if (max_depth) *max_depth = V.max_depth;
+    if (adj_size) {
+        std::vector<int> ap, a;
+        S3_TRY(host_adjacency(ctx, view, ap, a));
+        *adj_size = (int)a.size();
+    }
+    return 0;
+}
+
+#define D2H(dst, src, bytes)                                                                          \
+    do {                                                                                              \
+        if (dst) S3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));       \
+    } while (0)
+
+int s3dmst_get_forest(s3dmst_ctx* ctx, int view, uint16_t* edge_weight, uint8_t* edge_mask, int32_t* tree_id,
+                      int32_t* tree_start, int32_t* node_pixel, int32_t* parent, int32_t* child_begin,
+                      int32_t* child_count, uint16_t* parent_weight, int32_t* level, int32_t* adj_ptr, int32_t* adj) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    View& V = ctx->v[view];
+    if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "get_forest: no forest");
+    const size_t N = ctx->N;
+    D2H(edge_weight, V.ew, 2 * N * sizeof(uint16_t));
+    D2H(edge_mask, V.mask, 2 * N);
+    D2H(tree_id, V.tree_id, N * sizeof(int));
+    D2H(tree_start, V.tree_start, (V.T + 1) * sizeof(int));
+    D2H(node_pixel, V.node_pixel, N * sizeof(int));
+    D2H(parent, V.parent, N * sizeof(int));
+    D2H(parent_weight, V.pw, N * sizeof(uint16_t));
+    D2H(level, V.level, N * sizeof(int));
+    if (child_begin || child_count) {
+        std::vector<NodeUp> nu(N);
+        S3_CUDA(cudaMemcpyAsync(nu.data(), V.node_up, N * sizeof(NodeUp), cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < N; i++) {
+            if (child_begin) child_begin[i] = nu[i].child_begin;
+            if (child_count) child_count[i] = nu[i].child_count;
+        }
+    }
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (adj_ptr || adj) {
+        std::vector<int> ap, a;
+        S3_TRY(host_adjacency(ctx, view, ap, a));
+        if (adj_ptr) memcpy(adj_ptr, ap.data(), ap.size() * sizeof(int));
+        if (adj) memcpy(adj, a.data(), a.size() * sizeof(int));
+    }
+    return 0;
+}
+
+int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int32_t* tree_start, const int32_t* node_pixel,
+                      const int32_t* parent, const uint16_t* parent_weight) {
+    if (view < 0 || view > 1 || T < 1 || !tree_start || !node_pixel || !parent || !parent_weight)
+        return s3_fail(ctx, S3DMST_E_ARG, "set_forest: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->N == 0) S3_TRY(set_size(ctx, W, H));
+    if (W != ctx->W || H != ctx->H) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: size differs from the context's images");
+    View& V = ctx->v[view];
+    const int N = ctx->N;
+    if (tree_start[T] != N) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: tree_start[T] != W*H");
+    // derive the per-node records the kernels read (children contiguous in BFS order)
+    std::vector<NodeUp> nu(N);
+    std::vector<int> level(N, 0), pixel_node(N, -1), tree_id(N, 0), lvl(2 * (size_t)N + 2, 0), depth(T, 0);
+    for (int i = 0; i < N; i++) { nu[i].child_begin = 0; nu[i].child_count = 0; nu[i].cw01 = nu[i].cw23 = 0; }
+    for (int t = 0; t < T; t++) {
+        const int a = tree_start[t], b = tree_start[t + 1];
+        if (b <= a || parent[a] != a) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: tree %d malformed", t);
+        for (int g = a; g < b; g++) {
+            if (node_pixel[g] < 0 || node_pixel[g] >= N) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: pixel out of range");
+            pixel_node[node_pixel[g]] = g;
+            tree_id[node_pixel[g]] = t;
+            if (g == a) continue;
+            const int p = parent[g];
+            if (p < a || p >= g) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: node %d is not in BFS order", g);
+            level[g] = level[p] + 1;
+            if (level[g] < level[g - 1]) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: levels not monotone at %d", g);
+            NodeUp& P = nu[p];
+            if (P.child_count == 0) P.child_begin = g;
+            if (P.child_begin + P.child_count != g || P.child_count >= 4)
+                return s3_fail(ctx, S3DMST_E_ARG, "set_forest: children of %d not contiguous / more than 4", p);
+            const uint32_t wv = parent_weight[g];
+            if (wv >= S3_NUM_W) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: weight out of range");
+            if (P.child_count < 2) P.cw01 |= wv << (16 * P.child_count); else P.cw23 |= wv << (16 * (P.child_count - 2));
+            P.child_count++;
+        }
+        int* L = lvl.data() + a + t;
+        int d = 0;
+        L[0] = a;
+        for (int g = a + 1; g < b; g++)
+            if (level[g] != level[g - 1]) L[++d] = g;
+        L[++d] = b;
+        depth[t] = d;
+    }
+    std::vector<int> order(T);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tree_start[x + 1] - tree_start[x] > tree_start[y + 1] - tree_start[y]; });
+    std::vector<int> rootpix(T);
+    for (int t = 0; t < T; t++) rootpix[t] = node_pixel[tree_start[t]];
+#define H2D(dst, src, bytes) S3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))
+    H2D(V.tree_start, tree_start, sizeof(int) * (T + 1));
+    H2D(V.node_pixel, node_pixel, sizeof(int) * N);
+    H2D(V.parent, parent, sizeof(int) * N);
+    H2D(V.pw, parent_weight, sizeof(uint16_t) * N);
+    H2D(V.node_up, nu.data(), sizeof(NodeUp) * N);
+    H2D(V.level, level.data(), sizeof(int) * N);
+    H2D(V.pixel_node, pixel_node.data(), sizeof(int) * N);
+    H2D(V.tree_id, tree_id.data(), sizeof(int) * N);
+    H2D(V.lvl_start, lvl.data(), sizeof(int) * (N + T + 1));
+    H2D(V.tree_depth, depth.data(), sizeof(int) * T);
+    H2D(V.unit_tree, order.data(), sizeof(int) * T);
+    H2D(V.tree_rootpix, rootpix.data(), sizeof(int) * T);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    V.T = T;
+    V.h_tree_start.assign(tree_start, tree_start + T + 1);
+    V.h_unit_tree = order;
+    return s3_forest_finalize_host(ctx, view);
+}
+
+int s3dmst_build_cost_volume(s3dmst_ctx* ctx, int D, int apply_ingest) {
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_cost_adgrad(ctx, D, apply_ingest);
+}
+
+int s3dmst_set_cost_volume(s3dmst_ctx* ctx, int view, const float* vol, int D, int apply_ingest) {
+    if (view < 0 || view > 1 || !vol) return s3_fail(ctx, S3DMST_E_ARG, "set_cost_volume: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    float* stage = nullptr;
+    const size_t bytes = (size_t)ctx->N * D * sizeof(float);
+    S3_CUDA(cudaMalloc(&stage, bytes));
+    cudaError_t e = cudaMemcpyAsync(stage, vol, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = e == cudaSuccess ? s3_cost_from_dmajor(ctx, view, stage, D, apply_ingest) : s3_fail(ctx, S3DMST_E_CUDA, "H2D: %s", cudaGetErrorString(e));
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol) {
+    if (view < 0 || view > 1 || !vol) return s3_fail(ctx, S3DMST_E_ARG, "get_cost_volume: bad arguments");
+    View& V = ctx->v[view];
+    if (!V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "get_cost_volume: no volume");
+    float* stage = nullptr;
+    const size_t bytes = (size_t)ctx->N * V.D * sizeof(float);
+    S3_CUDA(cudaMalloc(&stage, bytes));
+    int rc = s3_cost_to_dmajor(ctx, view, stage);
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(vol, stage, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = s3_fail(ctx, S3DMST_E_CUDA, "D2H: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* disp, double* best_cost) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(s3_aggregate_dense(ctx, view, d0, d1));
+    View& V = ctx->v[view];
+    D2H(disp, V.disp_i, sizeof(int32_t) * ctx->N);
+    D2H(best_cost, V.best, sizeof(double) * ctx->N);
+    if (disp || best_cost) S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int s3dmst_get_aggregated(s3dmst_ctx* ctx, int view, double* agg) {
+    if (view < 0 || view > 1 || !agg) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    View& V = ctx->v[view];
+    if (!V.agg_ready || !ctx->P.keep_aggregated) return s3_fail(ctx, S3DMST_E_STATE, "get_aggregated: needs keep_aggregated and a dense run");
+    const size_t N = ctx->N;
+    std::vector<double> h(N * V.Dp);
+    std::vector<int> np(N);
+    S3_CUDA(cudaMemcpyAsync(h.data(), V.aup, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaMemcpyAsync(np.data(), V.node_pixel, N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t v = 0; v < N; v++)
+        for (int d = 0; d < V.D; d++) agg[(size_t)d * N + np[v]] = h[v * V.Dp + d];
+    return 0;
+}
+
+int s3dmst_dense_result_dev(s3dmst_ctx* ctx, int view, double** best_cost_dev, int32_t** disp_dev) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    if (best_cost_dev) *best_cost_dev = ctx->v[view].best;
+    if (disp_dev) *disp_dev = ctx->v[view].disp_i;
+    return 0;
+}
+
+int s3dmst_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev) {
+    if (view < 0 || view > 1 || !global_min_dev) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    return s3_minloc_mask(ctx, view, global_min_dev);
+}
+
+int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    return s3_dense_to_disp(ctx, view);
+}
+
+int s3dmst_set_labels(s3dmst_ctx* ctx, int view, const float* abc) {
+    if (view < 0 || view > 1 || !abc || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "set_labels: bad arguments");
+    S3_CUDA(cudaMemcpyAsync(ctx->v[view].abc, abc, sizeof(float) * 3 * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->v[view].labels_ready = true;
+    return 0;
+}
+int s3dmst_get_labels(s3dmst_ctx* ctx, int view, float* abc) {
+    if (view < 0 || view > 1 || !abc) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    D2H(abc, ctx->v[view].abc, sizeof(float) * 3 * ctx->N);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int s3dmst_reset_min_cost(s3dmst_ctx* ctx, int view) {
+    if (view < 0 || view > 1 || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    std::vector<double> h(ctx->N, DBL_MAX);  // Stereo3DMST.cpp:820-821
+    S3_CUDA(cudaMemcpyAsync(ctx->v[view].min_cost, h.data(), sizeof(double) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int s3dmst_get_min_cost(s3dmst_ctx* ctx, int view, double* mc) {
+    if (view < 0 || view > 1 || !mc) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    D2H(mc, ctx->v[view].min_cost, sizeof(double) * ctx->N);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int s3dmst_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* tree_ids, const float* labels, size_t n) {
+    if (view < 0 || view > 1 || (n && (!tree_ids || !labels))) return s3_fail(ctx, S3DMST_E_ARG, "pms_apply: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_pms_apply(ctx, view, tree_ids, labels, n);
+}
+
+int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    return s3_label_to_disp(ctx, view);
+}
+
+int s3dmst_set_disparity(s3dmst_ctx* ctx, int view, const float* disp) {
+    if (view < 0 || view > 1 || !disp || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    S3_CUDA(cudaMemcpyAsync(ctx->v[view].disp_f, disp, sizeof(float) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int s3dmst_get_disparity(s3dmst_ctx* ctx, int view, float* disp) {
+    if (view < 0 || view > 1 || !disp) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
+    D2H(disp, ctx->v[view].disp_f, sizeof(float) * ctx->N);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int s3dmst_lr_check(s3dmst_ctx* ctx, int fill) {
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_lr_check(ctx, fill);
+}
+
+int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp) {
+    S3_CUDA(cudaSetDevice(ctx->device));
+    memset(ctx->ev_set, 0, sizeof ctx->ev_set);
+    S3_TRY(s3dmst_build_forest(ctx, 0));
+    S3_TRY(s3dmst_build_forest(ctx, 1));
+    S3_TRY(s3_cost_adgrad(ctx, D, 0));
+    for (int view = 0; view < 2; view++) {
+        S3_TRY(s3_aggregate_dense(ctx, view, 0, D));
+        S3_TRY(s3_dense_to_disp(ctx, view));
+    }
+    S3_TRY(s3_lr_check(ctx, fill));
+    D2H(left_disp, ctx->v[0].disp_f, sizeof(float) * ctx->N);
+    D2H(right_disp, ctx->v[1].disp_f, sizeof(float) * ctx->N);
+    if (left_disp || right_disp) S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// stereomatch_b200/csrc/internal.h — context and per-view device state (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/s3dmst.h"
+
+#define S3_NUM_W 766            // integer edge weights 0..765 (|dR|+|dG|+|dB|)
+#define S3_NO_EDGE 0xFFFFu
+#define S3_DEAD 0xFFFFFFFFu
+
+// Per-node record read by the leaf->root pass: children are contiguous in BFS order.
+struct __align__(16) NodeUp {
+    int child_begin;      // global node index of the first child
+    int child_count;      // 0..4
+    uint32_t cw01, cw23;  // integer edge weights of children 0..3, 16 bits each
+};
+
+struct View {
+    // ---- image stage
+    uint8_t* bgr = nullptr;    // [N*3] tightly packed copy of the input
+    uchar4* raw4 = nullptr;    // [N] raw (b,g,r,0)
+    uchar4* med = nullptr;     // [N] median-filtered (b,g,r,0)
+    float* gray = nullptr;     // [N] s3_gray of the RAW image (cost kernel)
+    uint16_t* ew = nullptr;    // [2N] edge weights by canonical id
+    // ---- union-find / forest construction
+    int* uf_parent = nullptr;  // [N]
+    int* uf_size = nullptr;    // [N]
+    int* uf_lastw = nullptr;   // [N]
+    uint32_t* uf_best = nullptr;        // [N] Boruvka pick (edge id)
+    unsigned long long* uf_resv = nullptr;  // [N] merge reservation key
+    uint8_t* mask = nullptr;   // [2N] 0/1/2
+    uint32_t* elist = nullptr; // [2N] edge ids bucketed by weight, later the merge candidate list
+    int* e_ra = nullptr;       // [2N] per list position scratch
+    int* e_rb = nullptr;
+    uint8_t* e_flag = nullptr; // [2N]
+    int* hist = nullptr;       // [S3_NUM_W] weight histogram
+    int* lvl_off = nullptr;    // [S3_NUM_W+1] bucket offsets
+    int* lvl_cursor = nullptr; // [S3_NUM_W]
+    int* counters = nullptr;   // [S3_MAX_ROUNDS] per-round live counters + misc
+    // ---- labelling
+    int* minpix = nullptr;     // [N] min pixel of the component rooted here
+    int* scan_tmp = nullptr;   // [N] + block sums
+    int* tree_id = nullptr;    // [N] by pixel
+    int* tree_size = nullptr;  // [N] (first T used)
+    int* tree_rootpix = nullptr;  // [N] (first T used)
+    // ---- BFS-ordered forest
+    int T = 0, max_depth = 0;
+    int* tree_start = nullptr;  // [T+1] (allocated N+1)
+    int* tree_depth = nullptr;  // [T]
+    int* unit_tree = nullptr;   // [T] trees by decreasing size
+    int* node_pixel = nullptr;  // [N]
+    int* pixel_node = nullptr;  // [N]
+    int* parent = nullptr;      // [N]
+    int* level = nullptr;       // [N]
+    uint16_t* pw = nullptr;     // [N]
+    NodeUp* node_up = nullptr;  // [N]
+    int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
+    // tree adjacency (host side, built lazily for dumps / proposal generation)
+    std::vector<int> h_tree_start, h_tree_depth, h_unit_tree;
+    bool forest_ready = false;
+    // ---- volumes
+    int D = 0, Dp = 0;          // labels, padded row length (multiple of 4)
+    float* cost = nullptr;      // [N][Dp] node-major, label-minor
+    size_t cost_cap = 0;
+    double* aup = nullptr;      // [N][Dp] leaf->root sums, overwritten by final values on the way down
+    size_t aup_cap = 0;
+    bool cost_ready = false, agg_ready = false;
+    int agg_d0 = 0, agg_d1 = 0;
+    // ---- dense results (pixel order)
+    int32_t* disp_i = nullptr;  // [N]
+    double* best = nullptr;     // [N]
+    // ---- PatchMatch state (pixel order)
+    float* abc = nullptr;       // [N][3]
+    double* min_cost = nullptr; // [N]
+    bool labels_ready = false;
+    // ---- disparity maps
+    float* disp_f = nullptr;    // [N]
+    uint8_t* lr_mask = nullptr; // [N]
+};
+
+struct s3dmst_ctx {
+    int device = 0;
+    s3dmst_params P;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int W = 0, H = 0, N = 0;
+    int num_sms = 0;
+    View v[2];
+    double* lut_w = nullptr;   // [S3_NUM_W] exp(-iw*gamma)
+    double* lut_w2 = nullptr;  // [S3_NUM_W] 1 - w*w
+    float* lut_wf = nullptr;   // fp32 copies for the fast path
+    float* lut_w2f = nullptr;
+    cudaEvent_t ev[S3DMST_T_COUNT][2][2];  // [stage][view][begin/end]
+    bool ev_set[S3DMST_T_COUNT][2];
+    long long launches = 0;
+    std::string err;
+    // scratch for PMS
+    void* pms_scratch = nullptr;
+    size_t pms_scratch_cap = 0;
+};
+
+#define S3_MAX_ROUNDS 65536
+
+// error helpers ---------------------------------------------------------------------------------
+int s3_fail(s3dmst_ctx* c, int code, const char* fmt, ...);
+#define S3_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return s3_fail(ctx, S3DMST_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+#define S3_LAUNCH_CHECK()                                                                               \
+    do {                                                                                                \
+        ctx->launches++;                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                           \
+        if (e__ != cudaSuccess)                                                                         \
+            return s3_fail(ctx, S3DMST_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+#define S3_EV_BEGIN(stage, view) S3_CUDA(cudaEventRecord(ctx->ev[stage][view][0], ctx->stream))
+#define S3_EV_END(stage, view)                                              \
+    do {                                                                   \
+        S3_CUDA(cudaEventRecord(ctx->ev[stage][view][1], ctx->stream));    \
+        ctx->ev_set[stage][view] = true;                                   \
+    } while (0)
+#define S3_TRY(call)            \
+    do {                        \
+        int r__ = (call);       \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+// stage entry points implemented in the .cu files ------------------------------------------------
+int s3_image_stage(s3dmst_ctx* ctx, int view);                    // image.cu: median, gray, edge weights, buckets
+int s3_forest_stage(s3dmst_ctx* ctx, int view);                   // forest.cu: FH + merge + labels + BFS
+int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);           // forest.cu: unit order, depths
+int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
+int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
+int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
+int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu
+int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
+int s3_label_to_disp(s3dmst_ctx* ctx, int view);                  // post.cu
+int s3_dense_to_disp(s3dmst_ctx* ctx, int view);
+int s3_lr_check(s3dmst_ctx* ctx, int fill);
+int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
+int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D);

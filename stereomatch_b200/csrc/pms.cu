@@ -1,0 +1,185 @@
+// stereomatch_b200/csrc/pms.cu — PatchMatch 3D-label proposals over the forest (north-star item 5).
+//
+// Reference: MSTCostAggregationAndLabelUpdate src/Stereo3DMST.cpp:160-186, called from MST_PMS :546-629
+// once per proposal.  Here a whole injected proposal list is evaluated: proposals are grouped by tree
+// (order preserved), and one CTA per tree evaluates them KB at a time, the proposal index playing the
+// role the label index plays in the dense kernel (scratch layout [node][KB], proposal-minor).
+// Work item = (node of the current level, proposal); per-item arithmetic is the reference's:
+//   cost  = compute3DLabelCost (:103-118, two gathers from the node's label row + lerp, fp32)
+//   up    = (((0 + w_k A[c_k]) + ...) + w_1 A[c_1]) + cost          fp64, children in reverse order
+//   down  = w * A[parent] + w2 * A_up
+//   update: sequential over the proposals in list order, strict '<'  (:173-185)
+// Bytes per node-visit: 2x4 cost gathers + 8 write + 8 read scratch + 8 min_cost.
+#include <float.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "hd_math.h"
+#include "internal.h"
+
+#define PMS_KB 32
+
+struct PmsArgs {
+    int W, D, Dp;
+    float oob;
+    const int* unit_tree;
+    const int* tree_start;
+    const int* tree_depth;
+    const int* lvl_start;
+    const NodeUp* node_up;
+    const int* parent;
+    const uint16_t* pw;
+    const int* node_pixel;
+    const float* cost;
+    const double* lut_w;
+    const double* lut_w2;
+    const int* prop_off;   // [T+1] into labels, by tree
+    const float* labels;   // [n][3] grouped by tree, original order inside a tree
+    double* scr;           // [N][PMS_KB]
+    double* min_cost;      // [N] pixel order
+    float* abc;            // [N][3] pixel order
+    int cap;
+};
+
+__global__ void __launch_bounds__(256) k_pms(PmsArgs A) {
+    extern __shared__ double s_lvl[];  // [2][cap][PMS_KB]
+    __shared__ float s_lab[PMS_KB * 3];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int t = A.unit_tree[blockIdx.x];
+    const int p_lo = A.prop_off[t], p_hi = A.prop_off[t + 1];
+    if (p_lo == p_hi) return;
+    const int base = A.tree_start[t], end = A.tree_start[t + 1];
+    const int* lvl = A.lvl_start + base + t;
+    const int depth = A.tree_depth[t];
+    const int cap = A.cap;
+    double* cur = s_lvl;
+    double* prev = s_lvl + (size_t)cap * PMS_KB;
+
+    for (int b0 = p_lo; b0 < p_hi; b0 += PMS_KB) {
+        const int K = min(PMS_KB, p_hi - b0);
+        for (int i = tid; i < 3 * K; i += nt) s_lab[i] = A.labels[3 * (size_t)b0 + i];
+        __syncthreads();
+        // ---- leaf -> root
+        for (int L = depth - 1; L >= 0; --L) {
+            const int ls = lvl[L], le = lvl[L + 1];
+            const int items = (le - ls) * K;
+            for (int idx = tid; idx < items; idx += nt) {
+                const int i = idx / K, k = idx - i * K;
+                const int v = ls + i;
+                const NodeUp nu = A.node_up[v];
+                double acc = 0.0;
+                for (int c = nu.child_count - 1; c >= 0; --c) {
+                    const int ch = nu.child_begin + c;
+                    const int j = ch - le;
+                    const uint32_t iw = ((c & 2) ? nu.cw23 : nu.cw01) >> ((c & 1) * 16) & 0xFFFFu;
+                    const double val = j < cap ? prev[(size_t)j * PMS_KB + k] : A.scr[(size_t)ch * PMS_KB + k];
+                    acc = S3_DADD(acc, S3_DMUL(__ldg(A.lut_w + iw), val));
+                }
+                const int pix = A.node_pixel[v];
+                const float cst = s3_label_cost(A.cost + (size_t)v * A.Dp, s_lab[3 * k], s_lab[3 * k + 1], s_lab[3 * k + 2],
+                                                pix % A.W, pix / A.W, A.D, A.oob);
+                acc = S3_DADD(acc, (double)cst);
+                A.scr[(size_t)v * PMS_KB + k] = acc;
+                if (i < cap) cur[(size_t)i * PMS_KB + k] = acc;
+            }
+            __syncthreads();
+            double* tmp = cur; cur = prev; prev = tmp;
+        }
+        // ---- root -> leaf
+        for (int L = 0; L < depth; ++L) {
+            const int ls = lvl[L], le = lvl[L + 1];
+            const int ps = L > 0 ? lvl[L - 1] : 0;
+            const int items = (le - ls) * K;
+            for (int idx = tid; idx < items; idx += nt) {
+                const int i = idx / K, k = idx - i * K;
+                const int v = ls + i;
+                double fin = A.scr[(size_t)v * PMS_KB + k];
+                if (L > 0) {
+                    const int p = A.parent[v];
+                    const int j = p - ps;
+                    const uint32_t iw = A.pw[v];
+                    const double pv = j < cap ? prev[(size_t)j * PMS_KB + k] : A.scr[(size_t)p * PMS_KB + k];
+                    fin = S3_DADD(S3_DMUL(__ldg(A.lut_w + iw), pv), S3_DMUL(__ldg(A.lut_w2 + iw), fin));
+                    A.scr[(size_t)v * PMS_KB + k] = fin;
+                }
+                if (i < cap) cur[(size_t)i * PMS_KB + k] = fin;
+            }
+            __syncthreads();
+            double* tmp = cur; cur = prev; prev = tmp;
+        }
+        // ---- label update, proposals in list order (:173-185)
+        for (int v = base + tid; v < end; v += nt) {
+            const int pix = A.node_pixel[v];
+            double m = A.min_cost[pix];
+            int lab = -1;
+            for (int k = 0; k < K; k++) {
+                const double a = A.scr[(size_t)v * PMS_KB + k];
+                if (a < m) { m = a; lab = k; }
+            }
+            if (lab >= 0) {
+                A.min_cost[pix] = m;
+                A.abc[3 * (size_t)pix] = s_lab[3 * lab];
+                A.abc[3 * (size_t)pix + 1] = s_lab[3 * lab + 1];
+                A.abc[3 * (size_t)pix + 2] = s_lab[3 * lab + 2];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n) {
+    View& V = ctx->v[view];
+    if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
+        return s3_fail(ctx, S3DMST_E_STATE, "pms_apply: forest, cost volume and labels required");
+    if (n == 0) return 0;
+    const int T = V.T;
+    std::vector<int> off(T + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (h_tree_ids[i] < 0 || h_tree_ids[i] >= T) return s3_fail(ctx, S3DMST_E_ARG, "pms_apply: tree id %d out of range", h_tree_ids[i]);
+        off[h_tree_ids[i] + 1]++;
+    }
+    for (int t = 0; t < T; t++) off[t + 1] += off[t];
+    std::vector<float> lab(3 * n);
+    {
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (size_t i = 0; i < n; i++) {
+            const int pos = cur[h_tree_ids[i]]++;
+            lab[3 * (size_t)pos] = h_labels[3 * i];
+            lab[3 * (size_t)pos + 1] = h_labels[3 * i + 1];
+            lab[3 * (size_t)pos + 2] = h_labels[3 * i + 2];
+        }
+    }
+    const size_t scr_bytes = (size_t)ctx->N * PMS_KB * sizeof(double);
+    const size_t lab_bytes = (3 * n * sizeof(float) + 255) / 256 * 256;
+    const size_t off_bytes = ((T + 1) * sizeof(int) + 255) / 256 * 256;
+    const size_t need = scr_bytes + lab_bytes + off_bytes;
+    if (ctx->pms_scratch_cap < need) {
+        if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
+        ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
+        S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
+        ctx->pms_scratch_cap = need;
+    }
+    char* basep = (char*)ctx->pms_scratch;
+    double* scr = (double*)basep;
+    float* d_lab = (float*)(basep + scr_bytes);
+    int* d_off = (int*)(basep + scr_bytes + lab_bytes);
+    S3_CUDA(cudaMemcpyAsync(d_lab, lab.data(), 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaMemcpyAsync(d_off, off.data(), (T + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+    PmsArgs A;
+    A.W = ctx->W; A.D = V.D; A.Dp = V.Dp; A.oob = ctx->P.oob_cost;
+    A.unit_tree = V.unit_tree; A.tree_start = V.tree_start; A.tree_depth = V.tree_depth; A.lvl_start = V.lvl_start;
+    A.node_up = V.node_up; A.parent = V.parent; A.pw = V.pw; A.node_pixel = V.node_pixel; A.cost = V.cost;
+    A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2; A.prop_off = d_off; A.labels = d_lab; A.scr = scr;
+    A.min_cost = V.min_cost; A.abc = V.abc;
+    A.cap = ctx->P.agg_cache_nodes > 0 ? ctx->P.agg_cache_nodes : 32;
+    const size_t smem = 2 * (size_t)A.cap * PMS_KB * sizeof(double);
+    S3_CUDA(cudaFuncSetAttribute(k_pms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    S3_EV_BEGIN(S3DMST_T_PMS, view);
+    k_pms<<<T, 256, smem, ctx->stream>>>(A);
+    S3_LAUNCH_CHECK();
+    S3_EV_END(S3DMST_T_PMS, view);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    return 0;
+}

@@ -1,0 +1,50 @@
+// tests/models/hd_math_host.cpp — compiles stereomatch_b200/csrc/hd_math.h for the HOST so the per-element
+// arithmetic the CUDA kernels use can be checked against the oracle without a GPU (tests/test_hd_math.py).
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include "../../stereomatch_b200/csrc/hd_math.h"
+
+extern "C" {
+void hd_median3(const uint8_t* in, int W, int H, uint8_t* out) {
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int v[9], k = 0;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int yy = y + dy < 0 ? 0 : (y + dy >= H ? H - 1 : y + dy);
+                    int xx = x + dx < 0 ? 0 : (x + dx >= W ? W - 1 : x + dx);
+                    v[k++] = in[yy * W + xx];
+                }
+            out[y * W + x] = (uint8_t)s3_median9(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+        }
+}
+// same per-pixel logic as k_cost_adgrad, [d][p] output for direct comparison with orc_cost_adgrad
+void hd_cost_adgrad(const uint8_t* L, const uint8_t* R, int W, int H, int D, float* lv, float* rv) {
+    const size_t N = (size_t)W * H;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const size_t p = (size_t)y * W + x, rb = (size_t)y * W;
+            auto g = [&](const uint8_t* I, size_t q) { return s3_gray(I[3 * q], I[3 * q + 1], I[3 * q + 2]); };
+            const bool has_next = x + 1 < W;
+            for (int d = 0; d < D; d++) {
+                float cl = 3.0f, cr = 3.0f;
+                const int xr = x - d;
+                if (xr >= 0 && has_next)
+                    cl = s3_adgrad(R[3 * (rb + xr)], R[3 * (rb + xr) + 1], R[3 * (rb + xr) + 2], g(R, rb + xr), g(R, rb + xr + 1),
+                                   L[3 * p], L[3 * p + 1], L[3 * p + 2], g(L, p), g(L, p + 1));
+                const int xl = x + d;
+                if (xl + 1 < W)
+                    cr = s3_adgrad(R[3 * p], R[3 * p + 1], R[3 * p + 2], g(R, p), g(R, p + 1), L[3 * (rb + xl)],
+                                   L[3 * (rb + xl) + 1], L[3 * (rb + xl) + 2], g(L, rb + xl), g(L, rb + xl + 1));
+                lv[(size_t)d * N + p] = cl;
+                rv[(size_t)d * N + p] = cr;
+            }
+        }
+}
+float hd_label_cost(const float* row, float a, float b, float c, int x, int y, int D, float oob) {
+    return s3_label_cost(row, a, b, c, x, y, D, oob);
+}
+float hd_label_disp(float a, float b, float c, int x, int y, int D) { return s3_label_disp(a, b, c, x, y, D); }
+float hd_ingest(float v, float cap, float off, float sc) { return s3_ingest(v, cap, off, sc); }
+}

@@ -1,0 +1,373 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact for integer/index work and (exact mode) for the FP64 aggregated costs; run with -m gpu on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from stereomatch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({4: np.uint32, 8: np.uint64}[a.dtype.itemsize])
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from stereomatch_b200 import api as _api
+    _api.load_library()
+    return _api
+
+
+CASES = [  # W, H, D, seed, c, min_size, natural
+    (96, 64, 16, 7, 5000.0, 200, 0),
+    (96, 64, 16, 7, 300.0, 20, 0),
+    (64, 64, 8, 1, 50.0, 5, 0),
+    (160, 120, 24, 3, 5000.0, 200, 1),
+    (320, 200, 40, 5, 5000.0, 200, 0),
+    (317, 203, 33, 6, 1000.0, 50, 1),   # ragged sizes, odd D
+    (50, 30, 8, 10, 1e12, 2, 0),        # c -> inf: one tree == the (w, edge-id)-ordered Kruskal MST
+    (33, 1, 6, 11, 100.0, 2, 0),        # single row
+    (1, 37, 6, 12, 100.0, 2, 0),        # single column
+]
+
+
+def make(W, H, D, seed, nat):
+    return (synth.make_natural_pair if nat else synth.make_pair)(W, H, max(D, 12), seed=seed)
+
+
+def check_forest(F, G):
+    assert G["T"] == F.T
+    assert np.array_equal(G["ew"], F.ew)
+    assert np.array_equal(G["mask"], F.mask)
+    assert np.array_equal(G["tree_id"], F.tree_id)
+    assert np.array_equal(G["tree_start"], F.tree_start)
+    assert np.array_equal(G["node_pixel"], F.node_pixel)
+    assert np.array_equal(G["parent"], F.parent)
+    assert np.array_equal(G["child_count"], F.child_count)
+    m = F.child_count > 0
+    assert np.array_equal(G["child_begin"][m], F.child_begin[m])
+    assert np.array_equal(G["pw"], F.pw)
+    assert np.array_equal(G["level"], F.level)
+    assert np.array_equal(G["adj_ptr"], F.adj_ptr)
+    assert np.array_equal(G["adj"], F.adj)
+    assert G["max_depth"] == F.max_depth
+
+
+@pytest.mark.parametrize("W,H,D,seed,c,ms,nat", CASES)
+def test_forest_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat):
+    L, R, _ = make(W, H, D, seed, nat)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms)
+    eng.set_images(L, R)
+    for view, img in ((0, L), (1, R)):
+        eng.build_forest(view)
+        F = oracle.forest(img, c=c, min_size=ms)
+        check_forest(F, eng.get_forest(view))
+        # MST property (north star): with c = inf the forest is the unique (w, id)-ordered MST; total weight equal
+        assert int(F.ew[F.mask > 0].astype(np.int64).sum()) == int(eng.get_forest(view)["ew"][eng.get_forest(view)["mask"] > 0].astype(np.int64).sum())
+    eng.close()
+
+
+def test_forest_without_median(api, oracle):
+    L, R, _ = make(80, 60, 16, 4, 0)
+    eng = api.Stereo3DMST(median=0, fh_c=800.0, min_cc_size=30)
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    check_forest(oracle.forest(L, c=800.0, min_size=30, median=False), eng.get_forest(0))
+    eng.close()
+
+
+@pytest.mark.parametrize("W,H,D,seed", [(96, 64, 16, 7), (130, 50, 100, 2), (64, 40, 130, 3)])
+def test_cost_volume_matches_oracle(api, oracle, W, H, D, seed):
+    L, R, _ = make(W, H, 16, seed, 0)
+    eng = api.Stereo3DMST()
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    eng.build_forest(1)
+    lv, rv = oracle.cost_adgrad(L, R, D)
+    eng.build_cost_volume(D, ingest=False)
+    assert np.array_equal(bits(eng.get_cost_volume(0)), bits(lv))
+    assert np.array_equal(bits(eng.get_cost_volume(1)), bits(rv))
+    eng.close()
+    eng = api.Stereo3DMST(cost_scale=1 / 6.0)
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    eng.build_forest(1)
+    eng.build_cost_volume(D, ingest=True)
+    assert np.array_equal(bits(eng.get_cost_volume(0)), bits(oracle.ingest(lv, 0.5, 0.0, 1 / 6.0)))
+    # external volume path (mc-cnn layout) with NaN scrub
+    ext = lv.copy() * np.float32(0.25)
+    ext[1, 5] = np.nan
+    eng.set_cost_volume(0, ext, ingest=True)
+    assert np.array_equal(bits(eng.get_cost_volume(0)), bits(oracle.ingest(ext, 0.5, 0.0, 1 / 6.0)))
+    eng.close()
+
+
+@pytest.mark.parametrize("W,H,D,seed,c,ms,nat", CASES[:7])
+@pytest.mark.parametrize("own_forest", [False, True])
+def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat, own_forest):
+    L, R, _ = make(W, H, D, seed, nat)
+    F = oracle.forest(L, c=c, min_size=ms)
+    lv, _ = oracle.cost_adgrad(L, R, D)
+    disp_o, best_o, agg_o = oracle.aggregate_dense(F, lv, want_agg=True)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, keep_aggregated=1)
+    eng.set_images(L, R)
+    if own_forest:
+        eng.build_forest(0)
+    else:
+        eng.set_forest(0, W, H, F.tree_start, F.node_pixel, F.parent, F.pw)
+    eng.set_cost_volume(0, lv, ingest=False)
+    disp, best = eng.aggregate_dense(0)
+    agg = eng.get_aggregated(0)
+    assert np.array_equal(bits(agg), bits(agg_o))          # aggregated costs: bit-exact (>= the 1e-4 bar)
+    assert np.array_equal(disp, disp_o)                     # integer WTA disparities: bit-exact
+    assert np.array_equal(bits(best), bits(best_o))
+    np.testing.assert_allclose(agg, agg_o, rtol=1e-4)       # the tolerance north_star states, for the record
+    eng.close()
+
+
+@pytest.mark.parametrize("threads,cap", [(32, 1), (64, 2), (256, 4), (512, 64)])
+def test_dense_aggregation_config_independent(api, oracle, threads, cap):
+    W, H, D = 200, 120, 70   # two label chunks per lane, a partly filled second chunk
+    L, R, _ = make(W, H, 24, 9, 1)
+    F = oracle.forest(L)
+    lv, _ = oracle.cost_adgrad(L, R, D)
+    disp_o, best_o, _ = oracle.aggregate_dense(F, lv)
+    eng = api.Stereo3DMST(agg_threads=threads, agg_cache_nodes=cap)
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    eng.set_cost_volume(0, lv, ingest=False)
+    disp, best = eng.aggregate_dense(0)
+    assert np.array_equal(disp, disp_o) and np.array_equal(bits(best), bits(best_o))
+    eng.close()
+
+
+def test_dense_label_slices_and_ranges(api, oracle):
+    W, H, D = 120, 80, 200   # > 128 labels: several (tree, slice) units + the combine kernel
+    L, R, _ = make(W, H, 24, 13, 0)
+    F = oracle.forest(L, c=900.0, min_size=40)
+    lv, _ = oracle.cost_adgrad(L, R, D)
+    eng = api.Stereo3DMST(fh_c=900.0, min_cc_size=40)
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    eng.set_cost_volume(0, lv, ingest=False)
+    disp_o, best_o, _ = oracle.aggregate_dense(F, lv)
+    disp, best = eng.aggregate_dense(0)
+    assert np.array_equal(disp, disp_o) and np.array_equal(bits(best), bits(best_o))
+    # label-range sharding: min-loc over the shards == the full run (what the NCCL reduction computes)
+    parts = [eng.aggregate_dense(0, d0, d1) for d0, d1 in ((0, 50), (50, 100), (100, 151), (152, 200))]
+    po = [oracle.aggregate_dense(F, lv, d0, d1)[:2] for d0, d1 in ((0, 50), (50, 100), (100, 151), (152, 200))]
+    for (d, b), (do, bo) in zip(parts, po):
+        assert np.array_equal(d, do) and np.array_equal(bits(b), bits(bo))
+    eng.close()
+
+
+def test_pms_apply_matches_oracle(api, oracle):
+    W, H, D = 150, 90, 20
+    L, R, _ = make(W, H, D, 21, 0)
+    N = W * H
+    c, ms = 700.0, 30
+    F = oracle.forest(L, c=c, min_size=ms)
+    lv_raw, _ = oracle.cost_adgrad(L, R, D)
+    lv = oracle.ingest(lv_raw, 0.5, 0.0, 1 / 6.0)
+    rng = np.random.default_rng(4)
+    n = 40 * F.T + 77
+    trees = rng.integers(0, F.T, n).astype(np.int32)
+    labels = np.stack([rng.uniform(-0.05, 0.05, n), rng.uniform(-0.05, 0.05, n), rng.uniform(-3, D + 3, n)], 1).astype(np.float32)
+    labels[5] = (0, 0, 3.0)          # exactly-integer disparity: cost 0 (Q10)
+    labels[6] = (np.nan, 0, 3.0)     # NaN plane -> out-of-range cost
+    labels[7] = (0, 0, 1e12)
+    abc_o = oracle.plane_init(W, H, D)
+    mn_o = np.full(N, np.finfo(np.float64).max)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, cost_scale=1 / 6.0)
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    eng.build_forest(1)
+    eng.build_cost_volume(D, ingest=True)
+    assert np.array_equal(bits(eng.get_cost_volume(0)), bits(lv))
+    eng.set_labels(0, abc_o)
+    eng.reset_min_cost(0)
+    # two calls: state must carry over exactly like consecutive MST_PMS calls
+    h = n // 2
+    eng.pms_apply(0, trees[:h], labels[:h])
+    eng.pms_apply(0, trees[h:], labels[h:])
+    oracle.pms_apply(F, lv, D, trees, labels, mn_o, abc_o)
+    assert np.array_equal(bits(eng.get_min_cost(0)), bits(mn_o))
+    assert np.array_equal(bits(eng.get_labels(0)), bits(abc_o))
+    eng.label_to_disp(0)
+    want = oracle.label_to_disp(abc_o, W, H, D) * np.float32(D - 1.0)
+    assert np.array_equal(bits(eng.get_disparity(0)), bits(want))
+    eng.close()
+
+
+def test_pms_replays_recorded_reference_sequence(api, oracle):
+    """Injected-proposal parity (north star): record the proposal sequence of oracle MST_PMS iterations and
+    replay it on the GPU; labels and min costs must be identical."""
+    W, H, D = 120, 72, 14
+    L, R, _ = make(W, H, D, 31, 0)
+    N = W * H
+    c, ms = 600.0, 40
+    F = oracle.forest(L, c=c, min_size=ms)
+    lv = oracle.ingest(oracle.cost_adgrad(L, R, D)[0], 0.5, 0.0, 1 / 6.0)
+    abc_o = oracle.plane_init(W, H, D)
+    mn_o = np.full(N, np.finfo(np.float64).max)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, cost_scale=1 / 6.0)
+    eng.set_images(L, R)
+    eng.build_forest(0)
+    eng.build_forest(1)
+    eng.build_cost_volume(D, ingest=True)
+    eng.set_labels(0, abc_o)
+    eng.reset_min_cost(0)
+    g = oracle.rand_new(1)
+    for it in range(3):
+        n, rt, rl = oracle.mst_pms(F, lv, D, mn_o, abc_o, g, record_cap=64 * F.T)
+        eng.pms_apply(0, rt, rl)
+        assert np.array_equal(bits(eng.get_min_cost(0)), bits(mn_o)), it
+        assert np.array_equal(bits(eng.get_labels(0)), bits(abc_o)), it
+    eng.close()
+
+
+def test_golden_reference_proposals(api, oracle):
+    """tests/golden/ref_small.npz holds output of the reference's own code: replay its proposals on the GPU."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_small.npz"))
+    W, H, D = int(gold["W"]), int(gold["H"]), int(gold["D"])
+    N = W * H
+    for tag in ("a", "b"):
+        c, ms = gold[f"{tag}_params"]
+        eng = api.Stereo3DMST(fh_c=float(c), min_cc_size=int(ms))
+        eng.set_images(gold["left"], gold["right"])
+        eng.build_forest(0)
+        G = eng.get_forest(0)
+        assert np.array_equal(G["node_pixel"], gold[f"{tag}_node_pixel"])
+        assert np.array_equal(G["parent"], gold[f"{tag}_parent"])
+        assert np.array_equal(G["adj"], gold[f"{tag}_adj"])
+        eng.set_cost_volume(0, gold["lv_raw"], ingest=True)
+        eng.set_labels(0, gold[f"{tag}_abc"])
+        eng.reset_min_cost(0)
+        eng.pms_apply(0, gold[f"{tag}_prop_trees"], gold[f"{tag}_prop_labels"])
+        assert np.array_equal(bits(eng.get_min_cost(0)), bits(gold[f"{tag}_prop_min"]))
+        assert np.array_equal(bits(eng.get_labels(0)), bits(gold[f"{tag}_prop_abc"]))
+        eng.close()
+    eng = api.Stereo3DMST()
+    eng.set_images(gold["left"], gold["right"])
+    eng.build_forest(0)
+    eng.build_forest(1)
+    eng.build_cost_volume(D)
+    for fill, key in ((0, "lr_nofill"), (1, "lr_fill")):
+        eng.set_disparity(0, gold["lr_left"])
+        eng.set_disparity(1, gold["lr_right"])
+        eng.lr_check(fill=bool(fill))
+        assert np.array_equal(bits(eng.get_disparity(0)), bits(gold[key]))
+        assert np.array_equal(bits(eng.get_disparity(1)), bits(gold["lr_right"]))
+    eng.close()
+    del N
+
+
+@pytest.mark.parametrize("fill", [False, True])
+def test_lr_check_matches_oracle(api, oracle, fill):
+    rng = np.random.default_rng(8)
+    for (W, H, D) in ((97, 13, 16), (1300, 3, 60), (5, 4, 4)):
+        L, R, _ = make(W, H, 12, 1, 0)
+        eng = api.Stereo3DMST(min_cc_size=2, fh_c=10.0)
+        eng.set_images(L, R)
+        eng.build_forest(0)
+        eng.build_forest(1)
+        eng.build_cost_volume(D)
+        N = W * H
+        for trial in range(4):
+            left = rng.uniform(-2, D + 2, N).astype(np.float32)
+            right = (left + rng.normal(0, 1.0, N)).astype(np.float32)
+            if trial == 1:
+                left = np.round(left)
+            if trial == 2:
+                left[:] = 1e30      # everything invalid
+            if trial == 3:
+                right = left.copy()  # mostly valid
+                left[::7] = np.nan
+            eng.set_disparity(0, left)
+            eng.set_disparity(1, right)
+            eng.lr_check(fill=fill)
+            want, _ = oracle.lr_check(left, right, W, H, D, fill)
+            assert np.array_equal(bits(eng.get_disparity(0)), bits(want)), (W, H, trial)
+        eng.close()
+
+
+def test_run_dense_end_to_end(api, oracle):
+    W, H, D = 256, 160, 48
+    L, R, gt = make(W, H, D, 77, 0)
+    eng = api.Stereo3DMST()
+    eng.set_images(L, R)
+    dl, dr = eng.run_dense(D, fill=True)
+    n0 = eng.launch_count()
+    assert n0 > 0
+    lv, rv = oracle.cost_adgrad(L, R, D)
+    FL, FR = oracle.forest(L), oracle.forest(R)
+    dlo = oracle.aggregate_dense(FL, lv)[0].astype(np.float32)
+    dro = oracle.aggregate_dense(FR, rv)[0].astype(np.float32)
+    want, _ = oracle.lr_check(dlo, dro, W, H, D, True)
+    assert np.array_equal(bits(dl), bits(want))
+    assert np.array_equal(bits(dr), bits(dro))
+    # and it is a usable disparity map: most pixels within 1 px of the ground truth
+    err = np.abs(dl.reshape(H, W) - gt)
+    assert (err[:, D:] <= 1.0).mean() > 0.8
+    # second run on the same context: idempotent
+    dl2, dr2 = eng.run_dense(D, fill=True)
+    assert np.array_equal(bits(dl), bits(dl2)) and np.array_equal(bits(dr), bits(dr2))
+    eng.close()
+
+
+def test_reference_signature_wrapper(api, oracle):
+    W, H, D = 128, 80, 24
+    L, R, _ = make(W, H, D, 5, 0)
+    outl = np.zeros((H, W), np.float32)
+    outr = np.zeros((H, W), np.float32)
+    dl, dr = api.stereo3dmst("img1r.png", "img2r.png", L, R, outl, outr, "ADGRAD", D)
+    assert np.array_equal(dl, outl) and np.array_equal(dr, outr)
+    with pytest.raises(ValueError):
+        api.stereo3dmst("a", "b", L, R, None, None, "nope", D)
+    lv, rv = oracle.cost_adgrad(L, R, D)
+    dl2, _ = api.stereo3dmst("a", "b", L, R, None, None, "MCCNN_acrt", D, left_volume=lv, right_volume=rv)
+    # external-volume path applies the reference ingest (cap 0.5) first
+    FL, FR = oracle.forest(L), oracle.forest(R)
+    dlo = oracle.aggregate_dense(FL, oracle.ingest(lv))[0].astype(np.float32)
+    dro = oracle.aggregate_dense(FR, oracle.ingest(rv))[0].astype(np.float32)
+    want, _ = oracle.lr_check(dlo, dro, W, H, D, False)
+    assert np.array_equal(bits(dl2.ravel()), bits(want))
+
+
+def test_full_size_c2_properties(api, oracle):
+    """BASELINE config 2 at full size (1280x720, D=128): forest identical to the oracle, dense result
+    identical on both views, plus size-independent properties."""
+    W, H, D = 1280, 720, 128
+    L, R, gt = synth.make_pair(W, H, D)
+    eng = api.Stereo3DMST()
+    eng.set_images(L, R)
+    dl, dr = eng.run_dense(D, fill=False)
+    G = eng.get_forest(0)
+    from oracle.pyoracle import Oracle
+    fast = Oracle(fast=True)
+    F = fast.forest(L)
+    assert np.array_equal(G["mask"], F.mask) and np.array_equal(G["node_pixel"], F.node_pixel) and np.array_equal(G["parent"], F.parent)
+    assert int((G["mask"] > 0).sum()) == W * H - G["T"]                  # forest edge count = N - T
+    assert np.diff(G["tree_start"]).min() >= 200                         # every tree >= min size
+    lv = eng.get_cost_volume(0)
+    disp_o, best_o, _ = fast.aggregate_dense(F, lv)
+    disp, best = eng.aggregate_dense(0)
+    assert np.array_equal(disp, disp_o) and np.array_equal(bits(best), bits(best_o))
+    # linearity of the tree filter: scaling the volume by 2 scales the aggregated minimum by exactly 2
+    eng.set_cost_volume(0, lv * np.float32(2.0), ingest=False)
+    disp2, best2 = eng.aggregate_dense(0)
+    assert np.array_equal(disp2, disp) and np.array_equal(bits(best2), bits(best * 2.0))
+    # constant volume: every label ties, lowest d wins everywhere
+    eng.set_cost_volume(0, np.full((8, W * H), 0.25, np.float32), ingest=False)
+    dconst, _ = eng.aggregate_dense(0)
+    assert not dconst.any()
+    err = np.abs(dl.reshape(H, W) - gt)
+    valid = dl.reshape(H, W) > 0
+    assert valid.mean() > 0.5 and (err[valid] <= 1.0).mean() > 0.9
+    eng.close()
