@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the Stereo3DMST hot path (dense-label pipeline) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[1], "C2"): synthetic random-dot slanted-plane pair 1280x720, 128 disparities.
+One step = one full pass of the hot path over one stereo pair per GPU: median + edge weights + FH forest + min-size
+merge + BFS re-indexing (both views), truncated colour+gradient cost volume (both views), two-pass tree-filter
+aggregation + WTA (both views), left-right check + scan-line fill.  Frames are independent, so N GPUs process N
+different pairs per step with no collective ("weak" scaling).  Metric: Mpix*disparities/s = N*W*H*D / t_step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, D = 1280, 720, 128
+WORKLOAD = "C2 synthetic random-dot slanted-plane pair 1280x720, D=128, dense 3DMST pipeline (forest+cost+tree-filter+WTA+LR/fill, both views)"
+METRIC = "Mpix*disparities/s"
+ALG_BYTES_PER_PXLABEL = 12.0  # read cost 4 + write A_up 4 + read A_up 4 (fp32 model; exact mode moves 20)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU legs
+def _cpu_sample(args):
+    """Bounded sample of the same workload on one host core: a crop of the C2 pair, all D labels, full pipeline."""
+    seed, cw, ch = args
+    from oracle.pyoracle import Oracle
+    from stereomatch_b200 import synth
+    O = Oracle(fast=True)
+    L, R, _ = synth.make_pair(W, H, D, seed=seed)
+    L = np.ascontiguousarray(L[:ch, :cw]); R = np.ascontiguousarray(R[:ch, :cw])
+    t0 = time.perf_counter()
+    lv, rv = O.cost_adgrad(L, R, D)
+    FL, FR = O.forest(L), O.forest(R)
+    dl = O.aggregate_dense(FL, lv)[0].astype(np.float32)
+    dr = O.aggregate_dense(FR, rv)[0].astype(np.float32)
+    O.lr_check(dl, dr, cw, ch, D, True)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_serial(cw=W, ch=H):
+    from stereomatch_b200 import synth
+    dt = _cpu_sample((synth.BASE_SEED, cw, ch))
+    return {"value": cw * ch * D / dt / 1e6, "unit": METRIC, "cores": 1, "kind": "port",
+            "sample": f"the whole C2 pair ({cw}x{ch}, all {D} labels), full dense pipeline both views, oracle -O3 serial, {dt:.2f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (oracle port; the reference itself needs OpenCV/Boost/mc-cnn and cannot
+    run on the GPU box) on all host cores, one bounded sample per core per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from stereomatch_b200 import synth
+    cores = os.cpu_count() or 1
+    cw, ch = 320, 180
+    jobs = [(synth.BASE_SEED + i, cw, ch) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_cpu_sample, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_sample, jobs)
+        dt = time.perf_counter() - t0
+    value = cores * cw * ch * D * args.steps / dt / 1e6
+    sample = f"{cores} x ({cw}x{ch} crop of a C2 pair, all {D} labels, full dense pipeline both views) per step, one per core"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------- GPU leg
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from stereomatch_b200 import api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    eng = api.Stereo3DMST(device=local, stream=stream.cuda_stream, agg_threads=args.agg_threads, agg_cache_nodes=args.agg_cache)
+
+    L, R, gt = synth.make_pair(W, H, D, seed=synth.BASE_SEED + rank)   # one different frame per rank
+    # pinned host staging for the e2e leg
+    hl = torch.from_numpy(L.copy()).pin_memory(); hr = torch.from_numpy(R.copy()).pin_memory()
+    eng.set_images(hl.numpy(), hr.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for _ in range(max(3, args.warmup)):
+        eng.run_dense(D, fill=True, fetch=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    agg_ms = 0.0
+    stage_tot = np.zeros(4)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.run_dense(D, fill=True, fetch=False)
+        # stage events are read back after the step is enqueued; the host-side sync inside run_dense's forest
+        # stage (tree order metadata) already serialises steps, so this adds no device idle time
+        for s in range(4):
+            stage_tot[s] += eng.stage_ms(s)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    agg_ms = stage_tot[api.T_AGG]
+    value = world * W * H * D * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the public call with host buffers (H2D + pipeline + D2H inside the timed region)
+    out_l = torch.empty(W * H, dtype=torch.float32).pin_memory(); out_r = torch.empty(W * H, dtype=torch.float32).pin_memory()
+    import ctypes as C
+
+    def e2e_step():
+        eng.set_images(hl.numpy(), hr.numpy())
+        eng._ck(eng.L.s3dmst_run_dense(eng.h, D, 1, C.c_void_p(out_l.data_ptr()), C.c_void_p(out_r.data_ptr())))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * W * H * D * args.steps / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        n_agg_launch = 2 * args.steps                      # one aggregation kernel per view per step
+        per_launch_ms = agg_ms / n_agg_launch
+        achieved = ALG_BYTES_PER_PXLABEL * W * H * D / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_agg_dense_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = cpu_baseline_serial() if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded x{world}, no collective",
+                       "l2": "working set per step (2.8 GB of cost + running sums) exceeds the 126 MB L2; no explicit flush",
+                       "mode": "exact (fp64, reference association order)"},
+            "stage_ms_per_step": {k: float(stage_tot[i] / args.steps) for i, k in enumerate(("forest", "cost", "aggregate", "post"))},
+            "roofline": {"bound": "hbm", "kernel": "k_agg_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PXLABEL * W * H * D,
+                         "fp64_traffic_model_gbs": 20.0 * W * H * D / (per_launch_ms * 1e-3) / 1e9},
+            "e2e": {"value": e2e_value, "unit": METRIC, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 2 * W * H * 3, "d2h_bytes_per_step": 2 * W * H * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--agg-threads", type=int, default=0)
+    ap.add_argument("--agg-cache", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

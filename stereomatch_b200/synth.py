@@ -27,6 +27,8 @@ def make_pair(W: int, H: int, D: int, seed: int = BASE_SEED):
             y0, y1 = gy * H // 2, (gy + 1) * H // 2
             x0, x1 = gx * W // 3, (gx + 1) * W // 3
             a, b = rng.uniform(-0.02, 0.02, size=2)
+            if y1 <= y0 or x1 <= x0:
+                continue
             xx, yy = xs[y0:y1, x0:x1], ys[y0:y1, x0:x1]
             slope = a * (xx - x0) + b * (yy - y0)
             smin, smax = float(slope.min()), float(slope.max())
