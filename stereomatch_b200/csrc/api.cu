@@ -42,7 +42,7 @@ static void free_view(View& V) {
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
     DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
-    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up);
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn);
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
@@ -64,7 +64,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     S3_CUDA(dalloc(&V.tree_size, n)); S3_CUDA(dalloc(&V.tree_rootpix, n));
     S3_CUDA(dalloc(&V.tree_start, n + 1)); S3_CUDA(dalloc(&V.tree_depth, n)); S3_CUDA(dalloc(&V.unit_tree, n));
     S3_CUDA(dalloc(&V.node_pixel, n)); S3_CUDA(dalloc(&V.pixel_node, n)); S3_CUDA(dalloc(&V.parent, n));
-    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n));
+    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n));
     S3_CUDA(dalloc(&V.lvl_start, 2 * n + 2));
     S3_CUDA(dalloc(&V.disp_i, n)); S3_CUDA(dalloc(&V.best, n)); S3_CUDA(dalloc(&V.abc, 3 * n)); S3_CUDA(dalloc(&V.min_cost, n));
     S3_CUDA(dalloc(&V.disp_f, n)); S3_CUDA(dalloc(&V.lr_mask, n));
@@ -97,6 +97,8 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->keep_aggregated = 0;
     p->agg_threads = 0;
     p->agg_cache_nodes = 0;
+    p->agg_ring_nodes = 0;
+    p->agg_kernel = 0;
 }
 
 int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream) {
@@ -155,7 +157,7 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
-    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch);
+    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev);
     for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
         if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -341,6 +343,9 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.parent, parent, sizeof(int) * N);
     H2D(V.pw, parent_weight, sizeof(uint16_t) * N);
     H2D(V.node_up, nu.data(), sizeof(NodeUp) * N);
+    std::vector<int4> nd(N);
+    for (int i = 0; i < N; i++) nd[i] = make_int4(parent[i], parent_weight[i], level[i], node_pixel[i]);
+    H2D(V.node_dn, nd.data(), sizeof(int4) * N);
     H2D(V.level, level.data(), sizeof(int) * N);
     H2D(V.pixel_node, pixel_node.data(), sizeof(int) * N);
     H2D(V.tree_id, tree_id.data(), sizeof(int) * N);
@@ -393,7 +398,10 @@ int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol) {
 int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* disp, double* best_cost) {
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     S3_CUDA(cudaSetDevice(ctx->device));
-    S3_TRY(s3_aggregate_dense(ctx, view, d0, d1));
+    if (ctx->P.agg_kernel == 1 || (d0 & 3))
+        S3_TRY(s3_aggregate_dense(ctx, view, d0, d1));
+    else
+        S3_TRY(s3_aggregate_dense2(ctx, 1 << view, d0, d1));
     View& V = ctx->v[view];
     D2H(disp, V.disp_i, sizeof(int32_t) * ctx->N);
     D2H(best_cost, V.best, sizeof(double) * ctx->N);
@@ -495,10 +503,12 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     S3_TRY(s3dmst_build_forest(ctx, 0));
     S3_TRY(s3dmst_build_forest(ctx, 1));
     S3_TRY(s3_cost_adgrad(ctx, D, 0));
-    for (int view = 0; view < 2; view++) {
-        S3_TRY(s3_aggregate_dense(ctx, view, 0, D));
-        S3_TRY(s3_dense_to_disp(ctx, view));
+    if (ctx->P.agg_kernel == 1) {
+        for (int view = 0; view < 2; view++) S3_TRY(s3_aggregate_dense(ctx, view, 0, D));
+    } else {
+        S3_TRY(s3_aggregate_dense2(ctx, 3, 0, D));  // both views' trees in one launch
     }
+    for (int view = 0; view < 2; view++) S3_TRY(s3_dense_to_disp(ctx, view));
     S3_TRY(s3_lr_check(ctx, fill));
     D2H(left_disp, ctx->v[0].disp_f, sizeof(float) * ctx->N);
     D2H(right_disp, ctx->v[1].disp_f, sizeof(float) * ctx->N);

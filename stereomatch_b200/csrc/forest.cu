@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(int T, int W, int H, const 
                                                      const int* __restrict__ tree_rootpix,
                                                      const uint16_t* __restrict__ ew, const uint8_t* __restrict__ mask,
                                                      int* node_pixel, int* pixel_node, int* parent, int* level,
-                                                     uint16_t* pw, NodeUp* node_up, int* lvl_start, int* tree_depth) {
+                                                     uint16_t* pw, NodeUp* node_up, int4* node_dn, int* lvl_start, int* tree_depth) {
     __shared__ int s_warp[BFS_THREADS / 32];
     __shared__ int s_total;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(int T, int W, int H, const 
             parent[base] = base;
             level[base] = 0;
             pw[base] = 0;
+            node_dn[base] = make_int4(base, 0, 0, rp);
             lvl[0] = base;
         }
         __syncthreads();
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(int T, int W, int H, const 
                         parent[h] = g;
                         level[h] = L + 1;
                         pw[h] = (uint16_t)wq[k];
+                        node_dn[h] = make_int4(g, (int)wq[k], L + 1, q[k]);
                     }
                 }
                 run += chunk_total;
@@ -472,7 +474,7 @@ int s3_forest_stage(s3dmst_ctx* ctx, int view) {
         const int grid = std::min(T, ctx->num_sms * 8);
         k_bfs<<<grid, BFS_THREADS, 0, ctx->stream>>>(T, W, H, V.unit_tree, V.tree_start, V.tree_rootpix, V.ew, V.mask,
                                                       V.node_pixel, V.pixel_node, V.parent, V.level, V.pw, V.node_up,
-                                                      V.lvl_start, V.tree_depth);
+                                                      V.node_dn, V.lvl_start, V.tree_depth);
         S3_LAUNCH_CHECK();
     }
     return s3_forest_finalize_host(ctx, view);

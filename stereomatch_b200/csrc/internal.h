@@ -58,6 +58,7 @@ struct View {
     int* level = nullptr;       // [N]
     uint16_t* pw = nullptr;     // [N]
     NodeUp* node_up = nullptr;  // [N]
+    int4* node_dn = nullptr;    // [N] {parent, parent weight, level, pixel}: the root->leaf pass record
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
     // tree adjacency (host side, built lazily for dumps / proposal generation)
     std::vector<int> h_tree_start, h_tree_depth, h_unit_tree;
@@ -99,6 +100,8 @@ struct s3dmst_ctx {
     long long launches = 0;
     std::string err;
     // scratch for PMS
+    uint32_t* units_dev = nullptr;  // aggregation work units (view<<31 | tree), longest first
+    size_t units_cap = 0;
     void* pms_scratch = nullptr;
     size_t pms_scratch_cap = 0;
 };
@@ -139,7 +142,8 @@ int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);           // forest.cu: 
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
-int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu
+int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
+int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined)
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
 int s3_label_to_disp(s3dmst_ctx* ctx, int view);                  // post.cu
 int s3_dense_to_disp(s3dmst_ctx* ctx, int view);
