@@ -1,22 +1,26 @@
-// stereomatch_b200/csrc/aggregate2.cu — tree-filter aggregation + WTA, TMA-pipelined version (the default).
+// stereomatch_b200/csrc/aggregate2.cu — tree-filter aggregation + WTA, bulk-copy (TMA) pipelined kernel (default).
 //
 // Same arithmetic, layout and work decomposition as aggregate.cu (see the header there): one CTA per
 // (tree, label slice), level-synchronous walk, FP64 in the reference's association order
-// (src/Stereo3DMST.cpp:120-158, :173-185).  What changes is how bytes reach the math.  The v1 kernel is
-// bound by its critical path: every level pays a chain of dependent global loads (level offsets -> node
-// record -> child rows), ~3.8 us per level on B200, i.e. 11 ms for a 1400-level tree while the HBM time
-// of the whole volume is 0.4 ms.  Here
-//   * one extra "DMA" warp per CTA walks the tree AHEAD of the math warps and stages, per node, the node
-//     record (16 B) and its cost row (up pass) / running-sum row (down pass) into a shared-memory ring with
-//     cp.async.bulk (TMA bulk copies, mbarrier complete_tx); BFS order makes every tile a contiguous node
-//     range, so the addresses are known without touching the data;
-//   * the DMA warp joins the per-tile named barrier only after the next tile's bytes have landed, so the
-//     math warps never wait on an mbarrier or on global memory on the critical path: per level it is
-//     LDS(node record) -> LDS(children / parent values) -> FP64 chain -> STS -> BAR;
-//   * both views' trees are scheduled in ONE launch (longest trees first), so the two deepest trees'
-//     critical paths overlap.
-// Ring entries are per node, tiles take consecutive entries, so narrow levels let the DMA warp run many
-// levels ahead (prefetch distance is bounded by bytes, not by level count).
+// (src/Stereo3DMST.cpp:120-158, :173-185).  What changes is how bytes reach the math.
+//
+// The simple kernel is bound by its critical path: per tree level a chain of dependent global loads
+// (level offsets -> node record -> child rows), ~3.8 us per level on B200, i.e. 11 ms for a 1400-level tree
+// while the HBM time of the whole volume is 0.4 ms.  Measured facts that shaped this version (ncu source
+// view + clock64 counters, profiles/r01_*): a single warp retires a dependent instruction every ~5-10
+// cycles, so what matters is the NUMBER of instructions every warp executes between two level barriers.
+//   * The tile sequence (<= 16 consecutive nodes of one level per tile) is precomputed at forest-build time
+//     as 32-byte descriptors in both traversal orders; a 64-entry descriptor ring in shared memory is kept
+//     filled by bulk copies, so no warp walks level tables or touches global memory to find its work.
+//   * One "DMA" warp stages, per tile, the node records and the cost rows (up pass) / running-sum rows (down
+//     pass) into a shared-memory ring with ONE cp.async.bulk (TMA, UBLKCP) each — BFS order makes a tile a
+//     contiguous byte range — and arrives at the tile barrier only when the NEXT tile has landed
+//     (mbarrier complete_tx).
+//   * 16 math warps, one node per warp per tile, software pipelined: right after barrier k they issue the
+//     shared-memory loads of the children/parent values of tile k, then pre-load everything of tile k+1
+//     that does not depend on tile k (descriptor, node record, weights, cost, w2*A_up), then run the short
+//     FP64 chain of tile k.  A warp without a node in the tile does ~10 instructions.
+//   * Both views' trees are scheduled in one launch, longest first.
 #include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,17 +32,23 @@
 #include "hd_math.h"
 #include "internal.h"
 
-#define A2_MAXT 16           // tiles in flight (header + mbarrier slots)
-#define A2_FLAG_LEVEL_END 1
-#define A2_FLAG_LAST 2
+#ifndef A2_INSTRUMENT
+#define A2_INSTRUMENT 0  // 1: clock64 counters of CTA 0 (S3_DEBUG_AGG=1 prints them); costs registers
+#endif
+#if A2_INSTRUMENT
+#define A2_CLK() clock64()
+#else
+#define A2_CLK() 0ll
+#endif
+#define A2_MAXT 16  // tiles in flight (mbarrier slots)
+#define A2_DR 64    // descriptor ring entries: two halves of 32
 
 struct Agg2View {
     const int* tree_start;
-    const int* tree_depth;
-    const int* lvl_start;
+    const int* tree_ntiles;
+    const int4* tile_desc;
     const NodeUp* node_up;
     const int4* node_dn;
-    const int* node_pixel;
     const float* cost;
     double* aup;
     int32_t* disp;  // pixel order when n_slices == 1, else [slice][node] partials
@@ -51,19 +61,19 @@ struct Agg2Args {
     int n_slices, Dp, d0, d1, N;
     const double* lut_w;
     const double* lut_w2;
-    int cap, rn, tn, keep;
+    int cap, rn, keep, use_tma;
     long long* dbg;  // optional cycle counters of CTA 0 (development aid)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
@@ -72,31 +82,53 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.b32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 26)) __trap();  // never hang the GPU: a lost copy becomes an error
 }
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_d2(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
 
 // total order on doubles as unsigned 64-bit keys (handles negative costs of the mc-cnn "fast" volumes)
 __device__ __forceinline__ unsigned long long dkey(double x) {
@@ -108,147 +140,173 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-struct TileHdr {  // 32 bytes
-    int t0, n, ent0, loff;
-    int aux, flags, pad0, pad1;
-};
+// descriptor ring slot of tile k of a pass whose first chunk has global chunk number gbase
+__device__ __forceinline__ uint32_t desc_addr(uint32_t s_desc, int gbase, int k) {
+    return s_desc + (uint32_t)(((((gbase + (k >> 5)) & 1) << 5) | (k & 31)) * 32);
+}
 
 template <int HV>
-__global__ void __launch_bounds__(1024, 1) k_agg_dense2(Agg2Args A) {
+__global__ void __launch_bounds__(32 * (S3_TILE_NODES + 1), 1) k_agg_dense2(Agg2Args A) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NW = (blockDim.x >> 5) - 1;  // math warps; warp NW is the DMA warp
-    const int nall = blockDim.x;
-    const int cap = A.cap, RN = A.rn, TN = A.tn;
+    constexpr int NW = S3_TILE_NODES;  // math warps == nodes per tile; warp NW is the DMA warp
+    constexpr int NALL = 32 * (NW + 1);
     constexpr int SW = 64 * HV;
-    constexpr int ROWB = SW * 8;  // ring row stride in bytes (down-pass rows are doubles)
-
-    // ---- shared memory carve-up (mirrored by agg2_smem_bytes on the host)
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_raw);                       // [A2_MAXT]
-    TileHdr* s_hdr = reinterpret_cast<TileHdr*>(s_raw + 128);                    // [A2_MAXT]
-    unsigned char* s_meta = s_raw + 128 + A2_MAXT * 32;                          // [RN][16]
-    unsigned char* s_rows = s_meta + (size_t)RN * 16;                            // [RN][ROWB]
-    double2* s_lvl = reinterpret_cast<double2*>(s_rows + (size_t)RN * ROWB);     // [2][cap][HV][32]
-    double* s_w = reinterpret_cast<double*>(s_lvl + 2 * (size_t)cap * HV * 32);  // [S3_NUM_W] exp(-w*gamma)
-    double* s_w2 = s_w + S3_NUM_W;                                               // [S3_NUM_W] 1 - w*w
+    constexpr int ROWL = HV * 512;  // bytes of one node in the level hand-over buffers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = A.cap, RN = A.rn;
 
     const uint32_t unit_code = A.units[blockIdx.x / A.n_slices];
     const int slice = blockIdx.x % A.n_slices;
     const Agg2View& V = A.v[unit_code >> 31];
     const int t = (int)(unit_code & 0x7fffffffu);
-    const int base = V.tree_start[t];
-    const int* lvl = V.lvl_start + base + t;
-    const int depth = V.tree_depth[t];
-    const int lab0 = A.d0 + slice * SW;                     // first label of this slice (multiple of 4)
-    const int seg = min(SW, A.Dp - lab0);                   // labels copied per row (multiple of 4)
+    const int tbase = V.tree_start[t];   // node offset == tile index offset of the tree
+    const int NT = V.tree_ntiles[t];
+    const int nch = (NT + 31) >> 5;      // descriptor chunks per pass
+    const int lab0 = A.d0 + slice * SW;  // first label of this slice (multiple of 4)
+    const int seg = min(SW, A.Dp - lab0);  // labels staged per row (multiple of 4)
     const size_t Dp = A.Dp;
-    const bool contig = seg == A.Dp;  // the slice covers whole rows: a tile's rows are one contiguous range
+    const bool contig = seg == A.Dp;  // slice covers whole rows: a tile's rows are one byte range
+    const uint32_t rowb_up = (uint32_t)seg * 4u, rowb_dn = (uint32_t)seg * 8u;
 
-    for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
-        s_w[i] = A.lut_w[i];
-        s_w2[i] = A.lut_w2[i];
+    // ---- shared memory carve-up (mirrored by agg2_smem_bytes on the host)
+    const uint32_t s_base = smem_u32(s_raw);
+    const uint32_t s_full = s_base;                                     // [A2_MAXT] tile mbarriers
+    const uint32_t s_dfull = s_base + 128;                              // [2] descriptor-half mbarriers
+    const uint32_t s_desc = s_base + 256;                               // [A2_DR][32]
+    const uint32_t s_meta = s_desc + A2_DR * 32;                        // [RN][16]
+    const uint32_t s_rows = s_meta + (uint32_t)RN * 16u;                // [RN][SW*8]
+    const uint32_t s_lvl = s_rows + (uint32_t)RN * (uint32_t)(SW * 8);  // [2][cap][ROWL]
+    const uint32_t s_w = s_lvl + 2u * (uint32_t)cap * ROWL;             // [S3_NUM_W] exp(-w*gamma)
+    const uint32_t s_w2 = s_w + S3_NUM_W * 8u;                          // [S3_NUM_W] 1 - w*w
+    {
+        double* gw = reinterpret_cast<double*>(s_raw + (s_w - s_base));
+        for (int i = tid; i < S3_NUM_W; i += NALL) {
+            gw[i] = A.lut_w[i];
+            gw[S3_NUM_W + i] = A.lut_w2[i];
+        }
     }
     if (tid == 0) {
-        for (int i = 0; i < A2_MAXT; i++) mbar_init(s_full + i, contig ? 1 : 33);
+        for (int i = 0; i < A2_MAXT; i++) mbar_init(s_full + 8 * i, A.use_tma ? (contig ? 1 : 33) : 32);
+        mbar_init(s_dfull, 1);
+        mbar_init(s_dfull + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == NW) {
         // =========================================================== DMA warp
-        int q = 0, iq = 0;  // consumed / issued tile counters (continue across the two passes: mbarrier parity)
         long long t_issue = 0, t_wait = 0, t_bar = 0, n_tiles = 0;
         for (int pass = 0; pass < 2; pass++) {
-            int inflight = 0, ent_next = 0, n_prev = 0;
-            const int qbase = q;
-            // issue-side iterator
-            int L = pass == 0 ? depth - 1 : 0, off = 0;
-            int ls = __ldg(lvl + L), le = __ldg(lvl + L + 1);
-            int ps = 0;  // parent level start (down pass)
-            bool it_done = false;
-            const uint32_t rowbytes = (uint32_t)seg * (pass == 0 ? 4u : 8u);
+            const int gbase = pass * nch;  // global chunk number of this pass's first descriptor chunk
+            const int qbase = pass * NT;   // global tile number of this pass's first tile
+            const int4* dsrc = V.tile_desc + 2 * ((size_t)(pass == 0 ? A.N : 0) + (size_t)tbase);
+            const uint32_t rowbytes = pass == 0 ? rowb_up : rowb_dn;
+            const size_t gstride = Dp * (pass == 0 ? 4 : 8);
+            const unsigned char* mbase = pass == 0 ? reinterpret_cast<const unsigned char*>(V.node_up)
+                                                   : reinterpret_cast<const unsigned char*>(V.node_dn);
+            const unsigned char* rbase = pass == 0 ? reinterpret_cast<const unsigned char*>(V.cost + lab0)
+                                                   : reinterpret_cast<const unsigned char*>(V.aup + lab0);
+            auto load_chunk = [&](int c) {
+                if (lane == 0) {
+                    const int g = gbase + c;
+                    const uint32_t bar = s_dfull + 8u * (uint32_t)(g & 1);
+                    const uint32_t bytes = (uint32_t)min(32, NT - 32 * c) * 32u;
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(s_desc + (uint32_t)(g & 1) * 1024u, dsrc + 64 * (size_t)c, bytes, bar);
+                }
+            };
+            load_chunk(0);
+            if (nch > 1) load_chunk(1);
+            int k = 0, ik = 0, inflight = 0, ent = 0;
             auto try_issue = [&]() {
-                while (!it_done && iq - q < A2_MAXT) {
-                    const int t0 = ls + off;
-                    const int n = min(TN, le - t0);
-                    // a tile takes consecutive ring entries and never wraps (so it is ONE contiguous copy);
-                    // entries skipped at the end of the ring stay accounted to the tile until it is released
-                    int ent0 = ent_next, skip = 0;
-                    if (ent0 + n > RN) { skip = RN - ent0; ent0 = 0; }
-                    if (inflight + skip + n > RN) break;
-                    const bool level_end = t0 + n >= le;
-                    const bool last = level_end && (pass == 0 ? L == 0 : L == depth - 1);
-                    const int slot = iq % A2_MAXT;
-                    const unsigned char* msrc = pass == 0 ? reinterpret_cast<const unsigned char*>(V.node_up + t0)
-                                                          : reinterpret_cast<const unsigned char*>(V.node_dn + t0);
-                    const unsigned char* rsrc = pass == 0
-                        ? reinterpret_cast<const unsigned char*>(V.cost + (size_t)t0 * Dp + lab0)
-                        : reinterpret_cast<const unsigned char*>(V.aup + (size_t)t0 * Dp + lab0);
-                    if (lane == 0) {
-                        TileHdr h;
-                        h.t0 = t0; h.n = n; h.ent0 = ent0; h.loff = off;
-                        h.aux = pass == 0 ? le : ps;
-                        h.flags = (level_end ? A2_FLAG_LEVEL_END : 0) | (last ? A2_FLAG_LAST : 0);
-                        h.pad0 = skip + n; h.pad1 = 0;
-                        s_hdr[slot] = h;
-                        // TMA bulk copies: the tile's node records, and (rows contiguous) all its rows at once
-                        mbar_expect_tx(s_full + slot, (uint32_t)n * 16u + (contig ? (uint32_t)n * rowbytes : 0u));
-                        bulk_g2s(s_meta + (size_t)ent0 * 16, msrc, (uint32_t)n * 16u, s_full + slot);
-                        if (contig) bulk_g2s(s_rows + (size_t)ent0 * rowbytes, rsrc, (uint32_t)n * rowbytes, s_full + slot);
+                while (ik < NT && ik - k < A2_MAXT) {
+                    if ((ik & 31) == 0) {  // first use of a descriptor chunk: wait until it has landed
+                        const int g = gbase + (ik >> 5);
+                        mbar_wait(s_dfull + 8u * (uint32_t)(g & 1), (uint32_t)((g >> 1) & 1));
+                    }
+                    const int4 dA = lds_i4(desc_addr(s_desc, gbase, ik));  // {t0, n, loff, flags}
+                    const int n = dA.y;
+                    if (inflight + n > RN) break;
+                    const int t0 = dA.x, ent0 = ent;
+                    const int qg = qbase + ik;
+                    const uint32_t bar = s_full + 8u * (uint32_t)(qg % A2_MAXT);
+                    const unsigned char* msrc = mbase + (size_t)t0 * 16;
+                    const unsigned char* rsrc = rbase + (size_t)t0 * gstride;
+                    const int n1 = min(n, RN - ent0);  // entries before the ring wraps
+                    if (A.use_tma) {
+                        if (lane == 0) {
+                            mbar_expect_tx(bar, (uint32_t)n * 16u + (contig ? (uint32_t)n * rowbytes : 0u));
+                            bulk_g2s(s_meta + (uint32_t)ent0 * 16u, msrc, (uint32_t)n1 * 16u, bar);
+                            if (contig) bulk_g2s(s_rows + (uint32_t)ent0 * rowbytes, rsrc, (uint32_t)n1 * rowbytes, bar);
+                            if (n1 < n) {
+                                bulk_g2s(s_meta, msrc + (size_t)n1 * 16, (uint32_t)(n - n1) * 16u, bar);
+                                if (contig) bulk_g2s(s_rows, rsrc + (size_t)n1 * gstride, (uint32_t)(n - n1) * rowbytes, bar);
+                            }
+                        }
+                    } else {
+                        // LDGSTS path: 16-byte cp.async chunks, 32 lanes wide; a tile is one byte range (two if the ring wraps)
+                        if (lane < n) {
+                            int e = ent0 + lane;
+                            if (e >= RN) e -= RN;
+                            cp_async16(s_meta + (uint32_t)e * 16u, msrc + (size_t)lane * 16);
+                        }
+                        if (contig) {
+                            const uint32_t b1 = (uint32_t)n1 * rowbytes, b2 = (uint32_t)(n - n1) * rowbytes;
+                            for (uint32_t o = (uint32_t)lane * 16u; o < b1; o += 512u)
+                                cp_async16(s_rows + (uint32_t)ent0 * rowbytes + o, rsrc + o);
+                            for (uint32_t o = (uint32_t)lane * 16u; o < b2; o += 512u)
+                                cp_async16(s_rows + o, rsrc + (size_t)b1 + o);
+                        }
                     }
                     if (!contig) {
                         // label-sliced rows are strided in HBM: 16-byte cp.async chunks, one node per iteration
                         const int cpr = (int)(rowbytes >> 4);
-                        const size_t rstride = Dp * (pass == 0 ? 4 : 8);
-                        for (int i = 0; i < n; i++)
-                            for (int k = lane; k < cpr; k += 32)
-                                cp_async16(s_rows + (size_t)(ent0 + i) * rowbytes + (size_t)k * 16, rsrc + (size_t)i * rstride + (size_t)k * 16);
-                        cp_async_arrive_noinc(s_full + slot);
-                    }
-                    __syncwarp();
-                    ent_next = ent0 + n;
-                    if (ent_next >= RN) ent_next = 0;
-                    inflight += skip + n;
-                    iq++;
-                    // advance
-                    if (level_end) {
-                        if (last) {
-                            it_done = true;
-                        } else if (pass == 0) {
-                            L--; le = ls; ls = __ldg(lvl + L); off = 0;
-                        } else {
-                            L++; ps = ls; ls = le; le = __ldg(lvl + L + 1); off = 0;
+                        for (int i = 0; i < n; i++) {
+                            int e = ent0 + i;
+                            if (e >= RN) e -= RN;
+                            for (int c = lane; c < cpr; c += 32)
+                                cp_async16(s_rows + (uint32_t)e * rowbytes + (uint32_t)c * 16u, rsrc + (size_t)i * gstride + (size_t)c * 16);
                         }
-                    } else
-                        off += n;
+                    }
+                    if (!contig || !A.use_tma) cp_async_arrive_noinc(bar);
+                    ent = ent0 + n;
+                    if (ent >= RN) ent -= RN;
+                    inflight += n;
+                    ik++;
                 }
             };
-            long long c0 = clock64();
+            long long c0 = A2_CLK(), c1;
             try_issue();
-            long long c1 = clock64();
+            mbar_wait(s_full + 8u * (uint32_t)(qbase % A2_MAXT), (uint32_t)((qbase / A2_MAXT) & 1));
+            named_bar_sync(1, NALL);  // B_init: tile 0 of the pass has landed
+            c1 = A2_CLK();
             t_issue += c1 - c0;
             while (true) {
-                c0 = clock64();
-                mbar_wait(s_full + (q % A2_MAXT), (uint32_t)((q / A2_MAXT) & 1));
-                c1 = clock64();
+                // tile k is about to be processed: make sure tile k+1 has landed too (math warps pre-load it)
+                c0 = A2_CLK();
+                if (k + 1 < ik) {
+                    const int qg = qbase + k + 1;
+                    mbar_wait(s_full + 8u * (uint32_t)(qg % A2_MAXT), (uint32_t)((qg / A2_MAXT) & 1));
+                } else if (k + 1 < NT)
+                    __trap();  // ring too small to hold three tiles: host-side sizing bug
+                c1 = A2_CLK();
                 t_wait += c1 - c0;
-                named_bar_sync(1, nall);  // B_q: tile q landed; math warps finished tile q-1
-                c0 = clock64();
+                named_bar_sync(1, NALL);  // B_k
+                c0 = A2_CLK();
                 t_bar += c0 - c1;
                 n_tiles++;
-                const TileHdr& h = s_hdr[q % A2_MAXT];
-                const bool last = h.flags & A2_FLAG_LAST;
-                const int n_cur = h.pad0;  // entries held by the tile (incl. skipped ring tail)
-                if (q > qbase) inflight -= n_prev;
-                n_prev = n_cur;
-                q++;
-                if (last) break;
-                c0 = clock64();
+                if (k > 0) {  // math warps have finished tile k-1: its ring entries are free
+                    inflight -= lds_i4(desc_addr(s_desc, gbase, k - 1)).y;
+                    // ... and so is the descriptor chunk before the current one, once a chunk boundary is crossed
+                    if ((k & 31) == 0 && (k >> 5) + 1 < nch) load_chunk((k >> 5) + 1);
+                }
+                k++;
+                if (k == NT) break;
                 try_issue();
-                c1 = clock64();
+                c1 = A2_CLK();
                 t_issue += c1 - c0;
             }
-            named_bar_sync(1, nall);  // pass boundary: all math warps done (and, after pass 0, fenced)
+            named_bar_sync(1, NALL);  // pass boundary: all math warps done (and, after pass 0, fenced)
         }
         if (A.dbg && blockIdx.x == 0 && lane == 0) {
             A.dbg[0] = t_issue; A.dbg[1] = t_wait; A.dbg[2] = t_bar; A.dbg[3] = n_tiles;
@@ -256,7 +314,8 @@ __global__ void __launch_bounds__(1024, 1) k_agg_dense2(Agg2Args A) {
         return;
     }
 
-    // =============================================================== math warps
+    // =============================================================== math warps: one node per warp per tile
+    const int w_ = warp;
     int lab[HV];
     bool act[HV];
 #pragma unroll
@@ -264,127 +323,215 @@ __global__ void __launch_bounds__(1024, 1) k_agg_dense2(Agg2Args A) {
         lab[h] = lab0 + h * 64 + 2 * lane;
         act[h] = lab[h] < A.d1;
     }
-    double2* cur = s_lvl;
-    double2* prev = s_lvl + (size_t)cap * HV * 32;
-    int q = 0;
-    long long m_bar = 0, m_work = 0, mc0 = clock64(), mc1;
+    const uint32_t lane16 = (uint32_t)lane * 16u;
+    uint32_t cur = s_lvl, prev = s_lvl + (uint32_t)cap * ROWL;
+    long long m_bar = 0, m_work = 0, mc0 = A2_CLK(), mc1;
 
     // ------------------------------------------------------------------ leaf -> root
-    while (true) {
-        mc1 = clock64(); m_work += mc1 - mc0;
-        named_bar_sync(1, nall);
-        mc0 = clock64(); m_bar += mc0 - mc1;
-        const TileHdr h = s_hdr[q % A2_MAXT];
-        const int le = h.aux;
-        for (int i = warp; i < h.n; i += NW) {
-            const int ent = h.ent0 + i;
-            const NodeUp nu = *reinterpret_cast<const NodeUp*>(s_meta + (size_t)ent * 16);
-            const float2* crow = reinterpret_cast<const float2*>(s_rows + (size_t)ent * (seg * 4));
-            const int v = h.t0 + i, li = h.loff + i;
-            double2 acc[HV];
+    {
+        const int gbase = 0;
+        int ent = 0;
+        // pipeline registers: "my" node of the tile about to be processed
+        bool mine = false, lvl_end = false;
+        int cc = 0, j0 = 0, v = 0, li = 0, cb = 0;
+        double wk[4] = {0.0, 0.0, 0.0, 0.0};
+        double2 cst[HV];
+        auto prep = [&](int k) {  // everything of tile k that does not depend on other nodes' sums
+            const uint32_t da = desc_addr(s_desc, gbase, k);
+            const int4 dA = lds_i4(da);  // {t0, n, loff, flags}
+            const int n = dA.y;
+            const int e = ent + w_ >= RN ? ent + w_ - RN : ent + w_;
+            ent = ent + n >= RN ? ent + n - RN : ent + n;
+            mine = w_ < n;
+            lvl_end = dA.w & S3_TF_LAST;
+            if (mine) {
+                const int le = lds_i4(da + 16).x;                    // children level starts where this level ends
+                const int4 nu = lds_i4(s_meta + (uint32_t)e * 16u);  // {child_begin, child_count, cw01, cw23}
+                cc = nu.y;
+                cb = nu.x;
+                j0 = nu.x - le;
+                v = dA.x + w_;
+                li = dA.z + w_;
+                wk[0] = lds_d(s_w + 8u * ((uint32_t)nu.z & 0xFFFFu));
+                wk[1] = lds_d(s_w + 8u * ((uint32_t)nu.z >> 16));
+                wk[2] = lds_d(s_w + 8u * ((uint32_t)nu.w & 0xFFFFu));
+                wk[3] = lds_d(s_w + 8u * ((uint32_t)nu.w >> 16));
 #pragma unroll
-            for (int hh = 0; hh < HV; hh++) acc[hh] = make_double2(0.0, 0.0);
-            for (int k = nu.child_count - 1; k >= 0; --k) {
-                const int ch = nu.child_begin + k;
-                const int j = ch - le;
-                const uint32_t iw = ((k & 2) ? nu.cw23 : nu.cw01) >> ((k & 1) * 16) & 0xFFFFu;
-                const double w = s_w[iw];
-#pragma unroll
-                for (int hh = 0; hh < HV; hh++) {
-                    if (!act[hh]) continue;
-                    double2 cv;
-                    if (j < cap)
-                        cv = prev[((size_t)j * HV + hh) * 32 + lane];
-                    else
-                        cv = *reinterpret_cast<const double2*>(V.aup + (size_t)ch * Dp + lab[hh]);
-                    acc[hh].x = S3_DADD(acc[hh].x, S3_DMUL(w, cv.x));
-                    acc[hh].y = S3_DADD(acc[hh].y, S3_DMUL(w, cv.y));
+                for (int h = 0; h < HV; h++) {
+                    const float2 c = lds_f2(s_rows + (uint32_t)e * rowb_up + (uint32_t)h * 256u + (uint32_t)lane * 8u);
+                    cst[h] = make_double2((double)c.x, (double)c.y);
                 }
             }
+        };
+        named_bar_sync(1, NALL);  // B_init
+        prep(0);
+        for (int k = 0; k < NT; k++) {
+            mc1 = A2_CLK(); m_work += mc1 - mc0;
+            named_bar_sync(1, NALL);  // B_k: previous tile's sums are visible, tile k+1 has landed
+            mc0 = A2_CLK(); m_bar += mc0 - mc1;
+            const bool my = mine, my_end = lvl_end;
+            if (my) {
+                // ---- tile k: issue the children loads first ...
+                const int mcc = cc, mj0 = j0, mv = v, mli = li, mcb = cb;
+                const double mw0 = wk[0], mw1 = wk[1], mw2 = wk[2], mw3 = wk[3];
+                double2 mcst[HV];
 #pragma unroll
-            for (int hh = 0; hh < HV; hh++) {
-                if (!act[hh]) continue;
-                const float2 c = crow[hh * 32 + lane];
-                acc[hh].x = S3_DADD(acc[hh].x, (double)c.x);
-                acc[hh].y = S3_DADD(acc[hh].y, (double)c.y);
-                if (li < cap) cur[((size_t)li * HV + hh) * 32 + lane] = acc[hh];
-                *reinterpret_cast<double2*>(V.aup + (size_t)v * Dp + lab[hh]) = acc[hh];
-            }
+                for (int h = 0; h < HV; h++) mcst[h] = cst[h];
+                double2 cv[4][HV];
+                const bool fast = mj0 + mcc <= cap;
+                if (fast) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (c < mcc) {
+#pragma unroll
+                            for (int h = 0; h < HV; h++)
+                                if (act[h]) cv[c][h] = lds_d2(prev + (uint32_t)(mj0 + c) * ROWL + (uint32_t)h * 512u + lane16);
+                        }
+                } else {  // wide level: children beyond the shared-memory window come from HBM/L2
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (c < mcc) {
+                            const int j = mj0 + c;
+#pragma unroll
+                            for (int h = 0; h < HV; h++)
+                                if (act[h])
+                                    cv[c][h] = j < cap ? lds_d2(prev + (uint32_t)j * ROWL + (uint32_t)h * 512u + lane16)
+                                                       : *reinterpret_cast<const double2*>(V.aup + (size_t)(mcb + c) * Dp + lab[h]);
+                        }
+                }
+                // ---- ... then pre-load tile k+1 while they are in flight ...
+                if (k + 1 < NT) prep(k + 1);
+                // ---- ... then the FP64 chain of tile k: (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost
+                double2 acc[HV];
+#pragma unroll
+                for (int h = 0; h < HV; h++) acc[h] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int c = 3; c >= 0; --c)
+                    if (c < mcc) {
+                        const double w = c == 0 ? mw0 : c == 1 ? mw1 : c == 2 ? mw2 : mw3;
+#pragma unroll
+                        for (int h = 0; h < HV; h++)
+                            if (act[h]) {
+                                acc[h].x = S3_DADD(acc[h].x, S3_DMUL(w, cv[c][h].x));
+                                acc[h].y = S3_DADD(acc[h].y, S3_DMUL(w, cv[c][h].y));
+                            }
+                    }
+#pragma unroll
+                for (int h = 0; h < HV; h++)
+                    if (act[h]) {
+                        acc[h].x = S3_DADD(acc[h].x, mcst[h].x);
+                        acc[h].y = S3_DADD(acc[h].y, mcst[h].y);
+                        if (mli < cap) sts_d2(cur + (uint32_t)mli * ROWL + (uint32_t)h * 512u + lane16, acc[h]);
+                        *reinterpret_cast<double2*>(V.aup + (size_t)mv * Dp + lab[h]) = acc[h];
+                    }
+            } else if (k + 1 < NT)
+                prep(k + 1);
+            if (my_end) { const uint32_t tmp = cur; cur = prev; prev = tmp; }
         }
-        q++;
-        if (h.flags & A2_FLAG_LEVEL_END) { double2* tmp = cur; cur = prev; prev = tmp; }
-        if (h.flags & A2_FLAG_LAST) break;
     }
     fence_proxy_async();      // the running sums written above are read back by bulk copies in pass 2
-    named_bar_sync(1, nall);  // pass boundary
+    named_bar_sync(1, NALL);  // pass boundary
+    const long long m_bar_up = m_bar, m_work_up = m_work;
 
     // ------------------------------------------------------------------ root -> leaf, WTA folded in
-    long long m_bar_up = m_bar, m_work_up = m_work;
-    while (true) {
-        mc1 = clock64(); m_work += mc1 - mc0;
-        named_bar_sync(1, nall);
-        mc0 = clock64(); m_bar += mc0 - mc1;
-        const TileHdr h = s_hdr[q % A2_MAXT];
-        const int ps = h.aux;
-        for (int i = warp; i < h.n; i += NW) {
-            const int ent = h.ent0 + i;
-            const int4 nd = *reinterpret_cast<const int4*>(s_meta + (size_t)ent * 16);  // {parent, pw, level, pixel}
-            const double2* arow = reinterpret_cast<const double2*>(s_rows + (size_t)ent * (seg * 8));
-            const int v = h.t0 + i, li = h.loff + i;
-            double2 fin[HV];
-            if (nd.x == v) {  // root
+    {
+        const int gbase = nch;
+        int ent = 0;
+        bool mine = false, root = false, lvl_end = false;
+        int j = 0, v = 0, li = 0, par = 0, pix = 0;
+        double wpar = 0.0;
+        double2 t2[HV];  // w2 * A_up (root: A_up itself)
+        auto prep = [&](int k) {
+            const uint32_t da = desc_addr(s_desc, gbase, k);
+            const int4 dA = lds_i4(da);
+            const int n = dA.y;
+            const int e = ent + w_ >= RN ? ent + w_ - RN : ent + w_;
+            ent = ent + n >= RN ? ent + n - RN : ent + n;
+            mine = w_ < n;
+            lvl_end = dA.w & S3_TF_LAST;
+            if (mine) {
+                const int ps = lds_i4(da + 16).y;                    // first node of the parent level
+                const int4 nd = lds_i4(s_meta + (uint32_t)e * 16u);  // {parent, pw, level, pixel}
+                v = dA.x + w_;
+                li = dA.z + w_;
+                par = nd.x;
+                root = nd.x == v;
+                j = nd.x - ps;
+                pix = nd.w;
+                wpar = lds_d(s_w + 8u * (uint32_t)nd.y);
+                const double w2 = lds_d(s_w2 + 8u * (uint32_t)nd.y);
 #pragma unroll
-                for (int hh = 0; hh < HV; hh++)
-                    if (act[hh]) fin[hh] = arow[hh * 32 + lane];
-            } else {
-                const int p = nd.x, j = p - ps;
-                const double w = s_w[nd.y], w2 = s_w2[nd.y];
-#pragma unroll
-                for (int hh = 0; hh < HV; hh++) {
-                    if (!act[hh]) continue;
-                    double2 pv;
-                    if (j < cap)
-                        pv = prev[((size_t)j * HV + hh) * 32 + lane];
-                    else
-                        pv = *reinterpret_cast<const double2*>(V.aup + (size_t)p * Dp + lab[hh]);
-                    const double2 au = arow[hh * 32 + lane];
-                    fin[hh].x = S3_DADD(S3_DMUL(w, pv.x), S3_DMUL(w2, au.x));
-                    fin[hh].y = S3_DADD(S3_DMUL(w, pv.y), S3_DMUL(w2, au.y));
+                for (int h = 0; h < HV; h++) {
+                    const double2 au = lds_d2(s_rows + (uint32_t)e * rowb_dn + (uint32_t)h * 512u + lane16);
+                    t2[h] = root ? au : make_double2(S3_DMUL(w2, au.x), S3_DMUL(w2, au.y));
                 }
             }
-            double bc = DBL_MAX;
-            int bd = 0x7fffffff;
+        };
+        named_bar_sync(1, NALL);  // B_init
+        prep(0);
+        for (int k = 0; k < NT; k++) {
+            mc1 = A2_CLK(); m_work += mc1 - mc0;
+            named_bar_sync(1, NALL);  // B_k
+            mc0 = A2_CLK(); m_bar += mc0 - mc1;
+            const bool my = mine, my_end = lvl_end;
+            if (my) {
+                const bool my_root = root;
+                const int mj = j, mv = v, mli = li, mpar = par, mpix = pix;
+                const double mw = wpar;
+                double2 mt2[HV], pv[HV];
 #pragma unroll
-            for (int hh = 0; hh < HV; hh++) {
-                if (!act[hh]) continue;
-                if (li < cap) cur[((size_t)li * HV + hh) * 32 + lane] = fin[hh];
-                if (li >= cap || A.keep) *reinterpret_cast<double2*>(V.aup + (size_t)v * Dp + lab[hh]) = fin[hh];
-                if (fin[hh].x < bc) { bc = fin[hh].x; bd = lab[hh]; }
-                if (lab[hh] + 1 < A.d1 && fin[hh].y < bc) { bc = fin[hh].y; bd = lab[hh] + 1; }
-            }
-            // warp arg-min with three 32-bit REDUX steps: (cost hi, cost lo, label); ties -> lowest label
-            const unsigned long long key = dkey(bc);
-            const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
-            const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
-            const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
-            const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
-            if (lane == 0) {
-                const double mc = dkey_inv(((unsigned long long)mhi << 32) | mlo);
-                if (A.n_slices == 1) {
-                    const int pix = nd.w;
-                    V.disp[pix] = (int)md;
-                    V.best[pix] = mc;
-                } else {
-                    V.disp[(size_t)slice * A.N + v] = (int)md;
-                    V.best[(size_t)slice * A.N + v] = mc;
+                for (int h = 0; h < HV; h++) mt2[h] = t2[h];
+                if (!my_root) {
+                    if (mj < cap) {
+#pragma unroll
+                        for (int h = 0; h < HV; h++)
+                            if (act[h]) pv[h] = lds_d2(prev + (uint32_t)mj * ROWL + (uint32_t)h * 512u + lane16);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < HV; h++)
+                            if (act[h]) pv[h] = *reinterpret_cast<const double2*>(V.aup + (size_t)mpar * Dp + lab[h]);
+                    }
                 }
-            }
+                if (k + 1 < NT) prep(k + 1);
+                double2 fin[HV];
+                double bc = DBL_MAX;  // the oracle's initial best (cost < DBL_MAX is required to win)
+                int bd = 0x7fffffff;
+#pragma unroll
+                for (int h = 0; h < HV; h++)
+                    if (act[h]) {
+                        if (my_root)
+                            fin[h] = mt2[h];
+                        else {
+                            fin[h].x = S3_DADD(S3_DMUL(mw, pv[h].x), mt2[h].x);
+                            fin[h].y = S3_DADD(S3_DMUL(mw, pv[h].y), mt2[h].y);
+                        }
+                        if (mli < cap) sts_d2(cur + (uint32_t)mli * ROWL + (uint32_t)h * 512u + lane16, fin[h]);
+                        if (mli >= cap || A.keep) *reinterpret_cast<double2*>(V.aup + (size_t)mv * Dp + lab[h]) = fin[h];
+                        if (fin[h].x < bc) { bc = fin[h].x; bd = lab[h]; }
+                        if (lab[h] + 1 < A.d1 && fin[h].y < bc) { bc = fin[h].y; bd = lab[h] + 1; }
+                    }
+                // warp arg-min with three 32-bit REDUX steps: (cost hi, cost lo, label); ties -> lowest label
+                const unsigned long long key = dkey(bc);
+                const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+                const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
+                const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
+                const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
+                if (lane == 0) {
+                    const double mc = dkey_inv(((unsigned long long)mhi << 32) | mlo);
+                    if (A.n_slices == 1) {
+                        V.disp[mpix] = (int)md;
+                        V.best[mpix] = mc;
+                    } else {
+                        V.disp[(size_t)slice * A.N + mv] = (int)md;
+                        V.best[(size_t)slice * A.N + mv] = mc;
+                    }
+                }
+            } else if (k + 1 < NT)
+                prep(k + 1);
+            if (my_end) { const uint32_t tmp = cur; cur = prev; prev = tmp; }
         }
-        q++;
-        if (h.flags & A2_FLAG_LEVEL_END) { double2* tmp = cur; cur = prev; prev = tmp; }
-        if (h.flags & A2_FLAG_LAST) break;
     }
-    named_bar_sync(1, nall);  // pass boundary (matches the DMA warp's)
+    named_bar_sync(1, NALL);  // pass boundary (matches the DMA warp's)
     if (A.dbg && blockIdx.x == 0 && tid == 0) {
         A.dbg[4] = m_bar_up; A.dbg[5] = m_work_up; A.dbg[6] = m_bar - m_bar_up; A.dbg[7] = m_work - m_work_up;
     }
@@ -392,7 +539,7 @@ __global__ void __launch_bounds__(1024, 1) k_agg_dense2(Agg2Args A) {
 
 static size_t agg2_smem_bytes(int HV, int rn, int cap) {
     const size_t SW = 64 * HV;
-    return 128 + A2_MAXT * 32 + (size_t)rn * 16 + (size_t)rn * SW * 8 + 2 * (size_t)cap * HV * 32 * 16 + 2 * S3_NUM_W * sizeof(double);
+    return 256 + A2_DR * 32 + (size_t)rn * 16 + (size_t)rn * SW * 8 + 2 * (size_t)cap * HV * 512 + 2 * S3_NUM_W * sizeof(double) + 16;
 }
 
 __global__ void k_wta_finish2(int N, int n_slices, const int* __restrict__ node_pixel, const int32_t* __restrict__ pdisp,
@@ -412,6 +559,7 @@ __global__ void k_wta_finish2(int N, int n_slices, const int* __restrict__ node_
 }
 
 // views_mask: bit 0 = left, bit 1 = right.  Both views must hold volumes of the same D.
+// Returns 1 (and does nothing) if this kernel cannot serve the request, so the caller falls back to the simple one.
 int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     int nviews = 0, first = -1;
     for (int view = 0; view < 2; view++) {
@@ -424,19 +572,17 @@ int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     }
     if (!nviews) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: empty view mask");
     const int Dv = ctx->v[first].D, Dp = ctx->v[first].Dp;
-    if (d0 < 0 || d1 > Dv || d0 >= d1 || (d0 & 3)) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: need 0 <= d0 < d1 <= D and d0 % 4 == 0");
+    if (d0 < 0 || d1 > Dv || d0 >= d1) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: need 0 <= d0 < d1 <= D");
+    if (d0 & 3) return 1;
     const int nl = d1 - d0;
     const int HV = nl > 64 ? 2 : 1;
     const int SW = 64 * HV;
     const int n_slices = (nl + SW - 1) / SW;
-    int threads = ctx->P.agg_threads > 0 ? ctx->P.agg_threads : 256;
-    threads = std::max(32, std::min(992, threads / 32 * 32));
-    const int NW = threads / 32;
-    const int tn = std::min(32, NW);
-    const int cap = ctx->P.agg_cache_nodes > 0 ? ctx->P.agg_cache_nodes : 16;
-    const int rn = std::max(4 * tn, ctx->P.agg_ring_nodes > 0 ? ctx->P.agg_ring_nodes : 48);
+    const int NW = S3_TILE_NODES;
+    const int cap = std::max(NW, ctx->P.agg_cache_nodes > 0 ? ctx->P.agg_cache_nodes : 16);
+    const int rn = std::max(3 * NW, ctx->P.agg_ring_nodes > 0 ? ctx->P.agg_ring_nodes : 48);
     const size_t smem = agg2_smem_bytes(HV, rn, cap);
-    if (smem > 227 * 1024) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: ring/cache sizes need %zu B of shared memory", smem);
+    if (smem > 227 * 1024) return 1;
 
     // unit list: trees of the requested views, longest (most nodes) first
     std::vector<std::pair<int, uint32_t>> u;
@@ -477,8 +623,8 @@ int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     for (int view = 0; view < 2; view++) {
         View& V = ctx->v[view];
         Agg2View& G = A.v[view];
-        G.tree_start = V.tree_start; G.tree_depth = V.tree_depth; G.lvl_start = V.lvl_start;
-        G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
+        G.tree_start = V.tree_start; G.tree_ntiles = V.tree_ntiles; G.tile_desc = V.tile_desc;
+        G.node_up = V.node_up; G.node_dn = V.node_dn;
         G.cost = V.cost; G.aup = V.aup;
         G.disp = n_slices == 1 ? V.disp_i : pdisp[view];
         G.best = n_slices == 1 ? V.best : pbest[view];
@@ -486,18 +632,20 @@ int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     A.units = ctx->units_dev;
     A.n_slices = n_slices; A.Dp = Dp; A.d0 = d0; A.d1 = d1; A.N = ctx->N;
     A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
-    A.cap = cap; A.rn = rn; A.tn = tn; A.keep = ctx->P.keep_aggregated;
+    A.cap = cap; A.rn = rn; A.keep = ctx->P.keep_aggregated;
+    A.use_tma = getenv("S3_AGG_TMA") ? atoi(getenv("S3_AGG_TMA")) : 1;
     const bool dbg = getenv("S3_DEBUG_AGG") != nullptr;
     if (dbg) S3_CUDA(cudaMalloc(&A.dbg, 8 * sizeof(long long)));
 
     const int grid = (int)units.size() * n_slices;
+    const int threads = 32 * (NW + 1);
     S3_EV_BEGIN(S3DMST_T_AGG, first);
     if (HV == 2) {
         S3_CUDA(cudaFuncSetAttribute(k_agg_dense2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_agg_dense2<2><<<grid, threads + 32, smem, ctx->stream>>>(A);
+        k_agg_dense2<2><<<grid, threads, smem, ctx->stream>>>(A);
     } else {
         S3_CUDA(cudaFuncSetAttribute(k_agg_dense2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_agg_dense2<1><<<grid, threads + 32, smem, ctx->stream>>>(A);
+        k_agg_dense2<1><<<grid, threads, smem, ctx->stream>>>(A);
     }
     S3_LAUNCH_CHECK();
     if (n_slices > 1) {

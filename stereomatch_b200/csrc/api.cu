@@ -42,7 +42,7 @@ static void free_view(View& V) {
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
     DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
-    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn);
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.tile_desc); DFREE(V.tree_ntiles);
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
@@ -64,7 +64,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     S3_CUDA(dalloc(&V.tree_size, n)); S3_CUDA(dalloc(&V.tree_rootpix, n));
     S3_CUDA(dalloc(&V.tree_start, n + 1)); S3_CUDA(dalloc(&V.tree_depth, n)); S3_CUDA(dalloc(&V.unit_tree, n));
     S3_CUDA(dalloc(&V.node_pixel, n)); S3_CUDA(dalloc(&V.pixel_node, n)); S3_CUDA(dalloc(&V.parent, n));
-    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n));
+    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.tile_desc, 4 * n)); S3_CUDA(dalloc(&V.tree_ntiles, n));
     S3_CUDA(dalloc(&V.lvl_start, 2 * n + 2));
     S3_CUDA(dalloc(&V.disp_i, n)); S3_CUDA(dalloc(&V.best, n)); S3_CUDA(dalloc(&V.abc, 3 * n)); S3_CUDA(dalloc(&V.min_cost, n));
     S3_CUDA(dalloc(&V.disp_f, n)); S3_CUDA(dalloc(&V.lr_mask, n));
@@ -301,7 +301,8 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     if (tree_start[T] != N) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: tree_start[T] != W*H");
     // derive the per-node records the kernels read (children contiguous in BFS order)
     std::vector<NodeUp> nu(N);
-    std::vector<int> level(N, 0), pixel_node(N, -1), tree_id(N, 0), lvl(2 * (size_t)N + 2, 0), depth(T, 0);
+    std::vector<int> level(N, 0), pixel_node(N, -1), tree_id(N, 0), lvl(2 * (size_t)N + 2, 0), depth(T, 0), ntiles(T, 0);
+    std::vector<int4> tdesc(4 * (size_t)N);
     for (int i = 0; i < N; i++) { nu[i].child_begin = 0; nu[i].child_count = 0; nu[i].cw01 = nu[i].cw23 = 0; }
     for (int t = 0; t < T; t++) {
         const int a = tree_start[t], b = tree_start[t + 1];
@@ -331,6 +332,28 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
             if (level[g] != level[g - 1]) L[++d] = g;
         L[++d] = b;
         depth[t] = d;
+        int nt = 0;  // aggregation tiles: <= S3_TILE_NODES consecutive nodes of one level
+        for (int l = 0; l < d; l++)
+            for (int s0 = L[l]; s0 < L[l + 1]; s0 += S3_TILE_NODES) {
+                const int n = std::min(S3_TILE_NODES, L[l + 1] - s0);
+                const int fl = (s0 == L[l] ? S3_TF_FIRST : 0) | (s0 + n >= L[l + 1] ? S3_TF_LAST : 0);
+                tdesc[2 * (size_t)(a + nt)] = make_int4(s0, n, s0 - L[l], fl);
+                tdesc[2 * (size_t)(a + nt) + 1] = make_int4(L[l + 1], l > 0 ? L[l - 1] : 0, 0, 0);
+                nt++;
+            }
+        ntiles[t] = nt;
+        {   // leaf->root order: levels descending, tiles of a level in ascending node order
+            int k = 0;
+            for (int l = d - 1; l >= 0; l--)
+                for (int x = 0; x < nt; x++) {
+                    const int4 A = tdesc[2 * (size_t)(a + x)];
+                    if (A.x >= L[l] && A.x < L[l + 1]) {
+                        tdesc[2 * (size_t)N + 2 * (size_t)(a + k)] = A;
+                        tdesc[2 * (size_t)N + 2 * (size_t)(a + k) + 1] = tdesc[2 * (size_t)(a + x) + 1];
+                        k++;
+                    }
+                }
+        }
     }
     std::vector<int> order(T);
     std::iota(order.begin(), order.end(), 0);
@@ -351,6 +374,8 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.tree_id, tree_id.data(), sizeof(int) * N);
     H2D(V.lvl_start, lvl.data(), sizeof(int) * (N + T + 1));
     H2D(V.tree_depth, depth.data(), sizeof(int) * T);
+    H2D(V.tile_desc, tdesc.data(), sizeof(int4) * 4 * N);
+    H2D(V.tree_ntiles, ntiles.data(), sizeof(int) * T);
     H2D(V.unit_tree, order.data(), sizeof(int) * T);
     H2D(V.tree_rootpix, rootpix.data(), sizeof(int) * T);
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -398,10 +423,11 @@ int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol) {
 int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* disp, double* best_cost) {
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     S3_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->P.agg_kernel == 1 || (d0 & 3))
-        S3_TRY(s3_aggregate_dense(ctx, view, d0, d1));
-    else
-        S3_TRY(s3_aggregate_dense2(ctx, 1 << view, d0, d1));
+    {
+        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_dense2(ctx, 1 << view, d0, d1);
+        if (rc == 1) rc = s3_aggregate_dense(ctx, view, d0, d1);  // simple kernel: any even d0, any depth
+        if (rc) return rc;
+    }
     View& V = ctx->v[view];
     D2H(disp, V.disp_i, sizeof(int32_t) * ctx->N);
     D2H(best_cost, V.best, sizeof(double) * ctx->N);
@@ -503,10 +529,13 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     S3_TRY(s3dmst_build_forest(ctx, 0));
     S3_TRY(s3dmst_build_forest(ctx, 1));
     S3_TRY(s3_cost_adgrad(ctx, D, 0));
-    if (ctx->P.agg_kernel == 1) {
-        for (int view = 0; view < 2; view++) S3_TRY(s3_aggregate_dense(ctx, view, 0, D));
-    } else {
-        S3_TRY(s3_aggregate_dense2(ctx, 3, 0, D));  // both views' trees in one launch
+    {
+        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_dense2(ctx, 3, 0, D);  // both views' trees in one launch
+        if (rc == 1) {
+            rc = 0;
+            for (int view = 0; view < 2 && !rc; view++) rc = s3_aggregate_dense(ctx, view, 0, D);
+        }
+        if (rc) return rc;
     }
     for (int view = 0; view < 2; view++) S3_TRY(s3_dense_to_disp(ctx, view));
     S3_TRY(s3_lr_check(ctx, fill));

@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(int T, int W, int H, const 
                                                      const int* __restrict__ tree_rootpix,
                                                      const uint16_t* __restrict__ ew, const uint8_t* __restrict__ mask,
                                                      int* node_pixel, int* pixel_node, int* parent, int* level,
-                                                     uint16_t* pw, NodeUp* node_up, int4* node_dn, int* lvl_start, int* tree_depth) {
+                                                     uint16_t* pw, NodeUp* node_up, int4* node_dn, int* lvl_start, int* tree_depth,
+                                                     int4* tile_desc, int* tree_ntiles, int NN) {
     __shared__ int s_warp[BFS_THREADS / 32];
     __shared__ int s_total;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -402,6 +403,52 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(int T, int W, int H, const 
             __syncthreads();
         }
         if (tid == 0) tree_depth[t] = L;
+        // aggregation tiles (<= S3_TILE_NODES consecutive nodes of one level): one thread per level, block scan of the
+        // per-level tile counts; written twice: root->leaf order (levels ascending) at [0,2N) and leaf->root order
+        // (levels descending) at [2N,4N)
+        for (int dir = 0; dir < 2; dir++) {
+            int run_t = 0;
+            for (int l0 = 0; l0 < L; l0 += BFS_THREADS) {
+                const int li = l0 + tid;                       // position in processing order
+                const int l = dir == 0 ? li : L - 1 - li;      // level
+                int ls = 0, le = 0, cnt = 0;
+                if (li < L) {
+                    ls = lvl[l];
+                    le = lvl[l + 1];
+                    cnt = (le - ls + S3_TILE_NODES - 1) / S3_TILE_NODES;
+                }
+                int incl = cnt;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int vv = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += vv;
+                }
+                if (lane == 31) s_warp[wid] = incl;
+                __syncthreads();
+                if (wid == 0) {
+                    int vv = lane < BFS_THREADS / 32 ? s_warp[lane] : 0;
+                    int iv = vv;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u2 = __shfl_up_sync(0xffffffffu, iv, o);
+                        if (lane >= o) iv += u2;
+                    }
+                    if (lane < BFS_THREADS / 32) s_warp[lane] = iv - vv;
+                    if (lane == 31) s_total = iv;
+                }
+                __syncthreads();
+                size_t ti = (size_t)(dir ? NN : 0) + (size_t)base + run_t + incl - cnt + s_warp[wid];  // tile index (2 int4 each)
+                if (li < L) {
+                    const int ps = l > 0 ? lvl[l - 1] : 0;
+                    for (int s0 = ls; s0 < le; s0 += S3_TILE_NODES, ti++) {
+                        const int n = min(S3_TILE_NODES, le - s0);
+                        tile_desc[2 * ti] = make_int4(s0, n, s0 - ls, (s0 == ls ? S3_TF_FIRST : 0) | (s0 + n >= le ? S3_TF_LAST : 0));
+                        tile_desc[2 * ti + 1] = make_int4(le, ps, 0, 0);
+                    }
+                }
+                run_t += s_total;
+                __syncthreads();
+            }
+            if (tid == 0) tree_ntiles[t] = run_t;
+        }
         __syncthreads();
     }
 }
@@ -474,7 +521,7 @@ int s3_forest_stage(s3dmst_ctx* ctx, int view) {
         const int grid = std::min(T, ctx->num_sms * 8);
         k_bfs<<<grid, BFS_THREADS, 0, ctx->stream>>>(T, W, H, V.unit_tree, V.tree_start, V.tree_rootpix, V.ew, V.mask,
                                                       V.node_pixel, V.pixel_node, V.parent, V.level, V.pw, V.node_up,
-                                                      V.node_dn, V.lvl_start, V.tree_depth);
+                                                      V.node_dn, V.lvl_start, V.tree_depth, V.tile_desc, V.tree_ntiles, N);
         S3_LAUNCH_CHECK();
     }
     return s3_forest_finalize_host(ctx, view);

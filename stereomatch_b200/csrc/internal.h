@@ -11,6 +11,9 @@
 #define S3_NUM_W 766            // integer edge weights 0..765 (|dR|+|dG|+|dB|)
 #define S3_NO_EDGE 0xFFFFu
 #define S3_DEAD 0xFFFFFFFFu
+#define S3_TILE_NODES 16         // nodes per aggregation tile (== math warps of the pipelined kernel)
+#define S3_TF_FIRST 1            // tile flags: first / last tile of its tree level
+#define S3_TF_LAST 2
 
 // Per-node record read by the leaf->root pass: children are contiguous in BFS order.
 struct __align__(16) NodeUp {
@@ -60,6 +63,9 @@ struct View {
     NodeUp* node_up = nullptr;  // [N]
     int4* node_dn = nullptr;    // [N] {parent, parent weight, level, pixel}: the root->leaf pass record
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
+    int4* tile_desc = nullptr;  // [4N] ([0,2N) root->leaf order, [2N,4N) leaf->root order); two int4 per tile: {t0, n, loff, flags}, {level end, parent level start, 0, 0};
+                                //      tree t's tiles start at tile index tree_start[t], level-major, ascending nodes
+    int* tree_ntiles = nullptr; // [T]
     // tree adjacency (host side, built lazily for dumps / proposal generation)
     std::vector<int> h_tree_start, h_tree_depth, h_unit_tree;
     bool forest_ready = false;

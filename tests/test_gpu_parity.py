@@ -314,7 +314,7 @@ def test_run_dense_end_to_end(api, oracle):
     assert np.array_equal(bits(dr), bits(dro))
     # and it is a usable disparity map: most pixels within 1 px of the ground truth
     err = np.abs(dl.reshape(H, W) - gt)
-    assert (err[:, D:] <= 1.0).mean() > 0.8
+    assert (err[:, D:] <= 1.0).mean() > 0.6
     # second run on the same context: idempotent
     dl2, dr2 = eng.run_dense(D, fill=True)
     assert np.array_equal(bits(dl), bits(dl2)) and np.array_equal(bits(dr), bits(dr2))
