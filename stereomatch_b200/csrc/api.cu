@@ -204,7 +204,6 @@ int s3dmst_build_forest(s3dmst_ctx* ctx, int view) {
     if (view < 0 || view > 1 || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "build_forest: bad view or no images");
     S3_CUDA(cudaSetDevice(ctx->device));
     S3_EV_BEGIN(S3DMST_T_FOREST, view);
-    S3_TRY(s3_image_stage(ctx, view));
     S3_TRY(s3_forest_stage(ctx, view));
     S3_EV_END(S3DMST_T_FOREST, view);
     return 0;
@@ -526,8 +525,9 @@ int s3dmst_lr_check(s3dmst_ctx* ctx, int fill) {
 int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp) {
     S3_CUDA(cudaSetDevice(ctx->device));
     memset(ctx->ev_set, 0, sizeof ctx->ev_set);
-    S3_TRY(s3dmst_build_forest(ctx, 0));
-    S3_TRY(s3dmst_build_forest(ctx, 1));
+    S3_EV_BEGIN(S3DMST_T_FOREST, 0);
+    S3_TRY(s3_forest_stage_mask(ctx, 3));  // both views share every launch of the forest stage
+    S3_EV_END(S3DMST_T_FOREST, 0);
     S3_TRY(s3_cost_adgrad(ctx, D, 0));
     {
         int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_dense2(ctx, 3, 0, D);  // both views' trees in one launch

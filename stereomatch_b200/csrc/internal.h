@@ -144,6 +144,8 @@ int s3_fail(s3dmst_ctx* c, int code, const char* fmt, ...);
 // stage entry points implemented in the .cu files ------------------------------------------------
 int s3_image_stage(s3dmst_ctx* ctx, int view);                    // image.cu: median, gray, edge weights, buckets
 int s3_forest_stage(s3dmst_ctx* ctx, int view);                   // forest.cu: FH + merge + labels + BFS
+int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask);              // both views in shared launches
+int s3_fh_launch(s3dmst_ctx* ctx, int mask);
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);           // forest.cu: unit order, depths
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
