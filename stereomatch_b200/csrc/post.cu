@@ -157,7 +157,6 @@ int s3_lr_check(s3dmst_ctx* ctx, int fill) {
 
 int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev) {
     View& V = ctx->v[view];
-    if (!V.agg_ready) return s3_fail(ctx, S3DMST_E_STATE, "minloc_mask: aggregate_dense first");
     k_minloc_mask<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, V.best, global_min_dev, V.disp_i);
     S3_LAUNCH_CHECK();
     return 0;
