@@ -114,6 +114,13 @@ int s3dmst_get_min_cost(s3dmst_ctx* ctx, int view, double* min_cost);
 /* Injected proposals, applied in order (MSTCostAggregationAndLabelUpdate, :160-186): proposal i tests
  * label labels[3i..3i+2] on tree tree_ids[i]. */
 int s3dmst_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* tree_ids, const float* labels, size_t n);
+/* a6 random plane initialisation (:390-430), bit-identical to the reference (same libstdc++ engine and
+ * distribution, raster order); also resets min_cost to DBL_MAX (:820-821). */
+int s3dmst_init_labels(s3dmst_ctx* ctx, int view, int Dmax);
+/* a12 MST_PMS (:546-629) x n_iter with the library's own proposal generator (neighbour-tree labels, then the
+ * refinement ladder).  Labels are initialised as above if none were set.  Parity for this stage is by injection
+ * (s3dmst_pms_apply); the generator's two defined deviations are stated in csrc/pms.cu. */
+int s3dmst_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed);
 /* a13 LabelToDisp (:189-201) followed by the *(Dmax-1) of :900-902. */
 int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view);
 

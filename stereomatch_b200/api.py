@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_run_dense", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_stage_ms", "s3dmst_launch_count",
 ]
 
 _lib = None
@@ -82,6 +82,8 @@ def load_library():
     L.s3dmst_get_min_cost.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_pms_apply.argtypes = [c_p, C.c_int, c_p, c_p, C.c_size_t]
     L.s3dmst_label_to_disp.argtypes = [c_p, C.c_int]
+    L.s3dmst_init_labels.argtypes = [c_p, C.c_int, C.c_int]
+    L.s3dmst_pms_iterate.argtypes = [c_p, C.c_int, C.c_int, C.c_uint]
     L.s3dmst_set_disparity.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_get_disparity.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_lr_check.argtypes = [c_p, C.c_int]
@@ -250,6 +252,13 @@ class Stereo3DMST:
         tree_ids = np.ascontiguousarray(tree_ids, np.int32)
         labels = np.ascontiguousarray(labels, np.float32)
         self._ck(self.L.s3dmst_pms_apply(self.h, view, _ptr(tree_ids), _ptr(labels), len(tree_ids)))
+
+    def init_labels(self, view, Dmax):
+        """The reference's random plane initialisation (Stereo3DMST.cpp:390-430); resets min_cost."""
+        self._ck(self.L.s3dmst_init_labels(self.h, view, int(Dmax)))
+
+    def pms_iterate(self, view, n_iter, seed=1):
+        self._ck(self.L.s3dmst_pms_iterate(self.h, view, int(n_iter), int(seed)))
 
     def label_to_disp(self, view):
         self._ck(self.L.s3dmst_label_to_disp(self.h, view))

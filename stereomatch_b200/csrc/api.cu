@@ -499,6 +499,22 @@ int s3dmst_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* tree_ids, const f
     return s3_pms_apply(ctx, view, tree_ids, labels, n);
 }
 
+int s3dmst_init_labels(s3dmst_ctx* ctx, int view, int Dmax) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_init_labels(ctx, view, Dmax);
+}
+
+int s3dmst_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed) {
+    if (view < 0 || view > 1 || n_iter < 0) return s3_fail(ctx, S3DMST_E_ARG, "pms_iterate: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->v[view].forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: no forest");
+    if (!ctx->v[view].labels_ready) S3_TRY(s3_init_labels(ctx, view, ctx->v[view].D));  // :390-430
+    std::vector<int> adj_ptr, adj;
+    S3_TRY(host_adjacency(ctx, view, adj_ptr, adj));
+    return s3_pms_iterate(ctx, view, n_iter, seed, adj_ptr, adj);
+}
+
 int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view) {
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     return s3_label_to_disp(ctx, view);

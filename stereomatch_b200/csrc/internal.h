@@ -153,6 +153,8 @@ int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
 int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined)
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
+int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax);          // pms.cu: the reference's random plane initialisation
+int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed, const std::vector<int>& adj_ptr, const std::vector<int>& adj);
 int s3_label_to_disp(s3dmst_ctx* ctx, int view);                  // post.cu
 int s3_dense_to_disp(s3dmst_ctx* ctx, int view);
 int s3_lr_check(s3dmst_ctx* ctx, int fill);

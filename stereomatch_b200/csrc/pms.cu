@@ -183,3 +183,113 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
     S3_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Host-side label initialisation and proposal generation (a6, a12).  These are the two spots of the
+// path that draw random numbers; the numbers come from the same libstdc++ objects the reference uses,
+// so the initial labels are bit-identical to the reference's (src/Stereo3DMST.cpp:390-430: one
+// default_random_engine per view behind uniform_real_distribution<float>(0,1), raster order, rejection
+// sampling of the normal in the unit disc).
+#include <cmath>
+#include <functional>
+#include <random>
+
+int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax) {
+    View& V = ctx->v[view];
+    const int W = ctx->W, H = ctx->H;
+    if (ctx->N == 0 || Dmax <= 0) return s3_fail(ctx, S3DMST_E_ARG, "init_labels: images and Dmax > 0 required");
+    std::vector<float> abc(3 * (size_t)ctx->N);
+    std::default_random_engine engine;  // fresh engine per view (:390): both views draw the same stream
+    std::uniform_real_distribution<float> unit(0.0f, 1.0f);
+    size_t o = 0;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++, o += 3) {
+            const float d = unit(engine) * Dmax;
+            float u, v, s;
+            do {  // (u, v) uniform in the positive quadrant of the unit disc (Q7)
+                u = unit(engine);
+                v = unit(engine);
+                s = u * u + v * v;
+            } while (!(s < 1.0f));
+            const float k = std::sqrt(1.0f - u * u - v * v);
+            const float nx = 2.0f * u * k, ny = 2.0f * v * k;
+            const float nz = std::sqrt(1.0f - nx * nx - ny * ny);
+            abc[o] = -nx / nz;
+            abc[o + 1] = -ny / nz;
+            abc[o + 2] = (nx * x + ny * y + nz * d) / nz;
+        }
+    S3_CUDA(cudaMemcpyAsync(V.abc, abc.data(), abc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> big(ctx->N, DBL_MAX);  // :820-821
+    S3_CUDA(cudaMemcpyAsync(V.min_cost, big.data(), big.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    V.labels_ready = true;
+    return 0;
+}
+
+// n_iter rounds of MST_PMS (:546-629) with the library's own generator.  Per round and per tree (ascending id):
+// one proposal per neighbouring tree (ascending id) = the label of a random pixel of that tree, then the
+// refinement ladder max_d = Dmax/2, /2, ... > refine_floor around a random pixel of the tree itself.  The "dice"
+// stream is a fresh default engine behind U(-1,1) in every round, as in the reference (std::bind copies, Q8).
+// Defined deviation (parity for this stage is by proposal injection): proposals of a round read the
+// labels as they were when the round started (the serial reference lets tree t see what trees < t changed in
+// the same round; its own OpenMP build already races on exactly that, Q13), and the refinement pixel comes from
+// a seeded mt19937 instead of the unseeded process-global std::rand() (Q6/Q9).
+int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed, const std::vector<int>& adj_ptr, const std::vector<int>& adj) {
+    View& V = ctx->v[view];
+    if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
+        return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: forest, cost volume and labels required");
+    const int N = ctx->N, W = ctx->W, T = V.T, Dmax = V.D;
+    std::vector<int> tid(N);
+    S3_CUDA(cudaMemcpyAsync(tid.data(), V.tree_id, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> tstart(T + 1, 0), tpix(N);  // pixels of every tree in raster order (:352-367)
+    for (int p = 0; p < N; p++) tstart[tid[p] + 1]++;
+    for (int t = 0; t < T; t++) tstart[t + 1] += tstart[t];
+    {
+        std::vector<int> cur(tstart.begin(), tstart.end() - 1);
+        for (int p = 0; p < N; p++) tpix[cur[tid[p]]++] = p;
+    }
+    std::vector<float> abc(3 * (size_t)N), labels;
+    std::vector<int32_t> trees;
+    std::mt19937 pick(seed);
+    for (int it = 0; it < n_iter; it++) {
+        S3_CUDA(cudaMemcpyAsync(abc.data(), V.abc, abc.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::default_random_engine engine;
+        std::uniform_real_distribution<float> sym(-1.0f, 1.0f);
+        trees.clear();
+        labels.clear();
+        auto push = [&](int t, float a, float b, float c) {
+            trees.push_back(t);
+            labels.push_back(a); labels.push_back(b); labels.push_back(c);
+        };
+        for (int t = 0; t < T; t++) {
+            for (int k = adj_ptr[t]; k < adj_ptr[t + 1]; k++) {
+                const int nb = adj[k], sz = tstart[nb + 1] - tstart[nb];
+                const int idx = std::min(sz - 1, (int)((sym(engine) + 1.0f) * 0.5f * sz));  // Q11 clamp
+                const float* l = &abc[3 * (size_t)tpix[tstart[nb] + idx]];
+                push(t, l[0], l[1], l[2]);
+            }
+            const int sz = tstart[t + 1] - tstart[t];
+            const int p = tpix[tstart[t] + (int)(pick() % (unsigned)sz)];
+            const float px = (float)(p % W), py = (float)(p / W);
+            const float* l = &abc[3 * (size_t)p];
+            const float nz = 1.0f / std::sqrt(l[0] * l[0] + l[1] * l[1] + 1.0f);
+            const float nx = -l[0] * nz, ny = -l[1] * nz;
+            const float d = px * l[0] + py * l[1] + l[2];
+            float span_n = 1.0f;
+            for (float span_d = 0.5f * Dmax; span_d > ctx->P.refine_floor; span_d *= 0.5f, span_n *= 0.5f) {
+                const float rd = d + sym(engine) * span_d;
+                if (rd < 0.0f || rd > (float)Dmax) continue;  // draws 1 number, then 3 more only when in range (A11)
+                float rx = nx + sym(engine) * span_n;
+                float ry = ny + sym(engine) * span_n;
+                float rz = nz + sym(engine) * span_n;
+                const float inv = 1.0f / std::sqrt(rx * rx + ry * ry + rz * rz);
+                rx *= inv; ry *= inv; rz = std::fabs(rz * inv);
+                push(t, -rx / rz, -ry / rz, (rx * px + ry * py + rz * rd) / rz);
+            }
+        }
+        S3_TRY(s3_pms_apply(ctx, view, trees.data(), labels.data(), trees.size()));
+    }
+    return 0;
+}

@@ -232,6 +232,34 @@ def test_pms_replays_recorded_reference_sequence(api, oracle):
     eng.close()
 
 
+def test_init_labels_and_generator(api, oracle):
+    """a6: the library's plane initialisation is the reference's (bit-identical to the oracle, which is pinned to the
+    reference TU); a12 with the library's own generator: min_cost never increases, every accepted label is one
+    the round proposed for that tree, and a run is reproducible."""
+    W, H, D = 128, 80, 16
+    L, R, _ = make(W, H, D, 41, 0)
+    eng = api.Stereo3DMST(fh_c=600.0, min_cc_size=40, cost_scale=1 / 6.0)
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    eng.build_cost_volume(D, ingest=True)
+    eng.init_labels(0, D)
+    assert np.array_equal(bits(eng.get_labels(0)), bits(oracle.plane_init(W, H, D)))
+    assert np.all(eng.get_min_cost(0) == np.finfo(np.float64).max)
+    eng.pms_iterate(0, 1, seed=3)
+    m1 = eng.get_min_cost(0).copy(); l1 = eng.get_labels(0).copy()
+    assert np.all(m1 < np.finfo(np.float64).max)
+    eng.pms_iterate(0, 2, seed=4)
+    m3 = eng.get_min_cost(0)
+    assert np.all(m3 <= m1) and np.any(m3 < m1)
+    eng.init_labels(0, D)
+    eng.pms_iterate(0, 1, seed=3)
+    assert np.array_equal(bits(eng.get_min_cost(0)), bits(m1)) and np.array_equal(bits(eng.get_labels(0)), bits(l1))
+    eng.label_to_disp(0)
+    d = eng.get_disparity(0)
+    assert d.min() >= 0.0 and d.max() <= D - 1.0
+    eng.close()
+
+
 def test_golden_reference_proposals(api, oracle):
     """tests/golden/ref_small.npz holds output of the reference's own code: replay its proposals on the GPU."""
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_small.npz"))
