@@ -37,7 +37,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 
 static void free_view(View& V) {
     DFREE(V.bgr); DFREE(V.raw4); DFREE(V.med); DFREE(V.gray); DFREE(V.ew);
-    DFREE(V.uf_parent); DFREE(V.uf_size); DFREE(V.uf_lastw); DFREE(V.uf_best); DFREE(V.uf_resv);
+    DFREE(V.uf_parent); DFREE(V.uf_size); DFREE(V.uf_lastw); DFREE(V.adjw); DFREE(V.bfs_front); DFREE(V.uf_pick[0]); DFREE(V.uf_pick[1]); DFREE(V.fh_ent[0]); DFREE(V.fh_ent[1]); DFREE(V.uf_resv);
     DFREE(V.mask); DFREE(V.elist); DFREE(V.e_ra); DFREE(V.e_rb); DFREE(V.e_flag);
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
@@ -55,7 +55,9 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     S3_CUDA(dalloc(&V.bgr, 3 * n)); S3_CUDA(dalloc(&V.raw4, n)); S3_CUDA(dalloc(&V.med, n)); S3_CUDA(dalloc(&V.gray, n));
     S3_CUDA(dalloc(&V.ew, 2 * n));
     S3_CUDA(dalloc(&V.uf_parent, n)); S3_CUDA(dalloc(&V.uf_size, n)); S3_CUDA(dalloc(&V.uf_lastw, n));
-    S3_CUDA(dalloc(&V.uf_best, n)); S3_CUDA(dalloc(&V.uf_resv, n));
+    S3_CUDA(dalloc(&V.adjw, n)); S3_CUDA(dalloc(&V.bfs_front, n));
+    S3_CUDA(dalloc(&V.uf_pick[0], n)); S3_CUDA(dalloc(&V.uf_pick[1], n)); S3_CUDA(dalloc(&V.uf_resv, n));
+    for (int i = 0; i < 2; i++) { unsigned char* b = nullptr; S3_CUDA(dalloc(&b, 32 * n + 16 * (size_t)S3_FH_MAX_CTAS * (S3_FH_SEG_SLACK + 1))); V.fh_ent[i] = b; }
     S3_CUDA(dalloc(&V.mask, 2 * n)); S3_CUDA(dalloc(&V.elist, 2 * n)); S3_CUDA(dalloc(&V.e_ra, 2 * n));
     S3_CUDA(dalloc(&V.e_rb, 2 * n)); S3_CUDA(dalloc(&V.e_flag, 2 * n));
     S3_CUDA(dalloc(&V.hist, S3_NUM_W)); S3_CUDA(dalloc(&V.lvl_off, S3_NUM_W + 1)); S3_CUDA(dalloc(&V.lvl_cursor, S3_NUM_W));
@@ -157,7 +159,7 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
-    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev);
+    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev); DFREE(ctx->fh_sync);
     for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
         if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -24,8 +24,6 @@
 //  * BFS: one CTA per tree, level-synchronous inside the CTA; children of a node are its forest
 //    neighbours except the parent, ordered by (w, edge id) (= the reference's adjacency insertion
 //    order), numbered by a block-wide exclusive scan so BFS numbering equals the reference's queue order.
-#include <cooperative_groups.h>
-
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -36,25 +34,34 @@
 
 #include "internal.h"
 
-namespace cg = cooperative_groups;
-
 #define CNT_ERR (S3_MAX_ROUNDS - 1)
 #define CNT_LIST (S3_MAX_ROUNDS - 2)
 #define CNT_ROUNDS (S3_MAX_ROUNDS - 3)
 #define CNT_FIRSTS (S3_MAX_ROUNDS - 4)
+#define CNT_ACT (S3_MAX_ROUNDS - 20)  // [2] live-list lengths of the FH rounds
 #define ROUND_CAP (S3_MAX_ROUNDS - 32)
+
+struct __align__(16) FHEntry {
+    unsigned long long key;  // (w << 32) | edge id; bit 63 = accepted last round (ra = the root that hooked), bit 62 = rejected
+    int ra, rb;              // endpoint components when the entry was last looked at
+};
+#define FH_HOOKED (1ull << 63)
+#define FH_REJECT (1ull << 62)
+#define FH_NOKEY (~0ull)
 
 struct FHArgs {
     int W, N;
     float c;
     int m;
+    int band_low, band_high;  // live-list control: ingest further weight levels when fewer than band_low entries are live
     const uint16_t* ew;
     uint32_t* elist;
     const int* lvl_off;
     int* parent;
     int* size;
     int* lastw;
-    uint32_t* best;
+    unsigned long long* pick[2];  // [N] minimum live key per component, double-buffered by round parity
+    FHEntry* ent[2];              // [2N] live-edge lists, ping-pong
     unsigned long long* resv;
     uint8_t* mask;
     int* e_ra;
@@ -74,6 +81,33 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
     }
 }
 
+// two finds with their dependent loads interleaved (the chains are independent; each hop is an L2 round trip).
+// Full path compression for the first few nodes of each path (kept in registers), halving beyond.
+__device__ __forceinline__ void uf_find2(int* parent, int& x, int& y) {
+    int ax = -1, bx = -1, cx = -1, dx4 = -1, ay = -1, by = -1, cy = -1, dy4 = -1;  // the last 4 non-root nodes of each path
+    bool dx = false, dy = false;
+    while (!(dx && dy)) {
+        int px = x, py = y;
+        if (!dx) px = __ldcg(parent + x);
+        if (!dy) py = __ldcg(parent + y);
+        if (!dx) {
+            if (px == x) dx = true;
+            else { dx4 = cx; cx = bx; bx = ax; ax = x; x = px; }
+        }
+        if (!dy) {
+            if (py == y) dy = true;
+            else { dy4 = cy; cy = by; by = ay; ay = y; y = py; }
+        }
+    }
+    // ax / ay already point at the root; the three before them are re-pointed (racing writers only store ancestors)
+    if (bx >= 0) __stcg(parent + bx, x);
+    if (cx >= 0) __stcg(parent + cx, x);
+    if (dx4 >= 0) __stcg(parent + dx4, x);
+    if (by >= 0) __stcg(parent + by, y);
+    if (cy >= 0) __stcg(parent + cy, y);
+    if (dy4 >= 0) __stcg(parent + dy4, y);
+}
+
 // segment-graph.h:27,80 — THRESHOLD(size,c) is a float division (Q2), added to a double w
 __device__ __forceinline__ bool uf_open(const FHArgs& A, int r, int w) {
     const double thr = (double)__ldcg(A.lastw + r) + (double)__fdiv_rn(A.c, (float)__ldcg(A.size + r));
@@ -89,181 +123,208 @@ __device__ __forceinline__ int block_sum_to_counter(int v, int* counter) {
 
 struct FHArgs2 {
     FHArgs v[2];
+    int nviews;
+    int seg_cap;         // capacity of one CTA's segment of the live-edge lists (entries)
+    unsigned* bar;       // grid barrier counter (zeroed by the host)
+    int* gcnt;           // [S3_MAX_ROUNDS][2] per-round, per-view live counts (zeroed by the host)
 };
 
-// One thread-block CLUSTER per view (16 CTAs x 1024 threads on one GPC): the phases of a Boruvka / reservation
-// round are separated by cluster barriers (~0.3 us) instead of grid-wide barriers (~3-4 us), and the ~1500
-// barriers of a forest build are what bounds this kernel.  Clusters (views) never synchronise with each other.
+// Grid-wide barrier for a co-resident grid (cooperative launch): one arrive per CTA, thread 0 spins on the counter.
+// Mutable data is accessed with __ldcg/__stcg (L2), so the fence + barrier pair orders it across CTAs.
+__device__ __forceinline__ void fh_grid_bar(unsigned* bar, unsigned& target, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// FH phase — asynchronous exact formulation.  Sequential FH visits edges in key order (w, id) and accepts an edge iff
+// its endpoint components differ and are both open (w <= thr) at that moment.  Facts used (each validated
+// edge-for-edge against the sequential code on the FLIR and synthetic images, tests/models/forest_model.py):
+//   (1) if e is the minimum-key undecided edge of component C, C is unchanged when e's turn comes, so "C open at
+//       w(e)" can be evaluated now; if it fails, C can never merge again (every other edge of C is heavier): C is
+//       dead and all its edges are rejected;
+//   (2) if e is the minimum of both its components, the decision is final now;
+//   (3) if e = (C, D) is C's minimum, D is alive and D's minimum has the SAME weight, e is accepted: whatever D
+//       merges with before e at that level stays open for the rest of the level (thr = w + c/size >= w).
+// A round = every live edge posts its key on both components (atomicMin), then every edge that is somebody's
+// minimum is decided by (1)-(3); chains of (3) resolve in one round like Boruvka hooks.  Only a weight-ordered
+// PREFIX of the edges is live at any time (any prefix of the key order is self-contained for these rules); more
+// levels are ingested when the live list runs low.  ~110-145 rounds at the C2 workload instead of ~900 with
+// one-level-at-a-time Boruvka.
+//
+// Launch: cooperative, one CTA per SM; the first half of the grid serves view 0, the second half view 1 (random
+// 4-8 byte accesses: the kernel is bound by L2 sector throughput and by the two barriers per round, so it wants
+// every GPC's L2 ports, not one cluster's).  Every CTA keeps its OWN segment of the live list (survivors stay with
+// the CTA that looked at them, new levels are dealt out evenly), so compaction needs no global cursor.
 __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
-    cg::cluster_group grid = cg::this_cluster();
-    const FHArgs& A = AA.v[blockIdx.x / grid.num_blocks()];
-    const int gtid = grid.block_rank() * blockDim.x + threadIdx.x;
-    const int gstride = grid.num_blocks() * blockDim.x;
-    const int cbase = grid.block_rank() * blockDim.x;  // this CTA's first thread in the cluster-wide numbering
+    const int nblk_all = gridDim.x;
+    const int per_view = nblk_all / AA.nviews;
+    const int vi = min((int)blockIdx.x / per_view, AA.nviews - 1);
+    const FHArgs& A = AA.v[vi];
+    const int crank = blockIdx.x - vi * per_view;                                   // CTA rank inside its view
+    const int nblk = vi == AA.nviews - 1 ? nblk_all - vi * per_view : per_view;     // CTAs of this view
+    const int gtid = crank * blockDim.x + threadIdx.x;
+    const int gstride = nblk * blockDim.x;
+    const int cbase = crank * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int nviews = AA.nviews;
+    unsigned bar_target = 0;
     int round = 0;
-    long long tA = 0, tB = 0, tC = 0, tS = 0, t0 = clock64(), t1;
-    int nlev = 0;
+    long long tA = 0, tB = 0, tS = 0, t0 = clock64(), t1;
+    long long visits = 0;
+    __shared__ int s_cnt;
 #define FH_T(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+#define FH_BAR() fh_grid_bar(AA.bar, bar_target, (unsigned)nblk_all)
 
-    // cluster-wide sum of a per-thread count through distributed shared memory (one cluster barrier, no
-    // global-memory round trip): every CTA deposits its partial sum in every CTA's slot array
-    __shared__ int s_part[2];
-    __shared__ int s_cnt[2][16];
-    const int nb = (int)grid.num_blocks(), myrank = (int)grid.block_rank();
-    int sync_no = 0;
-    auto cluster_sum = [&](int v) -> int {
-        const int par = sync_no & 1;
-        sync_no++;
-        if (threadIdx.x == 0) s_part[par] = 0;
-        __syncthreads();
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_part[par], v);
-        __syncthreads();
-        if ((int)threadIdx.x < nb) grid.map_shared_rank(&s_cnt[par][0], threadIdx.x)[myrank] = s_part[par];
-        grid.sync();
-        int tot = 0;
-        for (int r = 0; r < nb; r++) tot += s_cnt[par][r];
-        return tot;
-    };
-    // the three phases of a Boruvka round on one edge (e becomes S3_DEAD when the edge can never join)
-    auto phase_a = [&](uint32_t& e, int& ra, int& rb, int w) -> int {
-        const int a = (int)(e >> 1), b = a + ((e & 1u) ? A.W : 1);
-        ra = uf_find(A.parent, a);
-        rb = uf_find(A.parent, b);
-        if (ra == rb || !uf_open(A, ra, w) || !uf_open(A, rb, w)) {
-            e = S3_DEAD;  // same component / closed component: permanent
-            return 0;
-        }
-        atomicMin(A.best + ra, e);
-        atomicMin(A.best + rb, e);
-        return 1;
-    };
-    auto phase_b = [&](uint32_t e, int ra, int rb, uint8_t& fl) -> int {  // returns 1 if the edge stays pending
-        const bool pa = __ldcg(A.best + ra) == e, pb = __ldcg(A.best + rb) == e;
-        fl = 0;
-        if (!(pa || pb)) return 1;
-        A.mask[e] = 1;
-        const bool mutual = pa && pb;
-        if (pa && !(mutual && ra < rb)) { __stcg(A.parent + ra, rb); fl |= 1; }
-        if (pb && !(mutual && rb < ra)) { __stcg(A.parent + rb, ra); fl |= 2; }
-        fl |= 4;
-        return 0;
-    };
-    auto phase_c = [&](int ra, int rb, uint8_t fl, int w) {
-        __stcg(A.best + ra, S3_DEAD);
-        __stcg(A.best + rb, S3_DEAD);
-        if (fl & 1) {
-            const int R = uf_find(A.parent, ra);
-            atomicAdd(A.size + R, __ldcg(A.size + ra));
-            __stcg(A.lastw + R, w);
-        }
-        if (fl & 2) {
-            const int R = uf_find(A.parent, rb);
-            atomicAdd(A.size + R, __ldcg(A.size + rb));
-            __stcg(A.lastw + R, w);
-        }
-    };
-
-    // ------------------------------------------------------------------ FH, level by level
-    for (int w = 0; w < S3_NUM_W; ++w) {
-        const int lo = A.lvl_off[w], hi = A.lvl_off[w + 1];
-        if (lo == hi) continue;
-        nlev++;
-        // a level with at most one edge per thread (the common case) keeps its edge state in registers
-        const bool single = hi - lo <= gstride;
-        uint32_t e1 = S3_DEAD;
-        int ra1 = 0, rb1 = 0;
-        uint8_t fl1 = 0;
-        if (single && lo + gtid < hi) e1 = A.elist[lo + gtid];
+    // ------------------------------------------------------------------ FH
+    {
+        int n_live[2] = {0, 0};    // live entries per view after the previous round (all CTAs)
+        int lev[2] = {0, 0};       // weight levels ingested so far
+        int band_pos[2] = {0, 0};  // == lvl_off[lev]
+        int my_src = 0;            // entries in this CTA's source segment (live + flagged ones of the previous round)
+        int par = 0;
+        const size_t seg = (size_t)crank * AA.seg_cap;
         while (true) {
-            round++;
-            // phase A: each live edge picks itself as the minimum edge of both endpoint components
-            int live = 0;
-            if (single) {
-                if (e1 != S3_DEAD) live = phase_a(e1, ra1, rb1, w);
-            } else {
-                for (int pos = lo + gtid; pos < hi; pos += gstride) {
-                    uint32_t e = A.elist[pos];
-                    if (e == S3_DEAD) continue;
-                    int ra, rb;
-                    if (phase_a(e, ra, rb, w)) {
-                        A.e_ra[pos] = ra;
-                        A.e_rb[pos] = rb;
-                        live++;
-                    } else
-                        A.elist[pos] = S3_DEAD;
-                }
+            int band_lo[2], work = 0;
+            for (int v = 0; v < nviews; v++) {  // uniform across the grid: every thread tracks both views
+                band_lo[v] = band_pos[v];
+                if (n_live[v] < AA.v[v].band_low)
+                    while (lev[v] < S3_NUM_W && n_live[v] + (band_pos[v] - band_lo[v]) < AA.v[v].band_high)
+                        band_pos[v] = AA.v[v].lvl_off[++lev[v]];
+                work += n_live[v] + (band_pos[v] - band_lo[v]);
             }
+            if (work == 0) break;  // nothing live and nothing left to ingest in either view
+            if (++round >= ROUND_CAP) {
+                if (gtid == 0) A.counters[CNT_ERR] = 1;
+                return;
+            }
+            const FHEntry* src = A.ent[par] + seg;
+            FHEntry* dst = A.ent[par ^ 1] + seg;
+            unsigned long long* pick = A.pick[par];
+            unsigned long long* pick_prev = A.pick[par ^ 1];
+            // ---- phase 1: settle last round's decisions, re-root the survivors, post keys, compact
+            const int n_new = band_pos[vi] - band_lo[vi];
+            const int share = (n_new + nblk - 1) / nblk;
+            const int new_lo = min(n_new, crank * share), new_hi = min(n_new, (crank + 1) * share);
+            const int total = my_src + (new_hi - new_lo);
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+            for (int base = 0; base < total; base += blockDim.x) {  // warp-uniform trip count
+                const int pos = base + threadIdx.x;
+                bool live = false;
+                FHEntry en;
+                en.key = FH_NOKEY; en.ra = 0; en.rb = 0;
+                if (pos < my_src) {
+                    en = src[pos];
+                    __stcg(pick_prev + en.ra, FH_NOKEY);  // clean the buffer the previous round posted into
+                    __stcg(pick_prev + en.rb, FH_NOKEY);
+                    if (en.key & FH_HOOKED) {
+                        // accepted last round, en.ra hooked: its size flows to the root it ended under
+                        const int R = uf_find(A.parent, en.ra);
+                        atomicAdd(A.size + R, __ldcg(A.size + en.ra));
+                        __stcg(A.lastw + R, (int)((en.key >> 32) & 0x3FFu));
+                    } else if (!(en.key & FH_REJECT)) {
+                        uf_find2(A.parent, en.ra, en.rb);
+                        live = en.ra != en.rb;
+                    }
+                } else if (pos < total) {
+                    const uint32_t e = A.elist[band_lo[vi] + new_lo + (pos - my_src)];
+                    en.key = ((unsigned long long)A.ew[e] << 32) | e;
+                    en.ra = (int)(e >> 1);
+                    en.rb = en.ra + ((e & 1u) ? A.W : 1);
+                    uf_find2(A.parent, en.ra, en.rb);
+                    live = en.ra != en.rb;
+                }
+                if (live) {
+                    atomicMin(pick + en.ra, en.key);
+                    atomicMin(pick + en.rb, en.key);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, live);
+                if (bal) {
+                    int off = 0;
+                    if (lane == 0) off = atomicAdd(&s_cnt, __popc(bal));
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (live) dst[off + __popc(bal & ((1u << lane) - 1))] = en;
+                }
+                visits++;
+            }
+            __syncthreads();
+            const int my_cnt = s_cnt;
+            if (threadIdx.x == 0 && my_cnt) atomicAdd(AA.gcnt + 2 * round + vi, my_cnt);
             FH_T(tA);
-            const int nlive = cluster_sum(live);
+            FH_BAR();
             FH_T(tS);
-            if (nlive == 0) break;
-            // phase B: picked edges join the forest; the picking component hooks under the other one
-            int remain = 0;
-            if (single) {
-                if (e1 != S3_DEAD) remain = phase_b(e1, ra1, rb1, fl1);
-            } else {
-                for (int pos = lo + gtid; pos < hi; pos += gstride) {
-                    const uint32_t e = A.elist[pos];
-                    if (e == S3_DEAD) continue;
-                    uint8_t fl;
-                    remain += phase_b(e, A.e_ra[pos], A.e_rb[pos], fl);
-                    A.e_flag[pos] = fl;
+            for (int v = 0; v < nviews; v++) n_live[v] = __ldcg(AA.gcnt + 2 * round + v);
+            // ---- phase 2: decide every edge that is the minimum of one of its components
+            for (int pos = threadIdx.x; pos < my_cnt; pos += blockDim.x) {
+                FHEntry en = dst[pos];
+                const unsigned long long ka = __ldcg(pick + en.ra), kb = __ldcg(pick + en.rb);
+                const int wa = (int)(ka >> 32), wb = (int)(kb >> 32), w = (int)(en.key >> 32);
+                if (!uf_open(A, en.ra, wa) || !uf_open(A, en.rb, wb)) {  // (1): a dead endpoint
+                    dst[pos].key = en.key | FH_REJECT;
+                    continue;
+                }
+                const bool pa = ka == en.key, pb = kb == en.key;
+                if (!(pa || pb)) continue;
+                if ((pa && pb) || (pa && wb == w) || (pb && wa == w)) {  // (2), (3)
+                    A.mask[(uint32_t)en.key] = 1;
+                    int frm, to;
+                    if (pa && pb) {  // only one side of a mutual pick hooks: the smaller component goes under the larger (shorter paths)
+                        const int sa = __ldcg(A.size + en.ra), sb = __ldcg(A.size + en.rb);
+                        const bool a_hooks = sa < sb || (sa == sb && en.ra > en.rb);
+                        frm = a_hooks ? en.ra : en.rb; to = a_hooks ? en.rb : en.ra;
+                    }
+                    else if (pa) { frm = en.ra; to = en.rb; }
+                    else { frm = en.rb; to = en.ra; }
+                    __stcg(A.parent + frm, to);
+                    en.key |= FH_HOOKED;
+                    en.ra = frm; en.rb = to;
+                    dst[pos] = en;
                 }
             }
             FH_T(tB);
-            const int nrem = cluster_sum(remain);
+            FH_BAR();
             FH_T(tS);
-            // phase C: sizes flow to the new roots, picks are cleared
-            if (single) {
-                if (e1 != S3_DEAD) {
-                    phase_c(ra1, rb1, fl1, w);
-                    if (fl1 & 4) e1 = S3_DEAD;
-                }
-            } else {
-                for (int pos = lo + gtid; pos < hi; pos += gstride) {
-                    const uint32_t e = A.elist[pos];
-                    if (e == S3_DEAD) continue;
-                    const uint8_t fl = A.e_flag[pos];
-                    phase_c(A.e_ra[pos], A.e_rb[pos], fl, w);
-                    if (fl & 4) A.elist[pos] = S3_DEAD;
-                }
-            }
-            FH_T(tC);
-            grid.sync();
-            FH_T(tS);
-            if (nrem == 0) break;  // every live edge of the level joined: nothing left to pick
+            my_src = my_cnt;
+            par ^= 1;
         }
     }
     if (gtid == 0) {
         A.counters[S3_MAX_ROUNDS - 8] = (int)(tA >> 10); A.counters[S3_MAX_ROUNDS - 7] = (int)(tB >> 10);
-        A.counters[S3_MAX_ROUNDS - 6] = (int)(tC >> 10); A.counters[S3_MAX_ROUNDS - 5] = (int)(tS >> 10);
-        A.counters[S3_MAX_ROUNDS - 9] = nlev; A.counters[S3_MAX_ROUNDS - 10] = round;
+        A.counters[S3_MAX_ROUNDS - 6] = (int)(visits); A.counters[S3_MAX_ROUNDS - 5] = (int)(tS >> 10);
+        A.counters[S3_MAX_ROUNDS - 9] = 0; A.counters[S3_MAX_ROUNDS - 10] = round;
         tA = 0;
     }
     t0 = clock64();
 
     // ------------------------------------------------------------------ min-size merge
-    grid.sync();
     const int E2 = 2 * A.N;
     for (int base = cbase; base < E2; base += gstride) {  // warp-uniform trip count
         const int e = base + threadIdx.x;
         bool cand = false;
         if (e < E2 && A.ew[e] != S3_NO_EDGE) {
-            const int a = e >> 1, b = a + ((e & 1) ? A.W : 1);
-            const int ra = uf_find(A.parent, a), rb = uf_find(A.parent, b);
+            int ra = e >> 1, rb = ra + ((e & 1) ? A.W : 1);
+            uf_find2(A.parent, ra, rb);
             cand = ra != rb && (__ldcg(A.size + ra) < A.m || __ldcg(A.size + rb) < A.m);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         if (bal) {
-            const int lane = threadIdx.x & 31;
             int off = 0;
             if (lane == 0) off = atomicAdd(A.counters + CNT_LIST, __popc(bal));
             off = __shfl_sync(0xffffffffu, off, 0);
             if (cand) A.elist[off + __popc(bal & ((1u << lane) - 1))] = (uint32_t)e;
         }
     }
-    grid.sync();
+    FH_BAR();
     const int nlist = __ldcg(A.counters + CNT_LIST);
     while (true) {
         if (round >= ROUND_CAP) {
@@ -274,8 +335,8 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
         for (int pos = gtid; pos < nlist; pos += gstride) {
             const uint32_t e = A.elist[pos];
             if (e == S3_DEAD) continue;
-            const int a = (int)(e >> 1), b = a + ((e & 1u) ? A.W : 1);
-            const int ra = uf_find(A.parent, a), rb = uf_find(A.parent, b);
+            int ra = (int)(e >> 1), rb = ra + ((e & 1u) ? A.W : 1);
+            uf_find2(A.parent, ra, rb);
             if (ra == rb) {
                 A.elist[pos] = S3_DEAD;
                 continue;
@@ -293,10 +354,10 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             A.e_flag[pos] = (uint8_t)((fa ? 1 : 0) | (fb ? 2 : 0));
             live++;
         }
-        block_sum_to_counter(live, A.counters + round);
-        grid.sync();
-        const int nlive = __ldcg(A.counters + round);
         round++;
+        block_sum_to_counter(live, AA.gcnt + 2 * round);  // both views add into one counter: the loop ends for both together
+        FH_BAR();
+        const int nlive = __ldcg(AA.gcnt + 2 * round);
         if (nlive == 0) break;
         for (int pos = gtid; pos < nlist; pos += gstride) {
             const uint32_t e = A.elist[pos];
@@ -316,7 +377,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                 A.e_flag[pos] = fl | 4;
             }
         }
-        grid.sync();
+        FH_BAR();
         for (int pos = gtid; pos < nlist; pos += gstride) {
             const uint32_t e = A.elist[pos];
             if (e == S3_DEAD) continue;
@@ -324,20 +385,21 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             __stcg(A.resv + A.e_rb[pos], ~0ull);
             if (A.e_flag[pos] & 4) A.elist[pos] = S3_DEAD;
         }
-        grid.sync();
+        FH_BAR();
     }
     FH_T(tA);
     if (gtid == 0) { A.counters[CNT_ROUNDS] = round; A.counters[S3_MAX_ROUNDS - 11] = (int)(tA >> 10); }
 }
 
-__global__ void k_uf_init(int N, int* parent, int* size, int* lastw, uint32_t* best, unsigned long long* resv,
-                          int* minpix) {
+__global__ void k_uf_init(int N, int* parent, int* size, int* lastw, unsigned long long* pick0, unsigned long long* pick1,
+                          unsigned long long* resv, int* minpix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     parent[i] = i;
     size[i] = 1;
     lastw[i] = 0;
-    best[i] = S3_DEAD;
+    pick0[i] = FH_NOKEY;
+    pick1[i] = FH_NOKEY;
     resv[i] = ~0ull;
     minpix[i] = 0x7fffffff;
 }
@@ -371,15 +433,30 @@ __global__ void k_label_ids(int N, const int* __restrict__ root_of, const int* _
     atomicAdd(tree_size + t, 1);
 }
 
+// ---- per-pixel forest adjacency: the integer weights of the forest edges to the (up, left, right, down) neighbours,
+// S3_NO_EDGE where the grid edge is not in the forest — one 8-byte record instead of 4 mask + 4 weight gathers per node
+__global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const uint8_t* __restrict__ mask, ushort4* __restrict__ adjw) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int x = p % W, y = p / W;
+    ushort4 a = make_ushort4(S3_NO_EDGE, S3_NO_EDGE, S3_NO_EDGE, S3_NO_EDGE);
+    if (y > 0 && mask[2 * (p - W) + 1]) a.x = ew[2 * (p - W) + 1];
+    if (x > 0 && mask[2 * (p - 1)]) a.y = ew[2 * (p - 1)];
+    if (x < W - 1 && mask[2 * p]) a.z = ew[2 * p];
+    if (y < H - 1 && mask[2 * p + 1]) a.w = ew[2 * p + 1];
+    adjw[p] = a;
+}
+
 // ---- BFS re-indexing, one CTA per tree
 #define BFS_THREADS 256
+#define BFS_FRONT 2048  // frontier entries kept in shared memory per level (wider levels go through global memory)
 struct BfsArgs {
     int T;
     const int* unit_tree;
     const int* tree_start;
     const int* tree_rootpix;
-    const uint16_t* ew;
-    const uint8_t* mask;
+    const ushort4* adjw;
+    uint32_t* front;  // [N] frontier words by node (pixel | direction of the parent << 28), the wide-level fallback
     int* node_pixel;
     int* pixel_node;
     int* parent;
@@ -397,21 +474,28 @@ struct BfsArgs2 {
     int W, H, NN;
     int grid0;  // CTAs [0, grid0) serve v[0], the rest v[1]: both views' trees re-indexed by one launch
 };
+// Level-synchronous BFS from the tree's minimum pixel.  The reference's queue order (Stereo3DMST.cpp:477-518) is:
+// nodes of a level in order, each appending its unvisited neighbours in adjacency order = the order their edges
+// were inserted = sorted-edge order (w, edge id); for equal w the edge ids order the directions up < left < right <
+// down.  A block-wide exclusive scan of the child counts reproduces that numbering.
+// Per level the dependent chain is: frontier word (shared memory) -> adjacency record (L1: the lines of a node's
+// neighbours are prefetched when the node is discovered, two levels before they are needed) -> scan -> frontier.
 __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     const int vi = (int)blockIdx.x >= AA.grid0;
     const BfsArgs& B = AA.v[vi];
     const int bid = vi ? blockIdx.x - AA.grid0 : blockIdx.x, nb = vi ? gridDim.x - AA.grid0 : AA.grid0;
-    const int T = B.T, W = AA.W, H = AA.H, NN = AA.NN;
+    const int T = B.T, W = AA.W, NN = AA.NN;
     const int* __restrict__ unit_tree = B.unit_tree;
     const int* __restrict__ tree_start = B.tree_start;
     const int* __restrict__ tree_rootpix = B.tree_rootpix;
-    const uint16_t* __restrict__ ew = B.ew;
-    const uint8_t* __restrict__ mask = B.mask;
+    const ushort4* __restrict__ adjw = B.adjw;
+    uint32_t* front = B.front;
     int* node_pixel = B.node_pixel; int* pixel_node = B.pixel_node; int* parent = B.parent; int* level = B.level;
     uint16_t* pw = B.pw; NodeUp* node_up = B.node_up; int4* node_dn = B.node_dn; int* lvl_start = B.lvl_start;
     int* tree_depth = B.tree_depth; int4* tile_desc = B.tile_desc; int* tree_ntiles = B.tree_ntiles;
     __shared__ int s_warp[BFS_THREADS / 32];
     __shared__ int s_total;
+    __shared__ uint32_t s_front[2][BFS_FRONT];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int u = bid; u < T; u += nb) {
         const int t = unit_tree[u];
@@ -426,43 +510,38 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             pw[base] = 0;
             node_dn[base] = make_int4(base, 0, 0, rp);
             lvl[0] = base;
+            s_front[0][0] = (uint32_t)rp | (4u << 28);  // direction 4 = no parent
+            front[base] = (uint32_t)rp | (4u << 28);
         }
         __syncthreads();
-        int a = base, b = base + 1, L = 0;
+        int a = base, b = base + 1, L = 0, cur = 0;
         while (a < b) {
             int run = 0;  // children emitted so far for this level (uniform)
+            const bool in_smem = b - a <= BFS_FRONT;
             for (int chunk = a; chunk < b; chunk += BFS_THREADS) {
                 const int g = chunk + tid;
                 int cc = 0;
-                int q[4];
-                uint32_t wq[4];
-                unsigned long long key[4];
+                uint32_t key[4];  // (w << 2) | direction rank; directions: 0 up, 1 left, 2 right, 3 down
+                int pix = 0;
                 if (g < b) {
-                    const int pix = node_pixel[g];
-                    const int ppix = node_pixel[parent[g]];
-                    const int x = pix % W, y = pix / W;
-                    // candidate neighbours: left, right, up, down — forest edges only
-                    int nq[4];
-                    int ne[4];
-                    nq[0] = pix - 1; ne[0] = x > 0 ? 2 * (pix - 1) : -1;
-                    nq[1] = pix + 1; ne[1] = x < W - 1 ? 2 * pix : -1;
-                    nq[2] = pix - W; ne[2] = y > 0 ? 2 * (pix - W) + 1 : -1;
-                    nq[3] = pix + W; ne[3] = y < H - 1 ? 2 * pix + 1 : -1;
+                    const uint32_t fw = in_smem ? s_front[cur][g - a] : front[g];
+                    pix = (int)(fw & 0x0FFFFFFFu);
+                    const int pdir = (int)(fw >> 28);
+                    const ushort4 aw = __ldg(adjw + pix);
+                    const uint32_t wv[4] = {aw.x, aw.y, aw.z, aw.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        if (ne[k] < 0 || nq[k] == ppix) continue;
-                        if (!mask[ne[k]]) continue;
-                        const uint32_t wv = ew[ne[k]];
-                        const unsigned long long kk = ((unsigned long long)wv << 32) | (uint32_t)ne[k];
+                        if (wv[k] == S3_NO_EDGE || k == pdir) continue;
+                        const uint32_t kk = (wv[k] << 2) | (uint32_t)k;
                         int j = cc++;  // insertion sort by (w, edge id)
                         while (j > 0 && key[j - 1] > kk) {
-                            key[j] = key[j - 1]; q[j] = q[j - 1]; wq[j] = wq[j - 1];
+                            key[j] = key[j - 1];
                             j--;
                         }
-                        key[j] = kk; q[j] = nq[k]; wq[j] = wv;
+                        key[j] = kk;
                     }
                 }
-                // block exclusive scan of cc
+                // block exclusive scan of cc (one barrier: every warp sums the warp totals itself)
                 int incl = cc;
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -470,46 +549,53 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                 }
                 if (lane == 31) s_warp[wid] = incl;
                 __syncthreads();
-                if (wid == 0) {
-                    int v = lane < BFS_THREADS / 32 ? s_warp[lane] : 0;
-                    int iv = v;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int u2 = __shfl_up_sync(0xffffffffu, iv, o);
-                        if (lane >= o) iv += u2;
-                    }
-                    if (lane < BFS_THREADS / 32) s_warp[lane] = iv - v;
-                    if (lane == 31) s_total = iv;
+                int wbase = 0, chunk_total = 0;
+#pragma unroll
+                for (int i = 0; i < BFS_THREADS / 32; i++) {
+                    const int v = s_warp[i];
+                    if (i < wid) wbase += v;
+                    chunk_total += v;
                 }
-                __syncthreads();
-                const int excl = incl - cc + s_warp[wid];
-                const int chunk_total = s_total;
+                const int excl = incl - cc + wbase;
                 if (g < b) {
                     const int cb = b + run + excl;
                     NodeUp nu;
                     nu.child_begin = cb;
                     nu.child_count = cc;
-                    nu.cw01 = (cc > 0 ? wq[0] : 0u) | ((cc > 1 ? wq[1] : 0u) << 16);
-                    nu.cw23 = (cc > 2 ? wq[2] : 0u) | ((cc > 3 ? wq[3] : 0u) << 16);
+                    nu.cw01 = (cc > 0 ? key[0] >> 2 : 0u) | ((cc > 1 ? key[1] >> 2 : 0u) << 16);
+                    nu.cw23 = (cc > 2 ? key[2] >> 2 : 0u) | ((cc > 3 ? key[3] >> 2 : 0u) << 16);
                     node_up[g] = nu;
+                    const bool next_smem = true;
                     for (int k = 0; k < cc; k++) {
                         const int h = cb + k;
-                        node_pixel[h] = q[k];
-                        pixel_node[q[k]] = h;
+                        const int dir = (int)(key[k] & 3u);
+                        const int q = pix + (dir == 0 ? -W : dir == 1 ? -1 : dir == 2 ? 1 : W);
+                        const uint32_t wq = key[k] >> 2;
+                        const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28);  // the parent lies in the opposite direction
+                        if (h - b < BFS_FRONT) s_front[cur ^ 1][h - b] = fw;
+                        front[h] = fw;
+                        node_pixel[h] = q;
+                        pixel_node[q] = h;
                         parent[h] = g;
                         level[h] = L + 1;
-                        pw[h] = (uint16_t)wq[k];
-                        node_dn[h] = make_int4(g, (int)wq[k], L + 1, q[k]);
+                        pw[h] = (uint16_t)wq;
+                        node_dn[h] = make_int4(g, (int)wq, L + 1, q);
+                        // the rows above and below q hold q's possible children: needed two levels from now
+                        if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
+                        if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
                     }
+                    (void)next_smem;
                 }
                 run += chunk_total;
-                __syncthreads();  // s_warp / s_total reuse + global writes visible to the block
+                __syncthreads();  // s_warp reuse; frontier words visible to the block
             }
             a = b;
             b = b + run;
             L++;
+            cur ^= 1;
             if (tid == 0) lvl[L] = a;
-            __syncthreads();
         }
+        __syncthreads();
         if (tid == 0) tree_depth[t] = L;
         // aggregation tiles (<= S3_TILE_NODES consecutive nodes of one level): one thread per level, block scan of the
         // per-level tile counts; written twice: root->leaf order (levels ascending) at [0,2N) and leaf->root order
@@ -565,41 +651,41 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
 static void fill_fh_args(s3dmst_ctx* ctx, View& V, FHArgs& A) {
     A.W = ctx->W; A.N = ctx->N; A.c = ctx->P.fh_c; A.m = std::max(2, ctx->P.min_cc_size);
     A.ew = V.ew; A.elist = V.elist; A.lvl_off = V.lvl_off;
-    A.parent = V.uf_parent; A.size = V.uf_size; A.lastw = V.uf_lastw; A.best = V.uf_best; A.resv = V.uf_resv;
+    A.parent = V.uf_parent; A.size = V.uf_size; A.lastw = V.uf_lastw; A.resv = V.uf_resv;
+    A.pick[0] = V.uf_pick[0]; A.pick[1] = V.uf_pick[1];
+    A.ent[0] = reinterpret_cast<FHEntry*>(V.fh_ent[0]); A.ent[1] = reinterpret_cast<FHEntry*>(V.fh_ent[1]);
+    static const int band_low = getenv("S3_FH_LOW") ? atoi(getenv("S3_FH_LOW")) : 8192;
+    static const int band_high = getenv("S3_FH_HIGH") ? atoi(getenv("S3_FH_HIGH")) : 32768;
+    A.band_low = band_low; A.band_high = band_high;
     A.mask = V.mask; A.e_ra = V.e_ra; A.e_rb = V.e_rb; A.e_flag = V.e_flag; A.counters = V.counters;
 }
 
-// FH + min-size merge for the views in `mask`, one cluster per view, one launch
+// FH + min-size merge for the views in `mask`: one cooperative launch, one CTA per SM, the grid split between the views
 int s3_fh_launch(s3dmst_ctx* ctx, int mask) {
     FHArgs2 AA;
+    memset(&AA, 0, sizeof AA);
     int nv = 0;
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) fill_fh_args(ctx, ctx->v[view], AA.v[nv++]);
     if (!nv) return 0;
-    static int cluster_size = 0;  // largest cluster this device schedules: 16 (non-portable) or 8
-    if (!cluster_size) {
-        cudaFuncSetAttribute(k_fh_merge, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaGetLastError();
-        for (int cs : {16, 8, 4, 2, 1}) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(cs * 2); cfg.blockDim = dim3(1024);
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, k_fh_merge, &cfg) == cudaSuccess && ncl >= 2) { cluster_size = cs; break; }
-            cudaGetLastError();
-        }
-        if (!cluster_size) return s3_fail(ctx, S3DMST_E_CUDA, "k_fh_merge: no cluster configuration is schedulable");
+    if (nv == 1) AA.v[1] = AA.v[0];
+    static int ctas_per_sm = -1;
+    if (ctas_per_sm < 0) {
+        int n = 0;
+        S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fh_merge, 1024, 0));
+        ctas_per_sm = n;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cluster_size * nv); cfg.blockDim = dim3(1024); cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    S3_CUDA(cudaLaunchKernelEx(&cfg, k_fh_merge, AA));
+    if (ctas_per_sm < 1) return s3_fail(ctx, S3DMST_E_CUDA, "k_fh_merge does not fit on an SM");
+    const int grid = std::max(nv, std::min(ctx->num_sms, S3_FH_MAX_CTAS));
+    const int per_view = grid / nv;
+    AA.nviews = nv;
+    AA.seg_cap = (2 * ctx->N + per_view - 1) / per_view + S3_FH_SEG_SLACK;
+    if (!ctx->fh_sync) S3_CUDA(cudaMalloc(&ctx->fh_sync, sizeof(int) * (2 * S3_MAX_ROUNDS + 64)));
+    S3_CUDA(cudaMemsetAsync(ctx->fh_sync, 0, sizeof(int) * (2 * S3_MAX_ROUNDS + 64), ctx->stream));
+    AA.bar = reinterpret_cast<unsigned*>(ctx->fh_sync);
+    AA.gcnt = ctx->fh_sync + 64;
+    void* args[] = {&AA};
+    S3_CUDA(cudaLaunchCooperativeKernel((const void*)k_fh_merge, dim3(grid), dim3(1024), args, 0, ctx->stream));
     ctx->launches++;
     return 0;
 }
@@ -629,7 +715,7 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
         View& V = ctx->v[view];
         V.forest_ready = false;
         S3_TRY(s3_image_stage(ctx, view));
-        k_uf_init<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.uf_parent, V.uf_size, V.uf_lastw, V.uf_best, V.uf_resv, V.minpix);
+        k_uf_init<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.uf_parent, V.uf_size, V.uf_lastw, V.uf_pick[0], V.uf_pick[1], V.uf_resv, V.minpix);
         S3_LAUNCH_CHECK();
         S3_CUDA(cudaMemsetAsync(V.counters, 0, sizeof(int) * S3_MAX_ROUNDS, ctx->stream));
         S3_CUDA(cudaMemsetAsync(V.mask, 0, 2 * (size_t)N, ctx->stream));
@@ -652,8 +738,8 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
         View& V = ctx->v[view];
         if (hc[view][15]) return s3_fail(ctx, S3DMST_E_LIMIT, "forest kernel hit the round cap");
         if (getenv("S3_DEBUG_FH"))
-            fprintf(stderr, "[fh view %d] levels %d fh-rounds %d total-rounds %d | kcycles A %d B %d C %d sync %d merge %d\n", view, hc[view][7], hc[view][6],
-                    hc[view][13], hc[view][8], hc[view][9], hc[view][10], hc[view][11], hc[view][5]);
+            fprintf(stderr, "[fh view %d] fh-rounds %d total-rounds %d visits/thread %d | kcycles phase1 %d phase2 %d sync %d merge %d\n", view, hc[view][6],
+                    hc[view][13], hc[view][10], hc[view][8], hc[view][9], hc[view][11], hc[view][5]);
         const int T = hc[view][16 - (S3_MAX_ROUNDS - CNT_FIRSTS)];
         if (T <= 0 || T > N) return s3_fail(ctx, S3DMST_E_CUDA, "labelling produced T=%d", T);
         V.T = T;
@@ -694,7 +780,7 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
         S3_CUDA(cudaMemcpyAsync(V.tree_start, V.h_tree_start.data(), sizeof(int) * (T + 1), cudaMemcpyHostToDevice, ctx->stream));
         S3_CUDA(cudaMemcpyAsync(V.unit_tree, V.h_unit_tree.data(), sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
         BfsArgs& B = BA.v[nv];
-        B.T = T; B.unit_tree = V.unit_tree; B.tree_start = V.tree_start; B.tree_rootpix = V.tree_rootpix; B.ew = V.ew; B.mask = V.mask;
+        B.T = T; B.unit_tree = V.unit_tree; B.tree_start = V.tree_start; B.tree_rootpix = V.tree_rootpix; B.adjw = V.adjw; B.front = V.bfs_front;
         B.node_pixel = V.node_pixel; B.pixel_node = V.pixel_node; B.parent = V.parent; B.level = V.level; B.pw = V.pw;
         B.node_up = V.node_up; B.node_dn = V.node_dn; B.lvl_start = V.lvl_start; B.tree_depth = V.tree_depth;
         B.tile_desc = V.tile_desc; B.tree_ntiles = V.tree_ntiles;
@@ -704,6 +790,12 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
         nv++;
     }
     if (nv == 1) BA.v[1] = BA.v[0];
+    for (int view = 0; view < 2; view++)
+        if (mask & (1 << view)) {
+            View& V = ctx->v[view];
+            k_pix_adj<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(W, H, V.ew, V.mask, V.adjw);
+            S3_LAUNCH_CHECK();
+        }
     k_bfs<<<grid, BFS_THREADS, 0, ctx->stream>>>(BA);
     S3_LAUNCH_CHECK();
     for (int view = 0; view < 2; view++)

@@ -33,7 +33,8 @@ struct View {
     int* uf_parent = nullptr;  // [N]
     int* uf_size = nullptr;    // [N]
     int* uf_lastw = nullptr;   // [N]
-    uint32_t* uf_best = nullptr;        // [N] Boruvka pick (edge id)
+    unsigned long long* uf_pick[2] = {nullptr, nullptr};  // [N] minimum live edge key per component (FH rounds, by parity)
+    void* fh_ent[2] = {nullptr, nullptr};                 // [2N] x 16 B live-edge lists of the FH rounds (ping-pong)
     unsigned long long* uf_resv = nullptr;  // [N] merge reservation key
     uint8_t* mask = nullptr;   // [2N] 0/1/2
     uint32_t* elist = nullptr; // [2N] edge ids bucketed by weight, later the merge candidate list
@@ -44,6 +45,8 @@ struct View {
     int* lvl_off = nullptr;    // [S3_NUM_W+1] bucket offsets
     int* lvl_cursor = nullptr; // [S3_NUM_W]
     int* counters = nullptr;   // [S3_MAX_ROUNDS] per-round live counters + misc
+    ushort4* adjw = nullptr;   // [N] forest-edge weights to the (up, left, right, down) neighbours, S3_NO_EDGE if none
+    uint32_t* bfs_front = nullptr;  // [N] BFS frontier words by node
     // ---- labelling
     int* minpix = nullptr;     // [N] min pixel of the component rooted here
     int* scan_tmp = nullptr;   // [N] + block sums
@@ -108,11 +111,14 @@ struct s3dmst_ctx {
     // scratch for PMS
     uint32_t* units_dev = nullptr;  // aggregation work units (view<<31 | tree), longest first
     size_t units_cap = 0;
+    int* fh_sync = nullptr;         // grid barrier + per-round live counters of the forest kernel
     void* pms_scratch = nullptr;
     size_t pms_scratch_cap = 0;
 };
 
 #define S3_MAX_ROUNDS 65536
+#define S3_FH_MAX_CTAS 256        // upper bound on the cooperative grid of the forest kernel
+#define S3_FH_SEG_SLACK 1024      // per-CTA slack of the live-edge list segments (one ingest event adds < 1 entry per CTA beyond its share)
 
 // error helpers ---------------------------------------------------------------------------------
 int s3_fail(s3dmst_ctx* c, int code, const char* fmt, ...);
