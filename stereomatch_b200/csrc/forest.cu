@@ -433,29 +433,44 @@ __global__ void k_label_ids(int N, const int* __restrict__ root_of, const int* _
     atomicAdd(tree_size + t, 1);
 }
 
-// ---- per-pixel forest adjacency: the integer weights of the forest edges to the (up, left, right, down) neighbours,
-// S3_NO_EDGE where the grid edge is not in the forest — one 8-byte record instead of 4 mask + 4 weight gathers per node
-__global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const uint8_t* __restrict__ mask, ushort4* __restrict__ adjw) {
+// ---- per-pixel forest adjacency, pre-sorted: four 16-bit entries (w << 2) | direction (0 up, 1 left, 2 right, 3 down) in
+// ascending order = the order the reference's per-vertex adjacency lists hold them (edges are inserted in sorted-edge
+// order (w, a, b), Stereo3DMST.cpp:436-445; for equal w the edge ids order the directions up < left < right < down);
+// 0xFFFF = no forest edge.  One 8-byte record per BFS node instead of 4 mask + 4 weight gathers and a sort.
+__global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const uint8_t* __restrict__ mask,
+                          unsigned long long* __restrict__ adjw) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= W * H) return;
     const int x = p % W, y = p / W;
-    ushort4 a = make_ushort4(S3_NO_EDGE, S3_NO_EDGE, S3_NO_EDGE, S3_NO_EDGE);
-    if (y > 0 && mask[2 * (p - W) + 1]) a.x = ew[2 * (p - W) + 1];
-    if (x > 0 && mask[2 * (p - 1)]) a.y = ew[2 * (p - 1)];
-    if (x < W - 1 && mask[2 * p]) a.z = ew[2 * p];
-    if (y < H - 1 && mask[2 * p + 1]) a.w = ew[2 * p + 1];
-    adjw[p] = a;
+    uint32_t e[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+    if (y > 0 && mask[2 * (p - W) + 1]) e[0] = ((uint32_t)ew[2 * (p - W) + 1] << 2) | 0u;
+    if (x > 0 && mask[2 * (p - 1)]) e[1] = ((uint32_t)ew[2 * (p - 1)] << 2) | 1u;
+    if (x < W - 1 && mask[2 * p]) e[2] = ((uint32_t)ew[2 * p] << 2) | 2u;
+    if (y < H - 1 && mask[2 * p + 1]) e[3] = ((uint32_t)ew[2 * p + 1] << 2) | 3u;
+#define S3_CSWAP(i, j) { const uint32_t lo = min(e[i], e[j]), hi = max(e[i], e[j]); e[i] = lo; e[j] = hi; }
+    S3_CSWAP(0, 1) S3_CSWAP(2, 3) S3_CSWAP(0, 2) S3_CSWAP(1, 3) S3_CSWAP(1, 2)
+#undef S3_CSWAP
+    adjw[p] = (unsigned long long)e[0] | ((unsigned long long)e[1] << 16) | ((unsigned long long)e[2] << 32) | ((unsigned long long)e[3] << 48);
 }
 
 // ---- BFS re-indexing, one CTA per tree
 #define BFS_THREADS 256
+#ifndef BFS_INSTR
+#define BFS_INSTR 0
+#endif
+#if BFS_INSTR
+#define BFS_CLK(acc) do { const long long c__ = clock64(); acc += c__ - tq; tq = c__; } while (0)
+#else
+#define BFS_CLK(acc) do { } while (0)
+#endif
 #define BFS_FRONT 2048  // frontier entries kept in shared memory per level (wider levels go through global memory)
 struct BfsArgs {
     int T;
     const int* unit_tree;
     const int* tree_start;
     const int* tree_rootpix;
-    const ushort4* adjw;
+    const unsigned long long* adjw;
+    int* dbg_out;     // development counters (4 ints)
     uint32_t* front;  // [N] frontier words by node (pixel | direction of the parent << 28), the wide-level fallback
     int* node_pixel;
     int* pixel_node;
@@ -473,13 +488,44 @@ struct BfsArgs2 {
     BfsArgs v[2];
     int W, H, NN;
     int grid0;  // CTAs [0, grid0) serve v[0], the rest v[1]: both views' trees re-indexed by one launch
+    int dbg;    // development knobs: 1 = no warm-up loads, 2 = no tile descriptors
 };
+
+#if BFS_INSTR
+__device__ long long g_dummy;
+#endif
+// One node of one BFS level: decode the frontier word, fetch the adjacency record, drop the parent entry.
+// Returns the child count; `kids` = the (at most 4) child entries in order, 0xFFFF-padded.
+__device__ __forceinline__ int bfs_expand(uint32_t fw, const unsigned long long* __restrict__ adjw, int& pix, unsigned long long& kids, long long& g_ldg_cycles) {
+    pix = (int)(fw & 0x0FFFFFFFu);
+    const uint32_t pdir = fw >> 28;
+#if BFS_INSTR
+    const long long tl0 = clock64();
+#endif
+    const unsigned long long rec = __ldg(adjw + pix);
+#if BFS_INSTR
+    if (rec == 0x1234567812345678ull) pix++;
+    g_ldg_cycles += clock64() - tl0;
+#endif
+    // position of the parent's entry (4 = none: the root, whose pdir is 4)
+    const uint32_t e0 = (uint32_t)rec & 0xFFFFu, e1 = (uint32_t)(rec >> 16) & 0xFFFFu, e2 = (uint32_t)(rec >> 32) & 0xFFFFu, e3 = (uint32_t)(rec >> 48);
+    const int pp = (e0 != 0xFFFFu && (e0 & 3u) == pdir) ? 0 : (e1 != 0xFFFFu && (e1 & 3u) == pdir) ? 1 : (e2 != 0xFFFFu && (e2 & 3u) == pdir) ? 2
+                   : (e3 != 0xFFFFu && (e3 & 3u) == pdir) ? 3 : 4;
+    const int nvalid = (e0 != 0xFFFFu) + (e1 != 0xFFFFu) + (e2 != 0xFFFFu) + (e3 != 0xFFFFu);
+    // delete element pp from the sorted list (invalid entries sort last, so the rest stays in order)
+    const unsigned long long lowmask = pp >= 4 ? ~0ull : ((1ull << (16 * pp)) - 1ull);
+    const unsigned long long hi = pp >= 3 ? 0ull : (rec >> (16 * (pp + 1))) << (16 * pp);
+    kids = pp >= 4 ? rec : ((rec & lowmask) | hi | (0xFFFFull << 48));
+    return nvalid - (pp < 4 ? 1 : 0);
+}
+
 // Level-synchronous BFS from the tree's minimum pixel.  The reference's queue order (Stereo3DMST.cpp:477-518) is:
-// nodes of a level in order, each appending its unvisited neighbours in adjacency order = the order their edges
-// were inserted = sorted-edge order (w, edge id); for equal w the edge ids order the directions up < left < right <
-// down.  A block-wide exclusive scan of the child counts reproduces that numbering.
-// Per level the dependent chain is: frontier word (shared memory) -> adjacency record (L1: the lines of a node's
-// neighbours are prefetched when the node is discovered, two levels before they are needed) -> scan -> frontier.
+// nodes of a level in order, each appending its unvisited neighbours in adjacency order.  An exclusive scan of the
+// child counts over the level reproduces that numbering.
+// A tree level here is a handful of nodes (median 10 at C2) and the deepest tree has > 1000 levels, so what bounds
+// the kernel is the number of dependent instructions ONE warp executes per level.  Levels of <= 32 nodes are run by
+// warp 0 alone (no block barrier, ballot-based scan); the adjacency records are pre-sorted; the lines holding a
+// node's possible grandchildren are pulled into L1 when the node is discovered, two levels before they are needed.
 __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     const int vi = (int)blockIdx.x >= AA.grid0;
     const BfsArgs& B = AA.v[vi];
@@ -488,60 +534,96 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     const int* __restrict__ unit_tree = B.unit_tree;
     const int* __restrict__ tree_start = B.tree_start;
     const int* __restrict__ tree_rootpix = B.tree_rootpix;
-    const ushort4* __restrict__ adjw = B.adjw;
+    const unsigned long long* __restrict__ adjw = B.adjw;
     uint32_t* front = B.front;
-    int* node_pixel = B.node_pixel; int* pixel_node = B.pixel_node; int* parent = B.parent; int* level = B.level;
-    uint16_t* pw = B.pw; NodeUp* node_up = B.node_up; int4* node_dn = B.node_dn; int* lvl_start = B.lvl_start;
+    int* pixel_node = B.pixel_node;
+    NodeUp* node_up = B.node_up; int4* node_dn = B.node_dn; int* lvl_start = B.lvl_start;
     int* tree_depth = B.tree_depth; int4* tile_desc = B.tile_desc; int* tree_ntiles = B.tree_ntiles;
     __shared__ int s_warp[BFS_THREADS / 32];
     __shared__ int s_total;
+    __shared__ int s_state[4];
     __shared__ uint32_t s_front[2][BFS_FRONT];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool warm = !(AA.dbg & 1);
     for (int u = bid; u < T; u += nb) {
         const int t = unit_tree[u];
         const int base = tree_start[t];
         int* lvl = lvl_start + base + t;
         if (tid == 0) {
             const int rp = tree_rootpix[t];
-            node_pixel[base] = rp;
             pixel_node[rp] = base;
-            parent[base] = base;
-            level[base] = 0;
-            pw[base] = 0;
             node_dn[base] = make_int4(base, 0, 0, rp);
             lvl[0] = base;
             s_front[0][0] = (uint32_t)rp | (4u << 28);  // direction 4 = no parent
-            front[base] = (uint32_t)rp | (4u << 28);
         }
         __syncthreads();
         int a = base, b = base + 1, L = 0, cur = 0;
-        while (a < b) {
+        const long long tb0 = clock64();
+        long long tq = tb0, q_load = 0, q_scan = 0, q_store = 0, q_sync = 0, q_ldg = 0;
+        (void)q_ldg; (void)tq; (void)q_load; (void)q_scan; (void)q_store; (void)q_sync;
+        // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record
+        auto emit = [&](int g, int pix, int cc, unsigned long long kids, int cb, int bnext, int Lc, int curc) {
+            NodeUp nu;
+            nu.child_begin = cb;
+            nu.child_count = cc;
+            const uint32_t k0 = (uint32_t)kids & 0xFFFFu, k1 = (uint32_t)(kids >> 16) & 0xFFFFu, k2 = (uint32_t)(kids >> 32) & 0xFFFFu, k3 = (uint32_t)(kids >> 48);
+            nu.cw01 = (cc > 0 ? k0 >> 2 : 0u) | ((cc > 1 ? k1 >> 2 : 0u) << 16);
+            nu.cw23 = (cc > 2 ? k2 >> 2 : 0u) | ((cc > 3 ? k3 >> 2 : 0u) << 16);
+            node_up[g] = nu;
+            unsigned long long kk = kids;
+            for (int k = 0; k < cc; k++, kk >>= 16) {
+                const uint32_t en = (uint32_t)kk & 0xFFFFu;
+                const int dir = (int)(en & 3u);
+                const int q = pix + (dir == 0 ? -W : dir == 1 ? -1 : dir == 2 ? 1 : W);
+                const int h = cb + k;
+                const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28);  // the parent lies in the opposite direction
+                if (h - bnext < BFS_FRONT) s_front[curc ^ 1][h - bnext] = fw;
+                else front[h] = fw;
+                pixel_node[q] = h;
+                node_dn[h] = make_int4(g, (int)(en >> 2), Lc + 1, q);
+                if (warm) {  // q's possible children: rows above and below (q +- 1 share q's line)
+                    if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
+                    if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
+                }
+            }
+        };
+        while (true) {
+            // ---- runs of narrow levels: warp 0 alone, no block barrier
+            if (wid == 0) {
+                while (a < b && b - a <= 32) {
+                    int cc = 0, pix = 0;
+                    unsigned long long kids = 0;
+                    const int g = a + lane;
+                    if (g < b) cc = bfs_expand(s_front[cur][lane], adjw, pix, kids, q_ldg);
+                    BFS_CLK(q_load);
+                    // exclusive prefix of cc (0..4) from three independent ballots
+                    const uint32_t b0 = __ballot_sync(0xffffffffu, cc & 1), b1 = __ballot_sync(0xffffffffu, cc & 2), b2 = __ballot_sync(0xffffffffu, cc & 4);
+                    const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+                    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                    BFS_CLK(q_scan);
+                    if (g < b) emit(g, pix, cc, kids, b + excl, b, L, cur);
+                    a = b;
+                    b += total;
+                    L++;
+                    cur ^= 1;
+                    if (lane == 0) lvl[L] = a;
+                    BFS_CLK(q_store);
+                    __syncwarp();
+                    BFS_CLK(q_sync);
+                }
+                if (lane == 0) { s_state[0] = a; s_state[1] = b; s_state[2] = L; s_state[3] = cur; }
+            }
+            __syncthreads();
+            a = s_state[0]; b = s_state[1]; L = s_state[2]; cur = s_state[3];
+            if (a >= b) break;
+            // ---- one wide level: the whole block, chunks of BFS_THREADS nodes
             int run = 0;  // children emitted so far for this level (uniform)
-            const bool in_smem = b - a <= BFS_FRONT;
             for (int chunk = a; chunk < b; chunk += BFS_THREADS) {
                 const int g = chunk + tid;
-                int cc = 0;
-                uint32_t key[4];  // (w << 2) | direction rank; directions: 0 up, 1 left, 2 right, 3 down
-                int pix = 0;
-                if (g < b) {
-                    const uint32_t fw = in_smem ? s_front[cur][g - a] : front[g];
-                    pix = (int)(fw & 0x0FFFFFFFu);
-                    const int pdir = (int)(fw >> 28);
-                    const ushort4 aw = __ldg(adjw + pix);
-                    const uint32_t wv[4] = {aw.x, aw.y, aw.z, aw.w};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (wv[k] == S3_NO_EDGE || k == pdir) continue;
-                        const uint32_t kk = (wv[k] << 2) | (uint32_t)k;
-                        int j = cc++;  // insertion sort by (w, edge id)
-                        while (j > 0 && key[j - 1] > kk) {
-                            key[j] = key[j - 1];
-                            j--;
-                        }
-                        key[j] = kk;
-                    }
-                }
-                // block exclusive scan of cc (one barrier: every warp sums the warp totals itself)
+                int cc = 0, pix = 0;
+                unsigned long long kids = 0;
+                if (g < b) cc = bfs_expand(g - a < BFS_FRONT ? s_front[cur][g - a] : front[g], adjw, pix, kids, q_ldg);
                 int incl = cc;
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -556,36 +638,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                     if (i < wid) wbase += v;
                     chunk_total += v;
                 }
-                const int excl = incl - cc + wbase;
-                if (g < b) {
-                    const int cb = b + run + excl;
-                    NodeUp nu;
-                    nu.child_begin = cb;
-                    nu.child_count = cc;
-                    nu.cw01 = (cc > 0 ? key[0] >> 2 : 0u) | ((cc > 1 ? key[1] >> 2 : 0u) << 16);
-                    nu.cw23 = (cc > 2 ? key[2] >> 2 : 0u) | ((cc > 3 ? key[3] >> 2 : 0u) << 16);
-                    node_up[g] = nu;
-                    const bool next_smem = true;
-                    for (int k = 0; k < cc; k++) {
-                        const int h = cb + k;
-                        const int dir = (int)(key[k] & 3u);
-                        const int q = pix + (dir == 0 ? -W : dir == 1 ? -1 : dir == 2 ? 1 : W);
-                        const uint32_t wq = key[k] >> 2;
-                        const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28);  // the parent lies in the opposite direction
-                        if (h - b < BFS_FRONT) s_front[cur ^ 1][h - b] = fw;
-                        front[h] = fw;
-                        node_pixel[h] = q;
-                        pixel_node[q] = h;
-                        parent[h] = g;
-                        level[h] = L + 1;
-                        pw[h] = (uint16_t)wq;
-                        node_dn[h] = make_int4(g, (int)wq, L + 1, q);
-                        // the rows above and below q hold q's possible children: needed two levels from now
-                        if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
-                        if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
-                    }
-                    (void)next_smem;
-                }
+                if (g < b) emit(g, pix, cc, kids, b + run + incl - cc + wbase, b, L, cur);
                 run += chunk_total;
                 __syncthreads();  // s_warp reuse; frontier words visible to the block
             }
@@ -593,14 +646,16 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             b = b + run;
             L++;
             cur ^= 1;
-            if (tid == 0) lvl[L] = a;
+            if (tid == 0) { lvl[L] = a; s_state[0] = a; s_state[1] = b; s_state[2] = L; s_state[3] = cur; }
+            __syncthreads();
         }
         __syncthreads();
+        const long long tb1 = clock64();
         if (tid == 0) tree_depth[t] = L;
         // aggregation tiles (<= S3_TILE_NODES consecutive nodes of one level): one thread per level, block scan of the
         // per-level tile counts; written twice: root->leaf order (levels ascending) at [0,2N) and leaf->root order
         // (levels descending) at [2N,4N)
-        for (int dir = 0; dir < 2; dir++) {
+        for (int dir = 0; dir < ((AA.dbg & 2) ? 0 : 2); dir++) {
             int run_t = 0;
             for (int l0 = 0; l0 < L; l0 += BFS_THREADS) {
                 const int li = l0 + tid;                       // position in processing order
@@ -644,7 +699,23 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             if (tid == 0) tree_ntiles[t] = run_t;
         }
         __syncthreads();
+#if BFS_INSTR
+        if (u == 0 && tid == 0) printf("bfs cycles/level: load %lld (ldg %lld) scan %lld store %lld sync %lld\n", q_load / L, q_ldg / L, q_scan / L, q_store / L, q_sync / L);
+#endif
+        if (u == 0 && tid == 0) { B.dbg_out[0] = (int)((tb1 - tb0) >> 4); B.dbg_out[1] = (int)((clock64() - tb1) >> 4); B.dbg_out[2] = L; B.dbg_out[3] = b - base; }
     }
+}
+
+// node_dn -> the flat per-node arrays the other stages and the parity dumps read (off the BFS critical path)
+__global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __restrict__ node_pixel, int* __restrict__ parent,
+                             int* __restrict__ level, uint16_t* __restrict__ pw) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= N) return;
+    const int4 nd = node_dn[h];
+    parent[h] = nd.x;
+    pw[h] = (uint16_t)nd.y;
+    level[h] = nd.z;
+    node_pixel[h] = nd.w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -766,6 +837,7 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
     BfsArgs2 BA;
     memset(&BA, 0, sizeof BA);
     BA.W = W; BA.H = H; BA.NN = N;
+    BA.dbg = getenv("S3_BFS_DBG") ? atoi(getenv("S3_BFS_DBG")) : 0;
     int nv = 0, grid = 0;
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
@@ -780,7 +852,7 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
         S3_CUDA(cudaMemcpyAsync(V.tree_start, V.h_tree_start.data(), sizeof(int) * (T + 1), cudaMemcpyHostToDevice, ctx->stream));
         S3_CUDA(cudaMemcpyAsync(V.unit_tree, V.h_unit_tree.data(), sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
         BfsArgs& B = BA.v[nv];
-        B.T = T; B.unit_tree = V.unit_tree; B.tree_start = V.tree_start; B.tree_rootpix = V.tree_rootpix; B.adjw = V.adjw; B.front = V.bfs_front;
+        B.T = T; B.unit_tree = V.unit_tree; B.tree_start = V.tree_start; B.tree_rootpix = V.tree_rootpix; B.adjw = reinterpret_cast<const unsigned long long*>(V.adjw); B.front = V.bfs_front; B.dbg_out = V.counters + S3_MAX_ROUNDS - 30;
         B.node_pixel = V.node_pixel; B.pixel_node = V.pixel_node; B.parent = V.parent; B.level = V.level; B.pw = V.pw;
         B.node_up = V.node_up; B.node_dn = V.node_dn; B.lvl_start = V.lvl_start; B.tree_depth = V.tree_depth;
         B.tile_desc = V.tile_desc; B.tree_ntiles = V.tree_ntiles;
@@ -793,7 +865,7 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) {
             View& V = ctx->v[view];
-            k_pix_adj<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(W, H, V.ew, V.mask, V.adjw);
+            k_pix_adj<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(W, H, V.ew, V.mask, reinterpret_cast<unsigned long long*>(V.adjw));
             S3_LAUNCH_CHECK();
         }
     k_bfs<<<grid, BFS_THREADS, 0, ctx->stream>>>(BA);
@@ -801,8 +873,20 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) {
             View& V = ctx->v[view];
+            k_bfs_unpack<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_dn, V.node_pixel, V.parent, V.level, V.pw);
+            S3_LAUNCH_CHECK();
+        }
+    for (int view = 0; view < 2; view++)
+        if (mask & (1 << view)) {
+            View& V = ctx->v[view];
             V.h_tree_depth.resize(V.T);
             S3_CUDA(cudaMemcpyAsync(V.h_tree_depth.data(), V.tree_depth, sizeof(int) * V.T, cudaMemcpyDeviceToHost, ctx->stream));
+            if (getenv("S3_DEBUG_FH")) {
+                int d[4];
+                S3_CUDA(cudaMemcpy(d, V.counters + S3_MAX_ROUNDS - 30, sizeof d, cudaMemcpyDeviceToHost));
+                fprintf(stderr, "[bfs view %d] largest tree: %d nodes, %d levels, bfs %d kcycles (%.0f cycles/level), tiles %d kcycles\n", view, d[3], d[2], d[0] >> 6,
+                        16.0 * d[0] / std::max(1, d[2]), d[1] >> 6);
+            }
         }
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int view = 0; view < 2; view++)
