@@ -54,7 +54,7 @@ typedef struct s3dmst_params {
     int agg_threads;    /* 0 = auto; threads per CTA of the aggregation kernels (multiple of 32)    */
     int agg_cache_nodes;/* 0 = auto; nodes of a tree level cached in shared memory per CTA          */
     int agg_ring_nodes; /* 0 = auto; node rows staged ahead per CTA by the bulk-copy (TMA) pipeline      */
-    int agg_kernel;     /* 0 = auto (TMA-pipelined kernel), 1 = simple level-synchronous kernel         */
+    int agg_kernel;     /* 0 = auto (dataflow kernel), 1 = simple level-synchronous kernel, 2 = TMA tile kernel */
 } s3dmst_params;
 
 void s3dmst_default_params(s3dmst_params* p);

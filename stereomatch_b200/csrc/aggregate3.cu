@@ -1,0 +1,489 @@
+// stereomatch_b200/csrc/aggregate3.cu — tree-filter aggregation + WTA, dataflow kernel (default).
+//
+// Same arithmetic and HBM layout as aggregate.cu (see the header there): FP64 in the reference's association
+// order (src/Stereo3DMST.cpp:120-158, :173-185), node-major label-minor volumes, a lane owns the label pairs
+// label(h, e) = l0 + h*64 + 2*lane + e for the whole kernel.  What changes is the schedule.
+//
+// Measured on B200 (profiles/r01_agg2_full.txt): the level-synchronous kernels are bound by what every warp has
+// to execute between two block barriers — a tree level is ~10 nodes, the deepest tree of the C2 workload has 1401
+// levels, and a lone warp retires a dependent instruction only every 6-15 cycles, so a barrier interval costs
+// ~1100 cycles however the bytes arrive; 53 % of all warp samples sit in the barrier and the SM issues 0.9
+// instructions per cycle.  Here there is NO block barrier inside a pass:
+//   * The nodes of a tree are dealt round-robin to the warps in traversal order (descending BFS index on the way
+//     up, ascending on the way down).  A warp owns a node from start to finish.
+//   * A node waits only for what it really depends on: on the way up for its children, on the way down for its
+//     parent.  Completion is published as one word per warp ("last node finished", release/acquire in shared
+//     memory); warps finish their nodes in order, so node c is done iff its owner's word has passed c.
+//   * Everything that does not depend on other nodes (node record, edge weights, the node's own cost / running-sum
+//     row — loaded one iteration ahead into registers, with the rows pulled into L2 further ahead by one bulk
+//     prefetch per round) happens before the wait; the dependent part is
+//     poll -> shared-memory load -> DMUL/DADD chain -> shared-memory store -> publish, ~200 cycles per tree level.
+//   * Values are handed over through a shared-memory ring indexed by node index (R = 64 rows).  A child/parent
+//     further than NEAR = 32 nodes away (levels wider than ~16 nodes, where the chain has slack) is read from the
+//     copy in L2.  Ring rows are reused safely without per-row flags: a row of node x is only ever read by nodes
+//     closer than NEAR, so writing row x -/+ R waits until every warp's progress word has passed x -/+ (R - NEAR)
+//     (a warp max/min over the progress words, cached while it holds).
+// Several CTAs (trees) share an SM, so the issue slots one tree leaves empty while it waits are used by another.
+#include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "hd_math.h"
+#include "internal.h"
+
+#define A3_R 64      // ring rows (power of two)
+#define A3_NEAR 32   // a dependency closer than this goes through the ring
+#define A3_PF 6      // rounds ahead of the bulk L2 prefetch
+#ifndef A3_SLEEP
+#define A3_SLEEP 20  // ns a waiting warp yields the issue slot for between two polls
+#endif
+#ifndef A3_INSTR
+#define A3_INSTR 0
+#endif
+#if A3_INSTR
+#define A3_CLK(acc) do { const long long c__ = clock64(); acc += c__ - tq; tq = c__; } while (0)
+#else
+#define A3_CLK(acc) do { } while (0)
+#endif
+
+struct Agg3View {
+    const int* tree_start;
+    const NodeUp* node_up;
+    const int4* node_dn;
+    const float* cost;
+    double* aup;
+    int32_t* disp;    // pixel order: final results when the launch has one slice
+    double* best;
+    int32_t* pdisp;   // [slice][node] partial results otherwise
+    double* pbest;
+};
+
+struct Agg3Args {
+    Agg3View v[2];
+    const int4* units;  // {view, tree, first label, slice index}, longest tree first
+    int Dp, d1, N, n_slices;
+    const double* lut_w;
+    const double* lut_w2;
+    int keep;
+};
+
+__device__ __forceinline__ uint32_t a3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int a3_ld_acquire(uint32_t a) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void a3_st_release(uint32_t a, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int a3_ld_relaxed(uint32_t a) {
+    int v;
+    asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 a3_ldcg_d2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double a3_lds_d(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 a3_lds_d2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void a3_sts_d2(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void a3_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// total order on doubles as unsigned 64-bit keys (handles negative costs of the mc-cnn "fast" volumes)
+__device__ __forceinline__ unsigned long long a3_dkey(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double a3_dkey_inv(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// FULL: every lane's label pairs are real labels in every half (no per-lane predication in the loops)
+template <int NH, bool FULL>
+__global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    double* s_w = reinterpret_cast<double*>(s_raw);                 // [S3_NUM_W] exp(-w*gamma)
+    double* s_w2 = s_w + S3_NUM_W;                                  // [S3_NUM_W] 1 - w*w
+    double2* s_ring = reinterpret_cast<double2*>(s_w2 + S3_NUM_W);  // [A3_R][NH][32]
+    int* s_prog = reinterpret_cast<int*>(s_ring + A3_R * NH * 32);  // [32] progress words
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, WM = W - 1;
+
+    const int4 unit = A.units[blockIdx.x];
+    const Agg3View& V = A.v[unit.x];
+    const int t = unit.y, l0 = unit.z, slice = unit.w;
+    const int base = V.tree_start[t], end = V.tree_start[t + 1], top = end - 1;
+    const size_t Dp = (size_t)A.Dp;
+    bool act[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;  // the lane's pair holds at least one real label
+
+    for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
+        s_w[i] = A.lut_w[i];
+        s_w2[i] = A.lut_w2[i];
+    }
+    if (tid < 32) s_prog[tid] = end;  // up pass: node c is done iff its owner's word is <= c
+    __syncthreads();
+    const uint32_t prog_a = a3_smem(s_prog);
+    const uint32_t ring_a = a3_smem(s_ring) + 16u * lane;  // this lane's column of the ring
+    const uint32_t w_a = a3_smem(s_w);
+    constexpr uint32_t ROWB = NH * 512;                     // bytes of one ring row
+    const long long strideC = (long long)W * (long long)Dp * 4, strideA = 2 * strideC;  // bytes between a warp's consecutive rows
+
+    // ================================================================== leaf -> root
+    {
+        int v = top - w;
+        const char* nup_p = reinterpret_cast<const char*>(V.node_up + v);
+        const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + l0 + 2 * lane);
+        char* aup_p = reinterpret_cast<char*>(V.aup + (size_t)v * Dp + l0 + 2 * lane);
+        const char* aup_lane0 = reinterpret_cast<const char*>(V.aup + l0 + 2 * lane);  // + c * Dp * 8 for a far child
+        int4 nu_n = make_int4(0, 0, 0, 0);
+        float2 cf_n[NH];
+#pragma unroll
+        for (int h = 0; h < NH; h++) cf_n[h] = make_float2(0.f, 0.f);
+        if (v >= base) {
+            nu_n = *reinterpret_cast<const int4*>(nup_p);
+#pragma unroll
+            for (int h = 0; h < NH; h++)
+                if (act[h]) cf_n[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
+        } else if (lane == 0)
+            a3_st_release(prog_a + 4u * w, base);  // a warp without nodes never holds anybody back
+        int guard_ok = top + 1;  // writing ring row v is known to be safe for every v >= guard_ok
+        while (v >= base) {
+            const int4 nu = nu_n;  // {child_begin, child_count, cw01, cw23}
+            float2 cf[NH];
+#pragma unroll
+            for (int h = 0; h < NH; h++) cf[h] = cf_n[h];
+            const int vn = v - W;
+            if (vn >= base) {  // next node of this warp: record and cost row, one iteration ahead
+                nu_n = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) cf_n[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
+            }
+            // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
+            if (lane < NH * 2 && v - A3_PF * W >= base)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - 2 * lane * 4 - A3_PF * strideC + lane * 128));
+            const int cc = nu.y & 7, cb = nu.x;
+            double2 acc[NH];
+#pragma unroll
+            for (int h = 0; h < NH; h++) acc[h] = make_double2(0.0, 0.0);
+            // (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost — children in reverse BFS order (Stereo3DMST.cpp:125-137)
+#define A3_CHILD(K, IW)                                                                                              \
+    if (cc > K) {                                                                                                    \
+        const int c = cb + K;                                                                                        \
+        const double wk = a3_lds_d(w_a + 8u * (IW));                                                                 \
+        const uint32_t pa = prog_a + 4u * (uint32_t)((top - c) & WM);                                                \
+        while (a3_ld_acquire(pa) > c) __nanosleep(A3_SLEEP);                                                         \
+        double2 cv[NH];                                                                                              \
+        if (c - v < A3_NEAR) {                                                                                       \
+            const uint32_t ra = ring_a + (uint32_t)(c & (A3_R - 1)) * ROWB;                                          \
+            _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = a3_lds_d2(ra + h * 512);                          \
+        } else {                                                                                                     \
+            const char* gp = aup_lane0 + (size_t)c * Dp * 8;                                                         \
+            _Pragma("unroll") for (int h = 0; h < NH; h++)                                                           \
+                cv[h] = act[h] ? a3_ldcg_d2(reinterpret_cast<const double*>(gp + h * 512)) : make_double2(0.0, 0.0); \
+        }                                                                                                            \
+        _Pragma("unroll") for (int h = 0; h < NH; h++) {                                                             \
+            acc[h].x = S3_DADD(acc[h].x, S3_DMUL(wk, cv[h].x));                                                      \
+            acc[h].y = S3_DADD(acc[h].y, S3_DMUL(wk, cv[h].y));                                                      \
+        }                                                                                                            \
+    }
+            A3_CHILD(3, (uint32_t)nu.w >> 16)
+            A3_CHILD(2, (uint32_t)nu.w & 0xFFFFu)
+            A3_CHILD(1, (uint32_t)nu.z >> 16)
+            A3_CHILD(0, (uint32_t)nu.z & 0xFFFFu)
+#undef A3_CHILD
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                acc[h].x = S3_DADD(acc[h].x, (double)cf[h].x);
+                acc[h].y = S3_DADD(acc[h].y, (double)cf[h].y);
+                if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = acc[h];  // read back on the way down (and by far parents)
+            }
+            // ring row v last held node v + R, which only nodes > v + R - NEAR may still read
+            if (v < guard_ok && v + A3_R <= top) {
+                int m;
+                while (true) {
+                    m = __reduce_max_sync(0xffffffffu, lane < W ? a3_ld_relaxed(prog_a + 4u * lane) : INT_MIN);
+                    if (m < v + A3_R - A3_NEAR + 1 + W) break;
+                    __nanosleep(A3_SLEEP);
+                }
+                guard_ok = m - (A3_R - A3_NEAR + W);
+                asm volatile("fence.acq_rel.cta;" ::: "memory");
+            }
+            {
+                const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
+#pragma unroll
+                for (int h = 0; h < NH; h++) a3_sts_d2(ra + h * 512, acc[h]);
+            }
+            __syncwarp();
+            if (lane == 0) a3_st_release(prog_a + 4u * w, v);
+            nup_p -= (long long)W * 16;
+            cost_p -= strideC;
+            aup_p -= strideA;
+            v = vn;
+        }
+    }
+    __syncthreads();
+    if (tid < 32) s_prog[tid] = base - 1;  // down pass: node p is done iff its owner's word is >= p
+    __syncthreads();
+
+    // ================================================================== root -> leaf, WTA folded in
+    {
+        int v = base + w;
+        const char* ndn_p = reinterpret_cast<const char*>(V.node_dn + v);
+        char* aup_p = reinterpret_cast<char*>(V.aup + (size_t)v * Dp + l0 + 2 * lane);
+        const char* aup_lane0 = reinterpret_cast<const char*>(V.aup + l0 + 2 * lane);
+        int4 nd_n = make_int4(0, 0, 0, 0);
+        double2 au_n[NH];
+#pragma unroll
+        for (int h = 0; h < NH; h++) au_n[h] = make_double2(0.0, 0.0);
+        if (v < end) {
+            nd_n = *reinterpret_cast<const int4*>(ndn_p);
+#pragma unroll
+            for (int h = 0; h < NH; h++)
+                if (act[h]) au_n[h] = *reinterpret_cast<const double2*>(aup_p + h * 512);
+        } else if (lane == 0)
+            a3_st_release(prog_a + 4u * w, end);
+        int guard_ok = base - 1;  // writing ring row v is known to be safe for every v <= guard_ok
+        while (v < end) {
+            const int4 nd = nd_n;  // {parent, parent weight, level | far-child flag, pixel}
+            double2 au[NH];
+#pragma unroll
+            for (int h = 0; h < NH; h++) au[h] = au_n[h];
+            const int vn = v + W;
+            if (vn < end) {
+                nd_n = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) au_n[h] = *reinterpret_cast<const double2*>(aup_p + strideA + h * 512);
+            }
+            if (lane < NH * 4 && v + A3_PF * W < end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * 8 + A3_PF * strideA + lane * 128));
+            const int p = nd.x;
+            double2 fin[NH];
+            if (p != v) {
+                // A[c] = w * A[parent] + (1 - w*w) * A_up[c]   (Stereo3DMST.cpp:155)
+                const double wp = a3_lds_d(w_a + 8u * (uint32_t)nd.y), wq = a3_lds_d(w_a + 8u * (uint32_t)(S3_NUM_W + nd.y));
+#pragma unroll
+                for (int h = 0; h < NH; h++) {  // the half that does not depend on the parent, before the wait
+                    au[h].x = S3_DMUL(wq, au[h].x);
+                    au[h].y = S3_DMUL(wq, au[h].y);
+                }
+                const uint32_t pa = prog_a + 4u * (uint32_t)((p - base) & WM);
+                while (a3_ld_acquire(pa) < p) __nanosleep(A3_SLEEP);
+                double2 pv[NH];
+                if (v - p < A3_NEAR) {
+                    const uint32_t ra = ring_a + (uint32_t)(p & (A3_R - 1)) * ROWB;
+#pragma unroll
+                    for (int h = 0; h < NH; h++) pv[h] = a3_lds_d2(ra + h * 512);
+                } else {
+                    const char* gp = aup_lane0 + (size_t)p * Dp * 8;
+#pragma unroll
+                    for (int h = 0; h < NH; h++) pv[h] = act[h] ? a3_ldcg_d2(reinterpret_cast<const double*>(gp + h * 512)) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int h = 0; h < NH; h++) {
+                    fin[h].x = S3_DADD(S3_DMUL(wp, pv[h].x), au[h].x);
+                    fin[h].y = S3_DADD(S3_DMUL(wp, pv[h].y), au[h].y);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < NH; h++) fin[h] = au[h];  // the root keeps its leaf->root sum
+            }
+            if ((nd.z & S3_ND_FAR) || A.keep) {  // children further than NEAR read the final value from L2
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = fin[h];
+            }
+            if (v > guard_ok && v - A3_R >= base) {
+                int m;
+                while (true) {
+                    m = __reduce_min_sync(0xffffffffu, lane < W ? a3_ld_relaxed(prog_a + 4u * lane) : INT_MAX);
+                    if (m > v - A3_R + A3_NEAR - 1 - W) break;
+                    __nanosleep(A3_SLEEP);
+                }
+                guard_ok = m + (A3_R - A3_NEAR + W);
+                asm volatile("fence.acq_rel.cta;" ::: "memory");
+            }
+            {
+                const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
+#pragma unroll
+                for (int h = 0; h < NH; h++) a3_sts_d2(ra + h * 512, fin[h]);
+            }
+            __syncwarp();
+            if (lane == 0) a3_st_release(prog_a + 4u * w, v);
+            // ---- WTA over this warp's labels: strict '<', lowest label wins ties
+            double bc = DBL_MAX;  // the oracle's initial best (cost < DBL_MAX is required to win)
+            int bd = 0x7fffffff;
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                const int lab = l0 + h * 64 + 2 * lane;
+                if ((FULL || lab < A.d1) && fin[h].x < bc) { bc = fin[h].x; bd = lab; }
+                if ((FULL || lab + 1 < A.d1) && fin[h].y < bc) { bc = fin[h].y; bd = lab + 1; }
+            }
+            const unsigned long long key = a3_dkey(bc);
+            const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
+            const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
+            if (lane == 0) {
+                const double mc = a3_dkey_inv(((unsigned long long)mhi << 32) | mlo);
+                if (A.n_slices == 1) {
+                    V.disp[nd.w] = (int)md;
+                    V.best[nd.w] = mc;
+                } else {
+                    V.pdisp[(size_t)slice * A.N + v] = (int)md;
+                    V.pbest[(size_t)slice * A.N + v] = mc;
+                }
+            }
+            ndn_p += (long long)W * 16;
+            aup_p += strideA;
+            v = vn;
+        }
+    }
+}
+
+static size_t agg3_smem_bytes(int NH) { return 2 * S3_NUM_W * sizeof(double) + (size_t)A3_R * NH * 32 * sizeof(double2) + 32 * sizeof(int); }
+
+__global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node_dn, const int32_t* __restrict__ pdisp,
+                              const double* __restrict__ pbest, int32_t* __restrict__ disp, double* __restrict__ best) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    double bc = pbest[v];
+    int bd = pdisp[v];
+    for (int s = 1; s < n_slices; s++) {
+        const double c = pbest[(size_t)s * N + v];
+        const int d = pdisp[(size_t)s * N + v];
+        if (c < bc || (c == bc && d < bd)) { bc = c; bd = d; }
+    }
+    const int pix = node_dn[v].w;
+    disp[pix] = bd;
+    best[pix] = bc;
+}
+
+// views_mask: bit 0 = left, bit 1 = right.  Both views must hold volumes of the same D.
+// Returns 1 (and does nothing) if this kernel cannot serve the request, so the caller falls back to the simple one.
+int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
+    int nviews = 0, first = -1;
+    for (int view = 0; view < 2; view++) {
+        if (!(views_mask & (1 << view))) continue;
+        View& V = ctx->v[view];
+        if (!V.forest_ready || !V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense: forest and cost volume required");
+        if (first < 0) first = view;
+        if (V.D != ctx->v[first].D) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: views hold different D");
+        nviews++;
+    }
+    if (!nviews) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: empty view mask");
+    const int Dv = ctx->v[first].D, Dp = ctx->v[first].Dp;
+    if (d0 < 0 || d1 > Dv || d0 >= d1) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: need 0 <= d0 < d1 <= D");
+    if (d0 & 3) return 1;  // 16-byte row alignment of the lane's label pairs
+    const int nl = d1 - d0;
+    static const int force_nh = getenv("S3_AGG_NH") ? atoi(getenv("S3_AGG_NH")) : 0;
+    const int NH = force_nh ? force_nh : (nl > 64 ? 2 : 1);
+    const int SW = 64 * NH;
+    const int n_slices = (nl + SW - 1) / SW;
+    const size_t smem = agg3_smem_bytes(NH);
+
+    // unit list: (tree, slice) of the requested views, longest (most nodes) tree first
+    std::vector<std::pair<int, int4>> u;
+    for (int view = 0; view < 2; view++) {
+        if (!(views_mask & (1 << view))) continue;
+        View& V = ctx->v[view];
+        for (int t = 0; t < V.T; t++)
+            for (int s = 0; s < n_slices; s++) u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(view, t, d0 + s * SW, s)});
+    }
+    std::stable_sort(u.begin(), u.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    std::vector<int4> units(u.size());
+    for (size_t i = 0; i < u.size(); i++) units[i] = u[i].second;
+    const size_t ubytes = units.size() * sizeof(int4);
+    if (ctx->units_cap < ubytes) {
+        if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
+        ctx->units_dev = nullptr; ctx->units_cap = 0;
+        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes));
+        ctx->units_cap = ubytes;
+    }
+    S3_CUDA(cudaMemcpyAsync(ctx->units_dev, units.data(), ubytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    Agg3Args A;
+    memset(&A, 0, sizeof A);
+    int32_t* pdisp[2] = {nullptr, nullptr};
+    double* pbest[2] = {nullptr, nullptr};
+    if (n_slices > 1) {
+        const size_t per_view = (size_t)n_slices * ctx->N * (sizeof(double) + sizeof(int32_t));
+        const size_t need = 2 * per_view;
+        if (ctx->pms_scratch_cap < need) {
+            if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
+            ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
+            S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
+            ctx->pms_scratch_cap = need;
+        }
+        for (int view = 0; view < 2; view++) {
+            pbest[view] = (double*)((char*)ctx->pms_scratch + view * per_view);
+            pdisp[view] = (int32_t*)(pbest[view] + (size_t)n_slices * ctx->N);
+        }
+    }
+    for (int view = 0; view < 2; view++) {
+        View& V = ctx->v[view];
+        Agg3View& G = A.v[view];
+        G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn;
+        G.cost = V.cost; G.aup = V.aup;
+        G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[view]; G.pbest = pbest[view];
+    }
+    A.units = reinterpret_cast<const int4*>(ctx->units_dev);
+    A.Dp = Dp; A.d1 = d1; A.N = ctx->N; A.n_slices = n_slices;
+    A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
+    A.keep = ctx->P.keep_aggregated;
+
+    const int grid = (int)units.size();
+    static const int threads_env = getenv("S3_AGG_WARPS") ? 32 * atoi(getenv("S3_AGG_WARPS")) : 0;
+    const int threads = threads_env ? threads_env : 512;  // warps per tree: a power of two
+    S3_EV_BEGIN(S3DMST_T_AGG, first);
+    const bool full = nl % SW == 0;  // every slice covers SW real labels
+#define A3_LAUNCH(NH_, FULL_)                                                                                              \
+    do {                                                                                                                  \
+        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<NH_, FULL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_agg_flow<NH_, FULL_><<<grid, threads, smem, ctx->stream>>>(A);                                                  \
+    } while (0)
+    if (NH == 2) {
+        if (full) A3_LAUNCH(2, true); else A3_LAUNCH(2, false);
+    } else {
+        if (full) A3_LAUNCH(1, true); else A3_LAUNCH(1, false);
+    }
+#undef A3_LAUNCH
+    S3_LAUNCH_CHECK();
+    if (n_slices > 1) {
+        for (int view = 0; view < 2; view++) {
+            if (!(views_mask & (1 << view))) continue;
+            View& V = ctx->v[view];
+            k_wta_finish3<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, n_slices, V.node_dn, pdisp[view], pbest[view], V.disp_i, V.best);
+            S3_LAUNCH_CHECK();
+        }
+    }
+    S3_EV_END(S3DMST_T_AGG, first);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // `units` (host vector) is read by the async copy above
+    for (int view = 0; view < 2; view++)
+        if (views_mask & (1 << view)) {
+            ctx->v[view].agg_ready = true;
+            ctx->v[view].agg_d0 = d0;
+            ctx->v[view].agg_d1 = d1;
+        }
+    return 0;
+}

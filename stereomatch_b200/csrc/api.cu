@@ -368,7 +368,10 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.pw, parent_weight, sizeof(uint16_t) * N);
     H2D(V.node_up, nu.data(), sizeof(NodeUp) * N);
     std::vector<int4> nd(N);
-    for (int i = 0; i < N; i++) nd[i] = make_int4(parent[i], parent_weight[i], level[i], node_pixel[i]);
+    for (int i = 0; i < N; i++) {
+        const bool far_child = nu[i].child_count > 0 && nu[i].child_begin + nu[i].child_count - 1 - i >= S3_AGG_NEAR;
+        nd[i] = make_int4(parent[i], parent_weight[i], level[i] | (far_child ? S3_ND_FAR : 0), node_pixel[i]);
+    }
     H2D(V.node_dn, nd.data(), sizeof(int4) * N);
     H2D(V.level, level.data(), sizeof(int) * N);
     H2D(V.pixel_node, pixel_node.data(), sizeof(int) * N);
@@ -425,7 +428,7 @@ int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* d
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     S3_CUDA(cudaSetDevice(ctx->device));
     {
-        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_dense2(ctx, 1 << view, d0, d1);
+        int rc = ctx->P.agg_kernel == 1 ? 1 : ctx->P.agg_kernel == 2 ? s3_aggregate_dense2(ctx, 1 << view, d0, d1) : s3_aggregate_flow(ctx, 1 << view, d0, d1);
         if (rc == 1) rc = s3_aggregate_dense(ctx, view, d0, d1);  // simple kernel: any even d0, any depth
         if (rc) return rc;
     }
@@ -548,7 +551,7 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     S3_EV_END(S3DMST_T_FOREST, 0);
     S3_TRY(s3_cost_adgrad(ctx, D, 0));
     {
-        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_dense2(ctx, 3, 0, D);  // both views' trees in one launch
+        int rc = ctx->P.agg_kernel == 1 ? 1 : ctx->P.agg_kernel == 2 ? s3_aggregate_dense2(ctx, 3, 0, D) : s3_aggregate_flow(ctx, 3, 0, D);  // both views' trees in one launch
         if (rc == 1) {
             rc = 0;
             for (int view = 0; view < 2 && !rc; view++) rc = s3_aggregate_dense(ctx, view, 0, D);

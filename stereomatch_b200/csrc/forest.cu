@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             nu.cw01 = (cc > 0 ? k0 >> 2 : 0u) | ((cc > 1 ? k1 >> 2 : 0u) << 16);
             nu.cw23 = (cc > 2 ? k2 >> 2 : 0u) | ((cc > 3 ? k3 >> 2 : 0u) << 16);
             node_up[g] = nu;
+            if (cc > 0 && cb + cc - 1 - g >= S3_AGG_NEAR) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_FAR;
             unsigned long long kk = kids;
             for (int k = 0; k < cc; k++, kk >>= 16) {
                 const uint32_t en = (uint32_t)kk & 0xFFFFu;
@@ -714,7 +715,7 @@ __global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __res
     const int4 nd = node_dn[h];
     parent[h] = nd.x;
     pw[h] = (uint16_t)nd.y;
-    level[h] = nd.z;
+    level[h] = nd.z & ~S3_ND_FAR;
     node_pixel[h] = nd.w;
 }
 

@@ -14,6 +14,8 @@
 #define S3_TILE_NODES 16         // nodes per aggregation tile (== math warps of the pipelined kernel)
 #define S3_TF_FIRST 1            // tile flags: first / last tile of its tree level
 #define S3_TF_LAST 2
+#define S3_AGG_NEAR 32          // dataflow aggregation: a parent/child closer than this (in BFS index) is handed over in shared memory
+#define S3_ND_FAR (1 << 30)      // node_dn.z flag: the node has a child S3_AGG_NEAR or more nodes away
 
 // Per-node record read by the leaf->root pass: children are contiguous in BFS order.
 struct __align__(16) NodeUp {
@@ -157,7 +159,8 @@ int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
-int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined)
+int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined, level-synchronous tiles)
+int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1);    // aggregate3.cu (dataflow, default)
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
 int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax);          // pms.cu: the reference's random plane initialisation
 int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed, const std::vector<int>& adj_ptr, const std::vector<int>& adj);
