@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(512) k_agg_dense(AggArgs A) {
             double2 acc[HV];
 #pragma unroll
             for (int h = 0; h < HV; h++) acc[h] = make_double2(0.0, 0.0);
-            for (int k = nu.child_count - 1; k >= 0; --k) {
+            for (int k = (nu.child_count & 7) - 1; k >= 0; --k) {
                 const int ch = nu.child_begin + k;
                 const int j = ch - le;
                 const uint32_t iw = ((k & 2) ? nu.cw23 : nu.cw01) >> ((k & 1) * 16) & 0xFFFFu;

@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(32 * (S3_TILE_NODES + A2_NP + A2_ND), 1) k_agg
                         r0 = make_int4((int)0x80000000u | tf, 0, 0, 0);
                         r2 = make_int4(0, 0, 0, 0);
                     } else if (pass == 0) {
-                        const int4 nu = lds_i4(s_meta + (uint32_t)e * 16u);  // {child_begin, child_count, cw01, cw23}
+                        int4 nu = lds_i4(s_meta + (uint32_t)e * 16u);  // {child_begin, child_count, cw01, cw23}
+                        nu.y &= 7;  // bit 8 is the dataflow kernel's far-parent flag
                         const int j0 = nu.x - dB.x;                          // children live in the next level
                         w0 = lds_d(s_w + 8u * ((uint32_t)nu.z & 0xFFFFu));
                         w1 = lds_d(s_w + 8u * ((uint32_t)nu.z >> 16));

@@ -35,8 +35,6 @@
 #include "hd_math.h"
 #include "internal.h"
 
-#define A3_R 64      // ring rows (power of two)
-#define A3_NEAR 32   // a dependency closer than this goes through the ring
 #define A3_PF 6      // rounds ahead of the bulk L2 prefetch
 #ifndef A3_SLEEP
 #define A3_SLEEP 20  // ns a waiting warp yields the issue slot for between two polls
@@ -66,6 +64,7 @@ struct Agg3Args {
     Agg3View v[2];
     const int4* units;  // {view, tree, first label, slice index}, longest tree first
     int Dp, d1, N, n_slices;
+    int unit0;          // first unit of this launch
     const double* lut_w;
     const double* lut_w2;
     int keep;
@@ -117,8 +116,9 @@ __device__ __forceinline__ double a3_dkey_inv(unsigned long long k) {
 }
 
 // FULL: every lane's label pairs are real labels in every half (no per-lane predication in the loops)
-template <int NH, bool FULL>
-__global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
+// BIG: 32 warps per tree, one CTA per SM (the biggest trees: enough warps that a level's nodes do not need every warp)
+template <int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR>
+__global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3Args A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     double* s_w = reinterpret_cast<double*>(s_raw);                 // [S3_NUM_W] exp(-w*gamma)
     double* s_w2 = s_w + S3_NUM_W;                                  // [S3_NUM_W] 1 - w*w
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
     int* s_prog = reinterpret_cast<int*>(s_ring + A3_R * NH * 32);  // [32] progress words
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, WM = W - 1;
 
-    const int4 unit = A.units[blockIdx.x];
+    const int4 unit = A.units[A.unit0 + blockIdx.x];
     const Agg3View& V = A.v[unit.x];
     const int t = unit.y, l0 = unit.z, slice = unit.w;
     const int base = V.tree_start[t], end = V.tree_start[t + 1], top = end - 1;
@@ -166,21 +166,18 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
         } else if (lane == 0)
             a3_st_release(prog_a + 4u * w, base);  // a warp without nodes never holds anybody back
         int guard_ok = top + 1;  // writing ring row v is known to be safe for every v >= guard_ok
+#if A3_INSTR
+        long long tq = clock64(), q_pre = 0, q_poll = 0, q_dep = 0, q_guard = 0, q_pub = 0, q_post = 0; const long long t_up0 = tq; int n_nodes = 0, n_guard = 0;
+#endif
         while (v >= base) {
+#if A3_INSTR
+            n_nodes++;
+#endif
             const int4 nu = nu_n;  // {child_begin, child_count, cw01, cw23}
             float2 cf[NH];
 #pragma unroll
             for (int h = 0; h < NH; h++) cf[h] = cf_n[h];
             const int vn = v - W;
-            if (vn >= base) {  // next node of this warp: record and cost row, one iteration ahead
-                nu_n = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
-#pragma unroll
-                for (int h = 0; h < NH; h++)
-                    if (act[h]) cf_n[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
-            }
-            // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
-            if (lane < NH * 2 && v - A3_PF * W >= base)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - 2 * lane * 4 - A3_PF * strideC + lane * 128));
             const int cc = nu.y & 7, cb = nu.x;
             double2 acc[NH];
 #pragma unroll
@@ -191,7 +188,9 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
         const int c = cb + K;                                                                                        \
         const double wk = a3_lds_d(w_a + 8u * (IW));                                                                 \
         const uint32_t pa = prog_a + 4u * (uint32_t)((top - c) & WM);                                                \
+        A3_CLK(q_pre);                                                                                               \
         while (a3_ld_acquire(pa) > c) __nanosleep(A3_SLEEP);                                                         \
+        A3_CLK(q_poll);                                                                                              \
         double2 cv[NH];                                                                                              \
         if (c - v < A3_NEAR) {                                                                                       \
             const uint32_t ra = ring_a + (uint32_t)(c & (A3_R - 1)) * ROWB;                                          \
@@ -215,19 +214,28 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
             for (int h = 0; h < NH; h++) {
                 acc[h].x = S3_DADD(acc[h].x, (double)cf[h].x);
                 acc[h].y = S3_DADD(acc[h].y, (double)cf[h].y);
-                if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = acc[h];  // read back on the way down (and by far parents)
             }
+            const bool far_parent = nu.y & S3_NU_FARPARENT;
+            if (far_parent) {  // a parent beyond the ring reads this row from L2: it has to be out before the publish
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = acc[h];
+            }
+            A3_CLK(q_dep);
             // ring row v last held node v + R, which only nodes > v + R - NEAR may still read
             if (v < guard_ok && v + A3_R <= top) {
+#if A3_INSTR
+                n_guard++;
+#endif
                 int m;
                 while (true) {
-                    m = __reduce_max_sync(0xffffffffu, lane < W ? a3_ld_relaxed(prog_a + 4u * lane) : INT_MIN);
+                    m = __reduce_max_sync(0xffffffffu, lane < W ? a3_ld_acquire(prog_a + 4u * lane) : INT_MIN);
                     if (m < v + A3_R - A3_NEAR + 1 + W) break;
                     __nanosleep(A3_SLEEP);
                 }
                 guard_ok = m - (A3_R - A3_NEAR + W);
-                asm volatile("fence.acq_rel.cta;" ::: "memory");
             }
+            A3_CLK(q_guard);
             {
                 const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
 #pragma unroll
@@ -235,11 +243,32 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
             }
             __syncwarp();
             if (lane == 0) a3_st_release(prog_a + 4u * w, v);
+            A3_CLK(q_pub);
+            // Global accesses are issued only AFTER the publish: the release fence waits for every memory operation the warp
+            // has in flight, and a load still on its way from HBM would put its latency on every level of the tree.
+            if (vn >= base) {  // next node of this warp: record and cost row, one iteration ahead
+                nu_n = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) cf_n[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
+            }
+            // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
+            if (lane < NH * 2 && v - A3_PF * W >= base)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - 2 * lane * 4 - A3_PF * strideC + lane * 128));
+            if (!far_parent) {  // read back on the way down
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = acc[h];
+            }
             nup_p -= (long long)W * 16;
             cost_p -= strideC;
             aup_p -= strideA;
             v = vn;
+            A3_CLK(q_post);
         }
+#if A3_INSTR
+        if (blockIdx.x == 0 && lane == 0 && (w == 0 || w == 9)) printf("up W=%d warp %d: %d nodes (%d guards), cycles/node total %lld | pre %lld poll %lld dep %lld guard %lld publish %lld post %lld\n", W, w, n_nodes, n_guard, (clock64() - t_up0) / n_nodes, q_pre / n_nodes, q_poll / n_nodes, q_dep / n_nodes, q_guard / n_nodes, q_pub / n_nodes, q_post / n_nodes);
+#endif
     }
     __syncthreads();
     if (tid < 32) s_prog[tid] = base - 1;  // down pass: node p is done iff its owner's word is >= p
@@ -263,20 +292,43 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
         } else if (lane == 0)
             a3_st_release(prog_a + 4u * w, end);
         int guard_ok = base - 1;  // writing ring row v is known to be safe for every v <= guard_ok
+        // WTA over a node's labels held by this warp: strict '<', lowest label wins ties
+        auto wta = [&](const double2* f, int vv, int pix) {
+            double bc = DBL_MAX;  // the oracle's initial best (cost < DBL_MAX is required to win)
+            int bd = 0x7fffffff;
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                const int lab = l0 + h * 64 + 2 * lane;
+                if ((FULL || lab < A.d1) && f[h].x < bc) { bc = f[h].x; bd = lab; }
+                if ((FULL || lab + 1 < A.d1) && f[h].y < bc) { bc = f[h].y; bd = lab + 1; }
+            }
+            const unsigned long long key = a3_dkey(bc);
+            const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
+            const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
+            if (lane == 0) {
+                const double mc = a3_dkey_inv(((unsigned long long)mhi << 32) | mlo);
+                if (A.n_slices == 1) {
+                    V.disp[pix] = (int)md;
+                    V.best[pix] = mc;
+                } else {
+                    V.pdisp[(size_t)slice * A.N + vv] = (int)md;
+                    V.pbest[(size_t)slice * A.N + vv] = mc;
+                }
+            }
+        };
+        double2 fin_prev[NH];
+#pragma unroll
+        for (int h = 0; h < NH; h++) fin_prev[h] = make_double2(0.0, 0.0);
+        int v_prev = -1, pix_prev = 0;
         while (v < end) {
             const int4 nd = nd_n;  // {parent, parent weight, level | far-child flag, pixel}
             double2 au[NH];
 #pragma unroll
             for (int h = 0; h < NH; h++) au[h] = au_n[h];
             const int vn = v + W;
-            if (vn < end) {
-                nd_n = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
-#pragma unroll
-                for (int h = 0; h < NH; h++)
-                    if (act[h]) au_n[h] = *reinterpret_cast<const double2*>(aup_p + strideA + h * 512);
-            }
-            if (lane < NH * 4 && v + A3_PF * W < end)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * 8 + A3_PF * strideA + lane * 128));
+            if (v_prev >= 0) wta(fin_prev, v_prev, pix_prev);
             const int p = nd.x;
             double2 fin[NH];
             if (p != v) {
@@ -316,12 +368,11 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
             if (v > guard_ok && v - A3_R >= base) {
                 int m;
                 while (true) {
-                    m = __reduce_min_sync(0xffffffffu, lane < W ? a3_ld_relaxed(prog_a + 4u * lane) : INT_MAX);
+                    m = __reduce_min_sync(0xffffffffu, lane < W ? a3_ld_acquire(prog_a + 4u * lane) : INT_MAX);
                     if (m > v - A3_R + A3_NEAR - 1 - W) break;
                     __nanosleep(A3_SLEEP);
                 }
                 guard_ok = m + (A3_R - A3_NEAR + W);
-                asm volatile("fence.acq_rel.cta;" ::: "memory");
             }
             {
                 const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
@@ -330,38 +381,29 @@ __global__ void __launch_bounds__(512, 2) k_agg_flow(Agg3Args A) {
             }
             __syncwarp();
             if (lane == 0) a3_st_release(prog_a + 4u * w, v);
-            // ---- WTA over this warp's labels: strict '<', lowest label wins ties
-            double bc = DBL_MAX;  // the oracle's initial best (cost < DBL_MAX is required to win)
-            int bd = 0x7fffffff;
+            // next node's loads: after the publish (see the leaf->root pass)
+            if (vn < end) {
+                nd_n = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
 #pragma unroll
-            for (int h = 0; h < NH; h++) {
-                const int lab = l0 + h * 64 + 2 * lane;
-                if ((FULL || lab < A.d1) && fin[h].x < bc) { bc = fin[h].x; bd = lab; }
-                if ((FULL || lab + 1 < A.d1) && fin[h].y < bc) { bc = fin[h].y; bd = lab + 1; }
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) au_n[h] = *reinterpret_cast<const double2*>(aup_p + strideA + h * 512);
             }
-            const unsigned long long key = a3_dkey(bc);
-            const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
-            const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
-            const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
-            const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
-            if (lane == 0) {
-                const double mc = a3_dkey_inv(((unsigned long long)mhi << 32) | mlo);
-                if (A.n_slices == 1) {
-                    V.disp[nd.w] = (int)md;
-                    V.best[nd.w] = mc;
-                } else {
-                    V.pdisp[(size_t)slice * A.N + v] = (int)md;
-                    V.pbest[(size_t)slice * A.N + v] = mc;
-                }
-            }
+            if (lane < NH * 4 && v + A3_PF * W < end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * 8 + A3_PF * strideA + lane * 128));
+            // the WTA of this node is done at the top of the next iteration, in the shadow of the next wait
+#pragma unroll
+            for (int h = 0; h < NH; h++) fin_prev[h] = fin[h];
+            v_prev = v;
+            pix_prev = nd.w;
             ndn_p += (long long)W * 16;
             aup_p += strideA;
             v = vn;
         }
+        if (v_prev >= 0) wta(fin_prev, v_prev, pix_prev);
     }
 }
 
-static size_t agg3_smem_bytes(int NH) { return 2 * S3_NUM_W * sizeof(double) + (size_t)A3_R * NH * 32 * sizeof(double2) + 32 * sizeof(int); }
+static size_t agg3_smem_bytes(int NH, int R) { return 2 * S3_NUM_W * sizeof(double) + (size_t)R * NH * 32 * sizeof(double2) + 32 * sizeof(int); }
 
 __global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node_dn, const int32_t* __restrict__ pdisp,
                               const double* __restrict__ pbest, int32_t* __restrict__ disp, double* __restrict__ best) {
@@ -400,7 +442,6 @@ int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     const int NH = force_nh ? force_nh : (nl > 64 ? 2 : 1);
     const int SW = 64 * NH;
     const int n_slices = (nl + SW - 1) / SW;
-    const size_t smem = agg3_smem_bytes(NH);
 
     // unit list: (tree, slice) of the requested views, longest (most nodes) tree first
     std::vector<std::pair<int, int4>> u;
@@ -452,23 +493,40 @@ int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
     A.keep = ctx->P.keep_aggregated;
 
-    const int grid = (int)units.size();
-    static const int threads_env = getenv("S3_AGG_WARPS") ? 32 * atoi(getenv("S3_AGG_WARPS")) : 0;
-    const int threads = threads_env ? threads_env : 512;  // warps per tree: a power of two
-    S3_EV_BEGIN(S3DMST_T_AGG, first);
+    // the biggest trees get 32 warps and an SM of their own; the rest 16 warps, two trees per SM
+    static const int big_nodes = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
+    int n_big = 0;
+    while (n_big < (int)u.size() && u[n_big].first >= big_nodes) n_big++;
+    const int n_small = (int)u.size() - n_big;
     const bool full = nl % SW == 0;  // every slice covers SW real labels
-#define A3_LAUNCH(NH_, FULL_)                                                                                              \
-    do {                                                                                                                  \
-        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<NH_, FULL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_agg_flow<NH_, FULL_><<<grid, threads, smem, ctx->stream>>>(A);                                                  \
+    S3_EV_BEGIN(S3DMST_T_AGG, first);
+#define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                                 \
+    do {                                                                                                                       \
+        const size_t smem = agg3_smem_bytes(NH_, R_);                                                                          \
+        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<NH_, FULL_, BIG_, R_, NEAR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_agg_flow<NH_, FULL_, BIG_, R_, NEAR_><<<GRID_, THREADS_, smem, ctx->stream>>>(A);                                    \
+        S3_LAUNCH_CHECK();                                                                                                     \
     } while (0)
-    if (NH == 2) {
-        if (full) A3_LAUNCH(2, true); else A3_LAUNCH(2, false);
-    } else {
-        if (full) A3_LAUNCH(1, true); else A3_LAUNCH(1, false);
+    // ring geometry: rows R and hand-over distance NEAR (>= S3_AGG_NEAR, the distance the forest stage flags nodes by).
+    // A warp may not run more than (R - NEAR) / W rounds ahead of the slowest one, so R - NEAR >= ~4 W.
+#define A3_DISPATCH(BIG_, RB_, NEARB_, GRID_, THREADS_)                                                 \
+    do {                                                                                               \
+        if (NH == 2) {                                                                                 \
+            if (full) A3_LAUNCH(2, true, BIG_, RB_ / 2, NEARB_, GRID_, THREADS_); else A3_LAUNCH(2, false, BIG_, RB_ / 2, NEARB_, GRID_, THREADS_); \
+        } else {                                                                                       \
+            if (full) A3_LAUNCH(1, true, BIG_, RB_, NEARB_, GRID_, THREADS_); else A3_LAUNCH(1, false, BIG_, RB_, NEARB_, GRID_, THREADS_); \
+        }                                                                                              \
+    } while (0)
+    if (n_big) {
+        A.unit0 = 0;
+        A3_DISPATCH(true, 256, 64, n_big, 1024);   // 128 KB ring (64-label slices) / 64 KB... one tree per SM
     }
+    if (n_small) {
+        A.unit0 = n_big;
+        A3_DISPATCH(false, 128, 32, n_small, 512);  // 64 KB ring: three trees per SM by shared memory, two by registers
+    }
+#undef A3_DISPATCH
 #undef A3_LAUNCH
-    S3_LAUNCH_CHECK();
     if (n_slices > 1) {
         for (int view = 0; view < 2; view++) {
             if (!(views_mask & (1 << view))) continue;

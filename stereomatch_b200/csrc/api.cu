@@ -277,7 +277,7 @@ int s3dmst_get_forest(s3dmst_ctx* ctx, int view, uint16_t* edge_weight, uint8_t*
         S3_CUDA(cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < N; i++) {
             if (child_begin) child_begin[i] = nu[i].child_begin;
-            if (child_count) child_count[i] = nu[i].child_count;
+            if (child_count) child_count[i] = nu[i].child_count & 7;
         }
     }
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -369,7 +369,8 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.node_up, nu.data(), sizeof(NodeUp) * N);
     std::vector<int4> nd(N);
     for (int i = 0; i < N; i++) {
-        const bool far_child = nu[i].child_count > 0 && nu[i].child_begin + nu[i].child_count - 1 - i >= S3_AGG_NEAR;
+        if (parent[i] != i && i - parent[i] >= S3_AGG_NEAR) nu[i].child_count |= S3_NU_FARPARENT;
+        const bool far_child = (nu[i].child_count & 7) > 0 && nu[i].child_begin + (nu[i].child_count & 7) - 1 - i >= S3_AGG_NEAR;
         nd[i] = make_int4(parent[i], parent_weight[i], level[i] | (far_child ? S3_ND_FAR : 0), node_pixel[i]);
     }
     H2D(V.node_dn, nd.data(), sizeof(int4) * N);

@@ -498,7 +498,7 @@ __device__ long long g_dummy;
 // Returns the child count; `kids` = the (at most 4) child entries in order, 0xFFFF-padded.
 __device__ __forceinline__ int bfs_expand(uint32_t fw, const unsigned long long* __restrict__ adjw, int& pix, unsigned long long& kids, long long& g_ldg_cycles) {
     pix = (int)(fw & 0x0FFFFFFFu);
-    const uint32_t pdir = fw >> 28;
+    const uint32_t pdir = (fw >> 28) & 7u;  // bit 31: the parent is S3_AGG_NEAR or more nodes back
 #if BFS_INSTR
     const long long tl0 = clock64();
 #endif
@@ -563,10 +563,10 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
         long long tq = tb0, q_load = 0, q_scan = 0, q_store = 0, q_sync = 0, q_ldg = 0;
         (void)q_ldg; (void)tq; (void)q_load; (void)q_scan; (void)q_store; (void)q_sync;
         // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record
-        auto emit = [&](int g, int pix, int cc, unsigned long long kids, int cb, int bnext, int Lc, int curc) {
+        auto emit = [&](int g, int pix, int cc, unsigned long long kids, int cb, int bnext, int Lc, int curc, uint32_t fwg) {
             NodeUp nu;
             nu.child_begin = cb;
-            nu.child_count = cc;
+            nu.child_count = cc | ((fwg >> 31) ? S3_NU_FARPARENT : 0);
             const uint32_t k0 = (uint32_t)kids & 0xFFFFu, k1 = (uint32_t)(kids >> 16) & 0xFFFFu, k2 = (uint32_t)(kids >> 32) & 0xFFFFu, k3 = (uint32_t)(kids >> 48);
             nu.cw01 = (cc > 0 ? k0 >> 2 : 0u) | ((cc > 1 ? k1 >> 2 : 0u) << 16);
             nu.cw23 = (cc > 2 ? k2 >> 2 : 0u) | ((cc > 3 ? k3 >> 2 : 0u) << 16);
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                 const int dir = (int)(en & 3u);
                 const int q = pix + (dir == 0 ? -W : dir == 1 ? -1 : dir == 2 ? 1 : W);
                 const int h = cb + k;
-                const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28);  // the parent lies in the opposite direction
+                const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28) | (h - g >= S3_AGG_NEAR ? 0x80000000u : 0u);  // the parent lies in the opposite direction
                 if (h - bnext < BFS_FRONT) s_front[curc ^ 1][h - bnext] = fw;
                 else front[h] = fw;
                 pixel_node[q] = h;
@@ -596,14 +596,15 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                     int cc = 0, pix = 0;
                     unsigned long long kids = 0;
                     const int g = a + lane;
-                    if (g < b) cc = bfs_expand(s_front[cur][lane], adjw, pix, kids, q_ldg);
+                    uint32_t fwg = 0;
+                    if (g < b) { fwg = s_front[cur][lane]; cc = bfs_expand(fwg, adjw, pix, kids, q_ldg); }
                     BFS_CLK(q_load);
                     // exclusive prefix of cc (0..4) from three independent ballots
                     const uint32_t b0 = __ballot_sync(0xffffffffu, cc & 1), b1 = __ballot_sync(0xffffffffu, cc & 2), b2 = __ballot_sync(0xffffffffu, cc & 4);
                     const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
                     const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
                     BFS_CLK(q_scan);
-                    if (g < b) emit(g, pix, cc, kids, b + excl, b, L, cur);
+                    if (g < b) emit(g, pix, cc, kids, b + excl, b, L, cur, fwg);
                     a = b;
                     b += total;
                     L++;
@@ -624,7 +625,8 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                 const int g = chunk + tid;
                 int cc = 0, pix = 0;
                 unsigned long long kids = 0;
-                if (g < b) cc = bfs_expand(g - a < BFS_FRONT ? s_front[cur][g - a] : front[g], adjw, pix, kids, q_ldg);
+                uint32_t fwg = 0;
+                if (g < b) { fwg = g - a < BFS_FRONT ? s_front[cur][g - a] : front[g]; cc = bfs_expand(fwg, adjw, pix, kids, q_ldg); }
                 int incl = cc;
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                     if (i < wid) wbase += v;
                     chunk_total += v;
                 }
-                if (g < b) emit(g, pix, cc, kids, b + run + incl - cc + wbase, b, L, cur);
+                if (g < b) emit(g, pix, cc, kids, b + run + incl - cc + wbase, b, L, cur, fwg);
                 run += chunk_total;
                 __syncthreads();  // s_warp reuse; frontier words visible to the block
             }

@@ -15,6 +15,7 @@
 #define S3_TF_FIRST 1            // tile flags: first / last tile of its tree level
 #define S3_TF_LAST 2
 #define S3_AGG_NEAR 32          // dataflow aggregation: a parent/child closer than this (in BFS index) is handed over in shared memory
+#define S3_NU_FARPARENT 0x100    // NodeUp.child_count flag: the node's parent is S3_AGG_NEAR or more nodes away
 #define S3_ND_FAR (1 << 30)      // node_dn.z flag: the node has a child S3_AGG_NEAR or more nodes away
 
 // Per-node record read by the leaf->root pass: children are contiguous in BFS order.

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_pms(PmsArgs A) {
                 const int v = ls + i;
                 const NodeUp nu = A.node_up[v];
                 double acc = 0.0;
-                for (int c = nu.child_count - 1; c >= 0; --c) {
+                for (int c = (nu.child_count & 7) - 1; c >= 0; --c) {
                     const int ch = nu.child_begin + c;
                     const int j = ch - le;
                     const uint32_t iw = ((c & 2) ? nu.cw23 : nu.cw01) >> ((c & 1) * 16) & 0xFFFFu;
