@@ -5,10 +5,10 @@
   python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores (oracle port)
 
 Workload (BASELINE.json configs[1], "C2"): synthetic random-dot slanted-plane pair 1280x720, 128 disparities.
-One step = one full pass of the hot path over one stereo pair per GPU: median + edge weights + FH forest + min-size
+One step = one full pass of the hot path over one batch of --batch stereo pairs per GPU (default 8): median + edge weights + FH forest + min-size
 merge + BFS re-indexing (both views), truncated colour+gradient cost volume (both views), two-pass tree-filter
 aggregation + WTA (both views), left-right check + scan-line fill.  Frames are independent, so N GPUs process N
-different pairs per step with no collective ("weak" scaling).  Metric: Mpix*disparities/s = N*W*H*D / t_step.
+different pairs per step with no collective ("weak" scaling).  Metric: Mpix*disparities/s = N*batch*W*H*D / t_step.
 """
 from __future__ import annotations
 
@@ -154,108 +154,131 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
-    eng = api.Stereo3DMST(device=local, stream=stream.cuda_stream, agg_threads=args.agg_threads, agg_cache_nodes=args.agg_cache)
-
-    L, R, gt = synth.make_pair(W, H, D, seed=synth.BASE_SEED + rank)   # one different frame per rank
+    B = max(1, args.batch)
+    # one context (and stream) per frame of the batch; in a batch the cooperative forest kernel takes a share of the SMs
+    engs = [api.Stereo3DMST(device=local, fh_ctas=(args.fh_ctas if B > 1 else 0)) for _ in range(B)]
+    frames = [synth.make_pair(W, H, D, seed=synth.BASE_SEED + rank * B + i) for i in range(B)]   # different frames per rank
     # pinned host staging for the e2e leg
-    hl = torch.from_numpy(L.copy()).pin_memory(); hr = torch.from_numpy(R.copy()).pin_memory()
-    eng.set_images(hl.numpy(), hr.numpy())
+    pin = [(torch.from_numpy(L.copy()).pin_memory(), torch.from_numpy(R.copy()).pin_memory()) for L, R, _ in frames]
+    outs = [(torch.empty(W * H, dtype=torch.float32).pin_memory(), torch.empty(W * H, dtype=torch.float32).pin_memory()) for _ in range(B)]
+    for e, (hl, hr) in zip(engs, pin):
+        e.set_images(hl.numpy(), hr.numpy())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value")
+    def maxms(ms):
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step():
+        api.run_dense_batch(engs, D, fill=True, fetch=False)
+
+    # ---- device-resident throughput ("value"): images already in HBM, results left in HBM
     for _ in range(max(3, args.warmup)):
-        eng.run_dense(D, fill=True, fetch=False)
+        step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = eng.launch_count()
-    agg_ms = 0.0
+    launches0 = sum(e.launch_count() for e in engs)
     stage_tot = np.zeros(4)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_wall = time.perf_counter()
     for _ in range(args.steps):
-        eng.run_dense(D, fill=True, fetch=False)
-        # stage events are read back after the step is enqueued; the host-side sync inside run_dense's forest
-        # stage (tree order metadata) already serialises steps, so this adds no device idle time
-        for s in range(4):
-            stage_tot[s] += eng.stage_ms(s)
+        step()
+        for e in engs:
+            e.sync()
+        # aggregation: ONE launch set per step (engine 0's stream); forest/cost: mean over the frames' own streams (they overlap)
+        stage_tot[api.T_AGG] += engs[0].stage_ms(api.T_AGG)
+        stage_tot[api.T_FOREST] += float(np.mean([e.stage_ms(api.T_FOREST) for e in engs]))
+        stage_tot[api.T_COST] += float(np.mean([e.stage_ms(api.T_COST) for e in engs]))
+        stage_tot[api.T_POST] += float(np.mean([e.stage_ms(api.T_POST) for e in engs]))
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - launches0
+    t_wall = (time.perf_counter() - t_wall) * 1e3
+    # the frames run on their own streams: the default-stream events bracket host-synchronised steps, so take the larger
+    ms_max = maxms(max(ev0.elapsed_time(ev1), t_wall))
+    launches = sum(e.launch_count() for e in engs) - launches0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     agg_ms = stage_tot[api.T_AGG]
-    value = world * W * H * D * args.steps / (ms_max * 1e-3) / 1e6
+    value = world * B * W * H * D * args.steps / (ms_max * 1e-3) / 1e6
 
     # ---- end to end through the public call with host buffers (H2D + pipeline + D2H inside the timed region)
-    out_l = torch.empty(W * H, dtype=torch.float32).pin_memory(); out_r = torch.empty(W * H, dtype=torch.float32).pin_memory()
-    import ctypes as C
-
     def e2e_step():
-        eng.set_images(hl.numpy(), hr.numpy())
-        eng._ck(eng.L.s3dmst_run_dense(eng.h, D, 1, C.c_void_p(out_l.data_ptr()), C.c_void_p(out_r.data_ptr())))
+        for e, (hl, hr) in zip(engs, pin):
+            e.set_images(hl.numpy(), hr.numpy())
+        api.run_dense_batch(engs, D, fill=True, out=outs)
 
     for _ in range(2):
         e2e_step()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = world * W * H * D * args.steps / (e2e_ms * 1e-3) / 1e6
+    e2e_ms = maxms((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * B * W * H * D * args.steps / (e2e_ms * 1e-3) / 1e6
+
+    # ---- single-frame latency (one pair alone on the GPU, forest kernel on every SM)
+    lat = api.Stereo3DMST(device=local)
+    lat.set_images(pin[0][0].numpy(), pin[0][1].numpy())
+    for _ in range(3):
+        lat.run_dense(D, fill=True, fetch=False)
+    lat.sync()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        lat.run_dense(D, fill=True, fetch=False)
+    lat.sync()
+    single_ms = (time.perf_counter() - t0) * 1e3 / 5
+    single_stages = {k: float(lat.stage_ms(i)) for i, k in enumerate(("forest", "cost", "aggregate", "post"))}
+    lat.close()
 
     if rank == 0:
         peak, peak_src = read_peaks()
-        n_agg_launch = args.steps                          # ONE aggregation launch per step covers both views' trees
-        per_launch_ms = agg_ms / n_agg_launch
-        alg_bytes = ALG_BYTES_PER_PXLABEL * W * H * D * 2  # both views
+        per_launch_ms = agg_ms / args.steps                # one aggregation launch set per step covers every frame's trees
+        alg_bytes = ALG_BYTES_PER_PXLABEL * W * H * D * 2 * B  # both views of B frames
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("k_agg_dense2_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("k_agg_flow_bytes_per_frame")
+                traffic = traffic * B if traffic else None
             except Exception:
                 traffic = None
         cpu = cpu_baseline_serial() if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded x{world}, no collective",
-                       "l2": "working set per step (2.8 GB of cost + running sums) exceeds the 126 MB L2; no explicit flush",
+            "ms_per_step": ms_max / args.steps, "ms_per_frame": ms_max / args.steps / B, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": f"frame-sharded x{world}, no collective",
+                       "batching": "frames of a step run on their own contexts/streams; one tree-aggregation launch covers the whole batch",
+                       "l2": f"working set per step ({2.8 * B:.0f} GB of cost + running sums) exceeds the 126 MB L2; no explicit flush",
                        "mode": "exact (fp64, reference association order)"},
             "stage_ms_per_step": {k: float(stage_tot[i] / args.steps) for i, k in enumerate(("forest", "cost", "aggregate", "post"))},
-            "roofline": {"bound": "hbm", "kernel": "k_agg_dense2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "single_frame": {"ms_per_frame": single_ms, "stage_ms": single_stages},
+            "roofline": {"bound": "hbm", "kernel": "k_agg_flow", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp64_traffic_model_gbs": 20.0 * W * H * D * 2 / (per_launch_ms * 1e-3) / 1e9},
+                         "fp64_traffic_model_gbs": 20.0 * W * H * D * 2 * B / (per_launch_ms * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": METRIC, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": 2 * W * H * 3, "d2h_bytes_per_step": 2 * W * H * 4},
+                    "h2d_bytes_per_step": 2 * W * H * 3 * B, "d2h_bytes_per_step": 2 * W * H * 4 * B},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    eng.close()
+    for e in engs:
+        e.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -266,8 +289,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--agg-threads", type=int, default=0)
-    ap.add_argument("--agg-cache", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=8, help="stereo pairs per step per GPU")
+    ap.add_argument("--fh-ctas", type=int, default=36, help="CTAs of the forest kernel per frame when batching")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -55,6 +55,7 @@ typedef struct s3dmst_params {
     int agg_cache_nodes;/* 0 = auto; nodes of a tree level cached in shared memory per CTA          */
     int agg_ring_nodes; /* 0 = auto; node rows staged ahead per CTA by the bulk-copy (TMA) pipeline      */
     int agg_kernel;     /* 0 = auto (dataflow kernel), 1 = simple level-synchronous kernel, 2 = TMA tile kernel */
+    int fh_ctas;        /* 0 = one CTA per SM; CTAs of the cooperative forest kernel (batches: ~1/4 of the SMs per frame) */
 } s3dmst_params;
 
 void s3dmst_default_params(s3dmst_params* p);
@@ -132,6 +133,13 @@ int s3dmst_lr_check(s3dmst_ctx* ctx, int fill);
 /* Whole dense pipeline on the current images: forests, cost volume, aggregation + WTA for both views,
  * LR check (+fill).  Outputs float[H][W] (NULL = leave on device). */
 int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp);
+
+/* The same pipeline over a batch of frames, one context per frame (all on one device, same image size; images set
+ * with s3dmst_set_images on each).  Forest and cost stages of the frames run concurrently on the contexts' streams
+ * (one host thread each), the tree aggregation of ALL frames is one launch (frames are independent: the trees of a
+ * batch fill the GPU where a single pair waits on its deepest tree), then LR check/fill per frame.
+ * left_disp[i] / right_disp[i]: float[H][W] per frame (the arrays or any entry may be NULL). */
+int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp);
 
 /* Per-stage device time of the most recent call, in ms (CUDA events on the context's stream). */
 enum {

@@ -32,7 +32,8 @@ class S3Params(C.Structure):
     _fields_ = [("fh_c", C.c_float), ("min_cc_size", C.c_int), ("gamma", C.c_float), ("median", C.c_int),
                 ("cost_cap", C.c_float), ("cost_offset", C.c_float), ("cost_scale", C.c_float), ("oob_cost", C.c_float),
                 ("num_iter", C.c_int), ("refine_floor", C.c_float), ("exact", C.c_int), ("keep_aggregated", C.c_int),
-                ("agg_threads", C.c_int), ("agg_cache_nodes", C.c_int), ("agg_ring_nodes", C.c_int), ("agg_kernel", C.c_int)]
+                ("agg_threads", C.c_int), ("agg_cache_nodes", C.c_int), ("agg_ring_nodes", C.c_int), ("agg_kernel", C.c_int),
+                ("fh_ctas", C.c_int)]
 
 
 # every symbol include/s3dmst.h declares (tests/test_abi.py checks the library exports all of them)
@@ -42,7 +43,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_stage_ms", "s3dmst_launch_count",
 ]
 
 _lib = None
@@ -88,6 +89,7 @@ def load_library():
     L.s3dmst_get_disparity.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_lr_check.argtypes = [c_p, C.c_int]
     L.s3dmst_run_dense.argtypes = [c_p, C.c_int, C.c_int, c_p, c_p]
+    L.s3dmst_run_dense_batch.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_stage_ms.argtypes = [c_p, C.c_int]
     L.s3dmst_stage_ms.restype = C.c_double
     L.s3dmst_launch_count.argtypes = [c_p]
@@ -291,6 +293,34 @@ class Stereo3DMST:
 
     def launch_count(self):
         return self.L.s3dmst_launch_count(self.h)
+
+
+def run_dense_batch(engines, D, fill=False, fetch=True, out=None):
+    """s3dmst_run_dense_batch over a list of Stereo3DMST handles (one frame each, images already set): forest and cost
+    stages of the frames overlap, one aggregation launch covers every frame's trees.  Returns [(left, right), ...]
+    (float32 [N]) when fetch, else None.  `out` = optional [(left, right), ...] of preallocated (e.g. pinned) buffers."""
+    n = len(engines)
+    L = engines[0].L
+    hs = (c_p * n)(*[e.h for e in engines])
+    if out is None and fetch:
+        out = [(np.empty(e.N, np.float32), np.empty(e.N, np.float32)) for e in engines]
+    if out is not None:
+        pl = (c_p * n)(*[c_p(_addr(o[0])) for o in out])
+        pr = (c_p * n)(*[c_p(_addr(o[1])) for o in out])
+    else:
+        pl = pr = None
+    rc = L.s3dmst_run_dense_batch(hs, n, int(D), int(fill), pl, pr)
+    if rc != 0:
+        raise S3Error(f"s3dmst error {rc}: {L.s3dmst_last_error(engines[0].h).decode()}")
+    for e in engines:
+        e.D = D
+    return out
+
+
+def _addr(a):
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
 
 
 def stereo3dmst(left_name, right_name, leftImg, rightImg, leftDisp=None, rightDisp=None, data_cost="MCCNN_acrt", Dmax=100,

@@ -61,7 +61,7 @@ struct Agg3View {
 };
 
 struct Agg3Args {
-    Agg3View v[2];
+    const Agg3View* views;  // device table: [frame][view] of every context in the launch
     const int4* units;  // {view, tree, first label, slice index}, longest tree first
     int Dp, d1, N, n_slices;
     int unit0;          // first unit of this launch
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, WM = W - 1;
 
     const int4 unit = A.units[A.unit0 + blockIdx.x];
-    const Agg3View& V = A.v[unit.x];
+    const Agg3View V = A.views[unit.x];
     const int t = unit.y, l0 = unit.z, slice = unit.w;
     const int base = V.tree_start[t], end = V.tree_start[t + 1], top = end - 1;
     const size_t Dp = (size_t)A.Dp;
@@ -421,20 +421,28 @@ __global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node
     best[pix] = bc;
 }
 
-// views_mask: bit 0 = left, bit 1 = right.  Both views must hold volumes of the same D.
+// One launch over the trees of every view in `views_mask` (bit 0 = left, bit 1 = right) of every context in `ctxs`
+// (all on one device, same image size and D): the unit list spans frames, so a batch of stereo pairs fills the GPU with
+// independent trees instead of waiting on the deepest tree of a single pair.  Runs on ctxs[0]'s stream; the other
+// contexts' streams are ordered before and after it with events.
 // Returns 1 (and does nothing) if this kernel cannot serve the request, so the caller falls back to the simple one.
-int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
-    int nviews = 0, first = -1;
-    for (int view = 0; view < 2; view++) {
-        if (!(views_mask & (1 << view))) continue;
-        View& V = ctx->v[view];
-        if (!V.forest_ready || !V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense: forest and cost volume required");
-        if (first < 0) first = view;
-        if (V.D != ctx->v[first].D) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: views hold different D");
-        nviews++;
-    }
-    if (!nviews) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: empty view mask");
+int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1) {
+    s3dmst_ctx* ctx = ctxs[0];
+    int first = -1;
+    for (int view = 0; view < 2 && first < 0; view++)
+        if (views_mask & (1 << view)) first = view;
+    if (first < 0) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: empty view mask");
     const int Dv = ctx->v[first].D, Dp = ctx->v[first].Dp;
+    for (int c = 0; c < nctx; c++) {
+        if (ctxs[c]->device != ctx->device || ctxs[c]->N != ctx->N)
+            return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: batched contexts must share the device and the image size");
+        for (int view = 0; view < 2; view++) {
+            if (!(views_mask & (1 << view))) continue;
+            View& V = ctxs[c]->v[view];
+            if (!V.forest_ready || !V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense: forest and cost volume required");
+            if (V.D != Dv) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: views hold different D");
+        }
+    }
     if (d0 < 0 || d1 > Dv || d0 >= d1) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: need 0 <= d0 < d1 <= D");
     if (d0 & 3) return 1;  // 16-byte row alignment of the lane's label pairs
     const int nl = d1 - d0;
@@ -443,57 +451,74 @@ int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     const int SW = 64 * NH;
     const int n_slices = (nl + SW - 1) / SW;
 
-    // unit list: (tree, slice) of the requested views, longest (most nodes) tree first
+    // unit list: (frame/view, tree, slice), longest (most nodes) tree first
     std::vector<std::pair<int, int4>> u;
-    for (int view = 0; view < 2; view++) {
-        if (!(views_mask & (1 << view))) continue;
-        View& V = ctx->v[view];
-        for (int t = 0; t < V.T; t++)
-            for (int s = 0; s < n_slices; s++) u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(view, t, d0 + s * SW, s)});
-    }
+    for (int c = 0; c < nctx; c++)
+        for (int view = 0; view < 2; view++) {
+            if (!(views_mask & (1 << view))) continue;
+            View& V = ctxs[c]->v[view];
+            for (int t = 0; t < V.T; t++)
+                for (int s = 0; s < n_slices; s++)
+                    u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(2 * c + view, t, d0 + s * SW, s)});
+        }
     std::stable_sort(u.begin(), u.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     std::vector<int4> units(u.size());
     for (size_t i = 0; i < u.size(); i++) units[i] = u[i].second;
-    const size_t ubytes = units.size() * sizeof(int4);
-    if (ctx->units_cap < ubytes) {
+
+    // per-view tables and (for several slices) partial WTA results
+    std::vector<Agg3View> table(2 * (size_t)nctx);
+    memset(table.data(), 0, table.size() * sizeof(Agg3View));
+    std::vector<int32_t*> pdisp(2 * (size_t)nctx, nullptr);
+    std::vector<double*> pbest(2 * (size_t)nctx, nullptr);
+    for (int c = 0; c < nctx; c++) {
+        s3dmst_ctx* cx = ctxs[c];
+        if (n_slices > 1) {
+            const size_t per_view = (size_t)n_slices * cx->N * (sizeof(double) + sizeof(int32_t));
+            const size_t need = 2 * per_view;
+            if (cx->pms_scratch_cap < need) {
+                if (cx->pms_scratch) S3_CUDA(cudaFree(cx->pms_scratch));
+                cx->pms_scratch = nullptr; cx->pms_scratch_cap = 0;
+                S3_CUDA(cudaMalloc(&cx->pms_scratch, need));
+                cx->pms_scratch_cap = need;
+            }
+            for (int view = 0; view < 2; view++) {
+                pbest[2 * c + view] = (double*)((char*)cx->pms_scratch + view * per_view);
+                pdisp[2 * c + view] = (int32_t*)(pbest[2 * c + view] + (size_t)n_slices * cx->N);
+            }
+        }
+        for (int view = 0; view < 2; view++) {
+            View& V = cx->v[view];
+            Agg3View& G = table[2 * c + view];
+            G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn;
+            G.cost = V.cost; G.aup = V.aup;
+            G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
+        }
+    }
+    const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16;
+    if (ctx->units_cap < ubytes + tbytes) {
         if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
         ctx->units_dev = nullptr; ctx->units_cap = 0;
-        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes));
-        ctx->units_cap = ubytes;
+        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes + tbytes));
+        ctx->units_cap = ubytes + tbytes;
     }
-    S3_CUDA(cudaMemcpyAsync(ctx->units_dev, units.data(), ubytes, cudaMemcpyHostToDevice, ctx->stream));
+    char* ubase = reinterpret_cast<char*>(ctx->units_dev);
+    S3_CUDA(cudaMemcpyAsync(ubase, table.data(), table.size() * sizeof(Agg3View), cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaMemcpyAsync(ubase + tbytes, units.data(), ubytes, cudaMemcpyHostToDevice, ctx->stream));
+    // everything the other contexts have queued (their cost volumes) comes first
+    for (int c = 1; c < nctx; c++) {
+        S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
+        S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[c]->ev_xctx, 0));
+    }
 
     Agg3Args A;
     memset(&A, 0, sizeof A);
-    int32_t* pdisp[2] = {nullptr, nullptr};
-    double* pbest[2] = {nullptr, nullptr};
-    if (n_slices > 1) {
-        const size_t per_view = (size_t)n_slices * ctx->N * (sizeof(double) + sizeof(int32_t));
-        const size_t need = 2 * per_view;
-        if (ctx->pms_scratch_cap < need) {
-            if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
-            ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
-            S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
-            ctx->pms_scratch_cap = need;
-        }
-        for (int view = 0; view < 2; view++) {
-            pbest[view] = (double*)((char*)ctx->pms_scratch + view * per_view);
-            pdisp[view] = (int32_t*)(pbest[view] + (size_t)n_slices * ctx->N);
-        }
-    }
-    for (int view = 0; view < 2; view++) {
-        View& V = ctx->v[view];
-        Agg3View& G = A.v[view];
-        G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn;
-        G.cost = V.cost; G.aup = V.aup;
-        G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[view]; G.pbest = pbest[view];
-    }
-    A.units = reinterpret_cast<const int4*>(ctx->units_dev);
+    A.views = reinterpret_cast<const Agg3View*>(ubase);
+    A.units = reinterpret_cast<const int4*>(ubase + tbytes);
     A.Dp = Dp; A.d1 = d1; A.N = ctx->N; A.n_slices = n_slices;
     A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
     A.keep = ctx->P.keep_aggregated;
 
-    // the biggest trees get 32 warps and an SM of their own; the rest 16 warps, two trees per SM
+    // all but the smallest trees get 32 warps and an SM of their own; the rest 16 warps, two trees per SM
     static const int big_nodes = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
     int n_big = 0;
     while (n_big < (int)u.size() && u[n_big].first >= big_nodes) n_big++;
@@ -508,7 +533,7 @@ int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
         S3_LAUNCH_CHECK();                                                                                                     \
     } while (0)
     // ring geometry: rows R and hand-over distance NEAR (>= S3_AGG_NEAR, the distance the forest stage flags nodes by).
-    // A warp may not run more than (R - NEAR) / W rounds ahead of the slowest one, so R - NEAR >= ~4 W.
+    // A warp may not run more than (R - NEAR) / W rounds ahead of the slowest one, so R - NEAR >= ~2 W.
 #define A3_DISPATCH(BIG_, RB_, NEARB_, GRID_, THREADS_)                                                 \
     do {                                                                                               \
         if (NH == 2) {                                                                                 \
@@ -519,29 +544,38 @@ int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) {
     } while (0)
     if (n_big) {
         A.unit0 = 0;
-        A3_DISPATCH(true, 256, 64, n_big, 1024);   // 128 KB ring (64-label slices) / 64 KB... one tree per SM
+        A3_DISPATCH(true, 256, 64, n_big, 1024);   // 128 KB ring, one tree per SM
     }
     if (n_small) {
         A.unit0 = n_big;
-        A3_DISPATCH(false, 128, 32, n_small, 512);  // 64 KB ring: three trees per SM by shared memory, two by registers
+        A3_DISPATCH(false, 128, 32, n_small, 512);  // 64 KB ring: two trees per SM
     }
 #undef A3_DISPATCH
 #undef A3_LAUNCH
     if (n_slices > 1) {
-        for (int view = 0; view < 2; view++) {
-            if (!(views_mask & (1 << view))) continue;
-            View& V = ctx->v[view];
-            k_wta_finish3<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, n_slices, V.node_dn, pdisp[view], pbest[view], V.disp_i, V.best);
-            S3_LAUNCH_CHECK();
-        }
+        for (int c = 0; c < nctx; c++)
+            for (int view = 0; view < 2; view++) {
+                if (!(views_mask & (1 << view))) continue;
+                View& V = ctxs[c]->v[view];
+                k_wta_finish3<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, n_slices, V.node_dn, pdisp[2 * c + view], pbest[2 * c + view], V.disp_i, V.best);
+                S3_LAUNCH_CHECK();
+            }
     }
     S3_EV_END(S3DMST_T_AGG, first);
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // `units` (host vector) is read by the async copy above
-    for (int view = 0; view < 2; view++)
-        if (views_mask & (1 << view)) {
-            ctx->v[view].agg_ready = true;
-            ctx->v[view].agg_d0 = d0;
-            ctx->v[view].agg_d1 = d1;
-        }
+    // the other contexts continue (WTA results -> disparity maps) only after the joint launch
+    if (nctx > 1) {
+        S3_CUDA(cudaEventRecord(ctx->ev_xctx, ctx->stream));
+        for (int c = 1; c < nctx; c++) S3_CUDA(cudaStreamWaitEvent(ctxs[c]->stream, ctx->ev_xctx, 0));
+    }
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host staging vectors are read by the async copies above
+    for (int c = 0; c < nctx; c++)
+        for (int view = 0; view < 2; view++)
+            if (views_mask & (1 << view)) {
+                ctxs[c]->v[view].agg_ready = true;
+                ctxs[c]->v[view].agg_d0 = d0;
+                ctxs[c]->v[view].agg_d1 = d1;
+            }
     return 0;
 }
+
+int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) { return s3_aggregate_flow_multi(&ctx, 1, views_mask, d0, d1); }

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -101,6 +102,7 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->agg_cache_nodes = 0;
     p->agg_ring_nodes = 0;
     p->agg_kernel = 0;
+    p->fh_ctas = 0;
 }
 
 int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream) {
@@ -128,6 +130,7 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
         ctx->own_stream = ok;
     }
     for (int i = 0; ok && i < S3DMST_T_COUNT * 4; i++) ok = cudaEventCreate(&ctx->ev[i / 4][(i / 2) & 1][i & 1]) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_xctx, cudaEventDisableTiming) == cudaSuccess;
     if (ok) {
         // weights (Stereo3DMST.cpp:444, :513): exp(-w*gamma) in double with gamma promoted from float
         std::vector<double> w(S3_NUM_W), w2(S3_NUM_W);
@@ -162,6 +165,7 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev); DFREE(ctx->fh_sync);
     for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
         if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
+    if (ctx->ev_xctx) cudaEventDestroy(ctx->ev_xctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -564,6 +568,63 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     D2H(left_disp, ctx->v[0].disp_f, sizeof(float) * ctx->N);
     D2H(right_disp, ctx->v[1].disp_f, sizeof(float) * ctx->N);
     if (left_disp || right_disp) S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {
+    if (!ctxs || n < 1) return S3DMST_E_ARG;
+    s3dmst_ctx* ctx = ctxs[0];
+    for (int c = 0; c < n; c++)
+        if (!ctxs[c] || ctxs[c]->device != ctx->device || ctxs[c]->N != ctx->N || ctxs[c]->N == 0)
+            return s3_fail(ctx, S3DMST_E_ARG, "run_dense_batch: contexts must share the device and hold images of one size");
+    // forest + cost volume per frame: independent streams, one host thread each (the forest stage reads tree counts back)
+    std::vector<int> rc(n, 0);
+    auto front = [&](int c) {
+        s3dmst_ctx* cx = ctxs[c];
+        rc[c] = [&]() -> int {
+            s3dmst_ctx* ctx = cx;  // the error macros report into this frame's context
+            S3_CUDA(cudaSetDevice(ctx->device));
+            memset(ctx->ev_set, 0, sizeof ctx->ev_set);
+            S3_EV_BEGIN(S3DMST_T_FOREST, 0);
+            S3_TRY(s3_forest_stage_mask(ctx, 3));
+            S3_EV_END(S3DMST_T_FOREST, 0);
+            S3_TRY(s3_cost_adgrad(ctx, D, 0));
+            return 0;
+        }();
+    };
+    if (n == 1)
+        front(0);
+    else {
+        std::vector<std::thread> th;
+        for (int c = 0; c < n; c++) th.emplace_back(front, c);
+        for (auto& t : th) t.join();
+    }
+    for (int c = 0; c < n; c++)
+        if (rc[c]) return c == 0 ? rc[c] : s3_fail(ctx, rc[c], "run_dense_batch: frame %d: %s", c, ctxs[c]->err.c_str());
+    S3_CUDA(cudaSetDevice(ctx->device));
+    {
+        int r = ctx->P.agg_kernel == 0 ? s3_aggregate_flow_multi(ctxs, n, 3, 0, D) : 1;
+        if (r == 1) {
+            r = 0;
+            for (int c = 0; c < n && !r; c++)
+                for (int view = 0; view < 2 && !r; view++) {
+                    r = s3_aggregate_dense(ctxs[c], view, 0, D);
+                    if (r && c) r = s3_fail(ctx, r, "run_dense_batch: frame %d: %s", c, ctxs[c]->err.c_str());
+                }
+        }
+        if (r) return r;
+    }
+    for (int c = 0; c < n; c++) {
+        s3dmst_ctx* cx = ctxs[c];
+        int r = s3_dense_to_disp(cx, 0);
+        if (!r) r = s3_dense_to_disp(cx, 1);
+        if (!r) r = s3_lr_check(cx, fill);
+        if (r) return c == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frame %d: %s", c, cx->err.c_str());
+        if (left_disp && left_disp[c]) S3_CUDA(cudaMemcpyAsync(left_disp[c], cx->v[0].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
+        if (right_disp && right_disp[c]) S3_CUDA(cudaMemcpyAsync(right_disp[c], cx->v[1].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
+    }
+    if (left_disp || right_disp)
+        for (int c = 0; c < n; c++) S3_CUDA(cudaStreamSynchronize(ctxs[c]->stream));
     return 0;
 }
 

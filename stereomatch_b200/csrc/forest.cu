@@ -750,7 +750,8 @@ int s3_fh_launch(s3dmst_ctx* ctx, int mask) {
         ctas_per_sm = n;
     }
     if (ctas_per_sm < 1) return s3_fail(ctx, S3DMST_E_CUDA, "k_fh_merge does not fit on an SM");
-    const int grid = std::max(nv, std::min(ctx->num_sms, S3_FH_MAX_CTAS));
+    const int want = ctx->P.fh_ctas > 0 ? ctx->P.fh_ctas : ctx->num_sms;
+    const int grid = std::max(nv, std::min(std::min(want, ctx->num_sms * ctas_per_sm), S3_FH_MAX_CTAS));
     const int per_view = grid / nv;
     AA.nviews = nv;
     AA.seg_cap = (2 * ctx->N + per_view - 1) / per_view + S3_FH_SEG_SLACK;

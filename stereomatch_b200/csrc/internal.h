@@ -112,7 +112,8 @@ struct s3dmst_ctx {
     long long launches = 0;
     std::string err;
     // scratch for PMS
-    uint32_t* units_dev = nullptr;  // aggregation work units (view<<31 | tree), longest first
+    cudaEvent_t ev_xctx = nullptr;  // orders this context's stream against another context's in batched launches
+    uint32_t* units_dev = nullptr;  // aggregation work units + view table of the current launch
     size_t units_cap = 0;
     int* fh_sync = nullptr;         // grid barrier + per-round live counters of the forest kernel
     void* pms_scratch = nullptr;
@@ -162,6 +163,7 @@ int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
 int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined, level-synchronous tiles)
 int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1);    // aggregate3.cu (dataflow, default)
+int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1);  // one launch over several frames
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
 int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax);          // pms.cu: the reference's random plane initialisation
 int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed, const std::vector<int>& adj_ptr, const std::vector<int>& adj);

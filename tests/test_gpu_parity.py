@@ -349,6 +349,35 @@ def test_run_dense_end_to_end(api, oracle):
     eng.close()
 
 
+def test_run_dense_batch_matches_single_frames(api, oracle):
+    """Batched pipeline (s3dmst_run_dense_batch): frames on their own contexts/streams, one aggregation launch over all
+    frames' trees, reduced forest-kernel grid — results identical to the oracle frame by frame."""
+    W, H, D = 200, 120, 40
+    frames = [make(W, H, D, 60 + i, i % 2) for i in range(3)]
+    engs = []
+    for L, R, _ in frames:
+        e = api.Stereo3DMST(fh_ctas=24)
+        e.set_images(L, R)
+        engs.append(e)
+    outs = api.run_dense_batch(engs, D, fill=True)
+    for (L, R, _), (dl, dr) in zip(frames, outs):
+        lv, rv = oracle.cost_adgrad(L, R, D)
+        dlo = oracle.aggregate_dense(oracle.forest(L), lv)[0].astype(np.float32)
+        dro = oracle.aggregate_dense(oracle.forest(R), rv)[0].astype(np.float32)
+        want, _ = oracle.lr_check(dlo, dro, W, H, D, True)
+        assert np.array_equal(bits(dl), bits(want)) and np.array_equal(bits(dr), bits(dro))
+    # a second batch on the same contexts (state reuse) with D not a multiple of the slice width
+    outs = api.run_dense_batch(engs[:2], 36, fill=False)
+    for (L, R, _), (dl, dr) in zip(frames[:2], outs):
+        lv, rv = oracle.cost_adgrad(L, R, 36)
+        dlo = oracle.aggregate_dense(oracle.forest(L), lv)[0].astype(np.float32)
+        dro = oracle.aggregate_dense(oracle.forest(R), rv)[0].astype(np.float32)
+        want, _ = oracle.lr_check(dlo, dro, W, H, 36, False)
+        assert np.array_equal(bits(dl), bits(want)) and np.array_equal(bits(dr), bits(dro))
+    for e in engs:
+        e.close()
+
+
 def test_reference_signature_wrapper(api, oracle):
     W, H, D = 128, 80, 24
     L, R, _ = make(W, H, D, 5, 0)
