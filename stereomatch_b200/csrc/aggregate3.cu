@@ -68,6 +68,7 @@ struct Agg3Args {
     const double* lut_w;
     const double* lut_w2;
     int keep;
+    int sleep_ns;       // back-off of a waiting warp between two polls
 };
 
 __device__ __forceinline__ uint32_t a3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     if (tid < 32) s_prog[tid] = end;  // up pass: node c is done iff its owner's word is <= c
     __syncthreads();
     const uint32_t prog_a = a3_smem(s_prog);
+    const unsigned sleep_ns = (unsigned)A.sleep_ns;
     const uint32_t ring_a = a3_smem(s_ring) + 16u * lane;  // this lane's column of the ring
     const uint32_t w_a = a3_smem(s_w);
     constexpr uint32_t ROWB = NH * 512;                     // bytes of one ring row
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         const double wk = a3_lds_d(w_a + 8u * (IW));                                                                 \
         const uint32_t pa = prog_a + 4u * (uint32_t)((top - c) & WM);                                                \
         A3_CLK(q_pre);                                                                                               \
-        while (a3_ld_acquire(pa) > c) __nanosleep(A3_SLEEP);                                                         \
+        while (a3_ld_acquire(pa) > c) __nanosleep(sleep_ns);                                                         \
         A3_CLK(q_poll);                                                                                              \
         double2 cv[NH];                                                                                              \
         if (c - v < A3_NEAR) {                                                                                       \
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 while (true) {
                     m = __reduce_max_sync(0xffffffffu, lane < W ? a3_ld_acquire(prog_a + 4u * lane) : INT_MIN);
                     if (m < v + A3_R - A3_NEAR + 1 + W) break;
-                    __nanosleep(A3_SLEEP);
+                    __nanosleep(sleep_ns);
                 }
                 guard_ok = m - (A3_R - A3_NEAR + W);
             }
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                     au[h].y = S3_DMUL(wq, au[h].y);
                 }
                 const uint32_t pa = prog_a + 4u * (uint32_t)((p - base) & WM);
-                while (a3_ld_acquire(pa) < p) __nanosleep(A3_SLEEP);
+                while (a3_ld_acquire(pa) < p) __nanosleep(sleep_ns);
                 double2 pv[NH];
                 if (v - p < A3_NEAR) {
                     const uint32_t ra = ring_a + (uint32_t)(p & (A3_R - 1)) * ROWB;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 while (true) {
                     m = __reduce_min_sync(0xffffffffu, lane < W ? a3_ld_acquire(prog_a + 4u * lane) : INT_MAX);
                     if (m > v - A3_R + A3_NEAR - 1 - W) break;
-                    __nanosleep(A3_SLEEP);
+                    __nanosleep(sleep_ns);
                 }
                 guard_ok = m + (A3_R - A3_NEAR + W);
             }
@@ -517,6 +519,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.Dp = Dp; A.d1 = d1; A.N = ctx->N; A.n_slices = n_slices;
     A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
     A.keep = ctx->P.keep_aggregated;
+    static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
+    A.sleep_ns = sleep_env ? sleep_env : 20;
 
     // all but the smallest trees get 32 warps and an SM of their own; the rest 16 warps, two trees per SM
     static const int big_nodes = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;

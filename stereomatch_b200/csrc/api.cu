@@ -43,7 +43,7 @@ static void free_view(View& V) {
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
     DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
-    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.tile_desc); DFREE(V.tree_ntiles);
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits); DFREE(V.tile_desc); DFREE(V.tree_ntiles);
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
@@ -67,7 +67,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     S3_CUDA(dalloc(&V.tree_size, n)); S3_CUDA(dalloc(&V.tree_rootpix, n));
     S3_CUDA(dalloc(&V.tree_start, n + 1)); S3_CUDA(dalloc(&V.tree_depth, n)); S3_CUDA(dalloc(&V.unit_tree, n));
     S3_CUDA(dalloc(&V.node_pixel, n)); S3_CUDA(dalloc(&V.pixel_node, n)); S3_CUDA(dalloc(&V.parent, n));
-    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.tile_desc, 4 * n)); S3_CUDA(dalloc(&V.tree_ntiles, n));
+    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.leaf_bits, n / 32 + 2)); S3_CUDA(dalloc(&V.tile_desc, 4 * n)); S3_CUDA(dalloc(&V.tree_ntiles, n));
     S3_CUDA(dalloc(&V.lvl_start, 2 * n + 2));
     S3_CUDA(dalloc(&V.disp_i, n)); S3_CUDA(dalloc(&V.best, n)); S3_CUDA(dalloc(&V.abc, 3 * n)); S3_CUDA(dalloc(&V.min_cost, n));
     S3_CUDA(dalloc(&V.disp_f, n)); S3_CUDA(dalloc(&V.lr_mask, n));
@@ -375,9 +375,13 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     for (int i = 0; i < N; i++) {
         if (parent[i] != i && i - parent[i] >= S3_AGG_NEAR) nu[i].child_count |= S3_NU_FARPARENT;
         const bool far_child = (nu[i].child_count & 7) > 0 && nu[i].child_begin + (nu[i].child_count & 7) - 1 - i >= S3_AGG_NEAR;
-        nd[i] = make_int4(parent[i], parent_weight[i], level[i] | (far_child ? S3_ND_FAR : 0), node_pixel[i]);
+        nd[i] = make_int4(parent[i], parent_weight[i], level[i] | (far_child ? S3_ND_FAR : 0) | ((nu[i].child_count & 7) == 0 ? S3_ND_LEAF : 0), node_pixel[i]);
     }
     H2D(V.node_dn, nd.data(), sizeof(int4) * N);
+    std::vector<uint32_t> lbits(N / 32 + 2, 0u);
+    for (int i = 0; i < N; i++)
+        if (nd[i].z & S3_ND_LEAF) lbits[i >> 5] |= 1u << (i & 31);
+    H2D(V.leaf_bits, lbits.data(), sizeof(uint32_t) * lbits.size());
     H2D(V.level, level.data(), sizeof(int) * N);
     H2D(V.pixel_node, pixel_node.data(), sizeof(int) * N);
     H2D(V.tree_id, tree_id.data(), sizeof(int) * N);

@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             nu.cw01 = (cc > 0 ? k0 >> 2 : 0u) | ((cc > 1 ? k1 >> 2 : 0u) << 16);
             nu.cw23 = (cc > 2 ? k2 >> 2 : 0u) | ((cc > 3 ? k3 >> 2 : 0u) << 16);
             node_up[g] = nu;
-            if (cc > 0 && cb + cc - 1 - g >= S3_AGG_NEAR) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_FAR;
+            if (cc == 0) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_LEAF;
+            else if (cb + cc - 1 - g >= S3_AGG_NEAR) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_FAR;
             unsigned long long kk = kids;
             for (int k = 0; k < cc; k++, kk >>= 16) {
                 const uint32_t en = (uint32_t)kk & 0xFFFFu;
@@ -711,13 +712,15 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
 
 // node_dn -> the flat per-node arrays the other stages and the parity dumps read (off the BFS critical path)
 __global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __restrict__ node_pixel, int* __restrict__ parent,
-                             int* __restrict__ level, uint16_t* __restrict__ pw) {
+                             int* __restrict__ level, uint16_t* __restrict__ pw, uint32_t* __restrict__ leaf_bits) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const int4 nd = h < N ? node_dn[h] : make_int4(0, 0, 0, 0);
+    const uint32_t lb = __ballot_sync(0xffffffffu, h < N && (nd.z & S3_ND_LEAF));
+    if ((threadIdx.x & 31) == 0 && h < N) leaf_bits[h >> 5] = lb;
     if (h >= N) return;
-    const int4 nd = node_dn[h];
     parent[h] = nd.x;
     pw[h] = (uint16_t)nd.y;
-    level[h] = nd.z & ~S3_ND_FAR;
+    level[h] = nd.z & ~S3_ND_FLAGS;
     node_pixel[h] = nd.w;
 }
 
@@ -877,7 +880,7 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) {
             View& V = ctx->v[view];
-            k_bfs_unpack<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_dn, V.node_pixel, V.parent, V.level, V.pw);
+            k_bfs_unpack<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_dn, V.node_pixel, V.parent, V.level, V.pw, V.leaf_bits);
             S3_LAUNCH_CHECK();
         }
     for (int view = 0; view < 2; view++)

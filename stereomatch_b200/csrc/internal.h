@@ -17,6 +17,8 @@
 #define S3_AGG_NEAR 32          // dataflow aggregation: a parent/child closer than this (in BFS index) is handed over in shared memory
 #define S3_NU_FARPARENT 0x100    // NodeUp.child_count flag: the node's parent is S3_AGG_NEAR or more nodes away
 #define S3_ND_FAR (1 << 30)      // node_dn.z flag: the node has a child S3_AGG_NEAR or more nodes away
+#define S3_ND_LEAF (1 << 29)     // node_dn.z flag: no children (its leaf->root sum is its cost: never stored)
+#define S3_ND_FLAGS (S3_ND_FAR | S3_ND_LEAF)
 
 // Per-node record read by the leaf->root pass: children are contiguous in BFS order.
 struct __align__(16) NodeUp {
@@ -67,7 +69,8 @@ struct View {
     int* level = nullptr;       // [N]
     uint16_t* pw = nullptr;     // [N]
     NodeUp* node_up = nullptr;  // [N]
-    int4* node_dn = nullptr;    // [N] {parent, parent weight, level, pixel}: the root->leaf pass record
+    int4* node_dn = nullptr;    // [N] {parent, parent weight, level | flags, pixel}: the root->leaf pass record
+    uint32_t* leaf_bits = nullptr;  // [N/32 + 1] bit v = node v is a leaf (prefetch target selection on the way down)
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
     int4* tile_desc = nullptr;  // [4N] ([0,2N) root->leaf order, [2N,4N) leaf->root order); two int4 per tile: {t0, n, loff, flags}, {level end, parent level start, 0, 0};
                                 //      tree t's tiles start at tile index tree_start[t], level-major, ascending nodes
