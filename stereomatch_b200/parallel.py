@@ -90,7 +90,8 @@ def aggregate_dense_label_sharded(eng, view, D, group=None):
         disp.fill_(INT32_MAX)
     eng.sync()
     torch.cuda.synchronize()
-    minloc_reduce(best, disp, group,
-                  mask_fn=lambda gmin: (torch.cuda.synchronize(), eng.minloc_mask(view, gmin.data_ptr()), eng.sync()))
+    gmin, _ = minloc_reduce(best, disp, group,
+                            mask_fn=lambda gmin: (torch.cuda.synchronize(), eng.minloc_mask(view, gmin.data_ptr()), eng.sync()))
+    best.copy_(gmin)  # the context now holds the global minimum next to the global disparity
     torch.cuda.synchronize()
     return best, disp

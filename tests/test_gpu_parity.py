@@ -429,3 +429,18 @@ def test_full_size_c2_properties(api, oracle):
     # sanity only: pixelwise AD+gradient on 2x2 random dots is ambiguous (the oracle scores 0.34 / 0.57 here)
     assert valid.mean() > 0.2 and (err[valid] <= 1.0).mean() > 0.4
     eng.close()
+
+
+def test_label_sharded_two_gpus_nccl(api, oracle):
+    """BASELINE config C5 in small: one pair, label range split over 2 GPUs (torchrun, NCCL), MIN-LOC reduction;
+    every rank's result must equal the oracle's full-range result bit for bit (tools/label_sharded.py --check)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "label_sharded.py"), "--check"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"check": true' in r.stdout
