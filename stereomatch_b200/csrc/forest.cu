@@ -7,23 +7,19 @@
 // (:352-367) and re-index every tree in BFS order from its minimum pixel (:450-522).
 //
 // Parallel formulation (validated edge-for-edge against the sequential code by
-// tests/models/forest_model.py and tests/test_forest_model.py):
-//  * FH decomposes exactly by integer weight level.  A component closed at level w (w > thr) stays
-//    closed for ever; a component that merges at level w is open for the rest of the level
-//    (thr = w + c/size >= w).  Hence inside one level the accepted edges are the minimum spanning
-//    forest, under the key "edge id" (== the reference's (a,b) tie-break: right edge 2p before down
-//    edge 2p+1, ascending p), of the level's edges between open components: Boruvka rounds with
-//    atomicMin picks.  thr is never stored: thr(r) = lastw[r] + f32(c)/f32(size[r]).
+// tests/models/forest_model.py + tests/test_forest_model.py on the CPU and tests/test_gpu_parity.py on the GPU):
+//  * FH: asynchronous exact rounds over a weight-ordered live prefix of the edges — see k_fh_merge.  thr is never
+//    stored: thr(r) = lastw[r] + f32(c)/f32(size[r]).  Edge key (w, edge id) == the reference's (w, a, b) order
+//    (right edge 2p before down edge 2p+1, ascending p).
 //  * The min-size merge is order dependent; it is replayed with deterministic reservations: every
 //    pending edge atomicMin's its key (w<<32 | id) onto both endpoint components; an edge commits
 //    when each endpoint component is either already >= m (its size can no longer matter) or holds
 //    this edge as its reservation (no earlier pending edge touches it).  Edges between two big
 //    components can never fire and are dropped.
-//  Both phases run in ONE persistent cooperative kernel (grid = all co-resident CTAs, grid.sync()
-//  between phases of a round); a round is: reserve | commit+hook | size/cleanup.
-//  * BFS: one CTA per tree, level-synchronous inside the CTA; children of a node are its forest
-//    neighbours except the parent, ordered by (w, edge id) (= the reference's adjacency insertion
-//    order), numbered by a block-wide exclusive scan so BFS numbering equals the reference's queue order.
+//  Both phases run in ONE persistent cooperative kernel (software grid barrier between the phases of a round).
+//  * BFS: one CTA per tree, level-synchronous inside the CTA (narrow levels: one warp, no block barrier); children
+//    of a node are its forest neighbours except the parent, ordered by (w, edge id) (= the reference's adjacency
+//    insertion order), numbered by an exclusive scan so BFS numbering equals the reference's queue order.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
