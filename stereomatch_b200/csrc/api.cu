@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <thread>
 #include <vector>
@@ -103,6 +104,7 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->agg_ring_nodes = 0;
     p->agg_kernel = 0;
     p->fh_ctas = 0;
+    p->fh_threads = 0;
 }
 
 int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream) {
@@ -582,6 +584,10 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
         if (!ctxs[c] || ctxs[c]->device != ctx->device || ctxs[c]->N != ctx->N || ctxs[c]->N == 0)
             return s3_fail(ctx, S3DMST_E_ARG, "run_dense_batch: contexts must share the device and hold images of one size");
     // forest + cost volume per frame: independent streams, one host thread each (the forest stage reads tree counts back)
+    const bool dbg = getenv("S3_DEBUG_BATCH") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    std::vector<double> t_forest(n, 0.0);
     std::vector<int> rc(n, 0);
     auto front = [&](int c) {
         s3dmst_ctx* cx = ctxs[c];
@@ -592,7 +598,9 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
             S3_EV_BEGIN(S3DMST_T_FOREST, 0);
             S3_TRY(s3_forest_stage_mask(ctx, 3));
             S3_EV_END(S3DMST_T_FOREST, 0);
+            if (dbg) { cudaStreamSynchronize(ctx->stream); t_forest[c] = now(); }
             S3_TRY(s3_cost_adgrad(ctx, D, 0));
+            if (dbg) cudaStreamSynchronize(ctx->stream);
             return 0;
         }();
     };
@@ -606,6 +614,7 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
     for (int c = 0; c < n; c++)
         if (rc[c]) return c == 0 ? rc[c] : s3_fail(ctx, rc[c], "run_dense_batch: frame %d: %s", c, ctxs[c]->err.c_str());
     S3_CUDA(cudaSetDevice(ctx->device));
+    const double t_front = now();
     {
         int r = ctx->P.agg_kernel == 0 ? s3_aggregate_flow_multi(ctxs, n, 3, 0, D) : 1;
         if (r == 1) {
@@ -627,8 +636,13 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
         if (left_disp && left_disp[c]) S3_CUDA(cudaMemcpyAsync(left_disp[c], cx->v[0].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
         if (right_disp && right_disp[c]) S3_CUDA(cudaMemcpyAsync(right_disp[c], cx->v[1].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
     }
-    if (left_disp || right_disp)
+    if (left_disp || right_disp || dbg)
         for (int c = 0; c < n; c++) S3_CUDA(cudaStreamSynchronize(ctxs[c]->stream));
+    if (dbg) {
+        double tf = 0.0;
+        for (int c = 0; c < n; c++) tf = std::max(tf, t_forest[c]);
+        fprintf(stderr, "[batch %d] forests done +%.2f ms, cost volumes done +%.2f ms, total %.2f ms\n", n, tf - t_begin, t_front - t_begin, now() - t_begin);
+    }
     return 0;
 }
 

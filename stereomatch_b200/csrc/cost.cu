@@ -23,50 +23,105 @@ struct CostArgs {
     float cap, offset, scale;
 };
 
-// one warp per pixel; lane owns labels 4*lane + 128*it .. +3 (16-byte stores, 512 B per warp-store)
+// One CTA per 128-pixel row segment (8 warps x 16 pixels); a lane owns labels lane + 32*j of a pixel, so that a warp
+// reads 32 consecutive window entries per shared-memory access (no bank conflicts) and stores 128 contiguous bytes.
+// Every label of the segment reads the OTHER view's image inside one contiguous window of the same row (left volume:
+// right pixels x0-(D-1) .. x0+128; right volume: left pixels x0 .. x0+128+D), so the window (packed BGR + gray) is
+// staged into shared memory once — with two bulk copies (TMA, cp.async.bulk + mbarrier) when the window lies inside the
+// row and the row pitch keeps it 16-byte aligned, with plain coalesced loads at the image borders — and the inner loop
+// touches shared memory only.  The colour term depends on the integer L1 distance alone and saturates at L1 = 21: a
+// 22-entry table built with the oracle's exact expression lives in the lanes' registers (one shuffle per label) and
+// replaces the int->double->float chain; the L1 distance itself is two SIMD-in-word instructions.
+#define CV_TP 128       // pixels per CTA
+#define CV_MAXWIN 1216  // window entries: CV_TP + Dp + 8 (Dp <= 1080)
+__device__ __forceinline__ uint32_t cv_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int VIEW>
 __global__ void __launch_bounds__(256) k_cost_adgrad(CostArgs A) {
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int N = A.W * A.H;
-    if (warp_global >= N) return;
-    const int p = warp_global;
-    const int x = p % A.W, rowbase = p - x;
-    float* row = A.cost + (size_t)A.pixel_node[p] * A.Dp;
-    // the pixel of this view
-    const uchar4 me = A.view == 0 ? A.left4[p] : A.right4[p];
-    const float me_g = A.view == 0 ? A.lgray[p] : A.rgray[p];
-    const bool has_next = x + 1 < A.W;
-    const float me_gn = has_next ? (A.view == 0 ? A.lgray[p + 1] : A.rgray[p + 1]) : 0.0f;
-    for (int d4 = 4 * lane; d4 < A.Dp; d4 += 128) {
-        float out[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int d = d4 + e;
-            float c = 3.0f;  // bad_cost, and the value of never-written left entries (Q19)
-            if (d < A.D) {
-                if (A.view == 0) {
-                    // left volume at (d, x): ref = right(x-d), match = left(x); valid iff x-d >= 0 and x+1 < W
-                    const int xr = x - d;
-                    if (xr >= 0 && has_next) {
-                        const uchar4 r = A.right4[rowbase + xr];
-                        c = s3_adgrad(r.x, r.y, r.z, A.rgray[rowbase + xr], A.rgray[rowbase + xr + 1], me.x, me.y, me.z,
-                                      me_g, me_gn);
-                    }
-                } else {
-                    // right volume at (d, x): ref = right(x), match = left(x+d); valid iff x+d+1 < W
-                    const int xl = x + d;
-                    if (xl + 1 < A.W) {
-                        const uchar4 m = A.left4[rowbase + xl];
-                        c = s3_adgrad(me.x, me.y, me.z, me_g, me_gn, m.x, m.y, m.z, A.lgray[rowbase + xl],
-                                      A.lgray[rowbase + xl + 1]);
-                    }
-                }
-                if (A.ingest) c = s3_ingest(c, A.cap, A.offset, A.scale);
-            } else
-                c = 0.0f;  // row padding
-            out[e] = c;
+    __shared__ __align__(16) uint32_t s_win4[CV_MAXWIN];
+    __shared__ __align__(16) float s_wing[CV_MAXWIN];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = A.W, D = A.D, Dp = A.Dp;
+    const int segs = (W + CV_TP - 1) / CV_TP;
+    const int y = blockIdx.x / segs, x0 = (blockIdx.x % segs) * CV_TP;
+    const int rowbase = y * W;
+    const uchar4* other4 = VIEW == 0 ? A.right4 : A.left4;
+    const float* otherg = VIEW == 0 ? A.rgray : A.lgray;
+    const uchar4* me4 = VIEW == 0 ? A.left4 : A.right4;
+    const float* meg = VIEW == 0 ? A.lgray : A.rgray;
+    // window [xs, xs + nwin) of the other image's row: every (x, d) of this segment plus the right neighbour
+    const int Dr = (D + 3) & ~3;
+    const int xs = VIEW == 0 ? x0 - Dr : x0;
+    const int nwin = CV_TP + Dr + 4;  // multiple of 4
+    const bool bulk = (W & 3) == 0 && xs >= 0 && xs + nwin <= W;
+    if (bulk) {
+        const uint32_t bar = cv_smem(&s_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = (uint32_t)nwin * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cv_smem(s_win4)),
+                         "l"(other4 + rowbase + xs), "r"(bytes), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cv_smem(s_wing)),
+                         "l"(otherg + rowbase + xs), "r"(bytes), "r"(bar)
+                         : "memory");
         }
-        *reinterpret_cast<float4*>(row + d4) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+        for (int i = tid; i < nwin; i += 256) {
+            const int x = xs + i;
+            const bool in = x >= 0 && x < W;
+            const uchar4 o = in ? other4[rowbase + x] : make_uchar4(0, 0, 0, 0);
+            s_win4[i] = (uint32_t)o.x | ((uint32_t)o.y << 8) | ((uint32_t)o.z << 16);
+            s_wing[i] = in ? otherg[rowbase + x] : 0.0f;
+        }
+    }
+    // colour term of L1 = lane (lanes >= 21 hold the saturated value): 0.11f * min((float)((double)l1 * 0.33333333333), 7.0f)
+    float ct_lane = (float)S3_DMUL((double)(float)lane, 0.33333333333);
+    ct_lane = ct_lane < 7.0f ? ct_lane : 7.0f;
+    ct_lane = S3_FMUL(0.11f, ct_lane);
+    __syncthreads();
+    if (bulk) {
+        const uint32_t bar = cv_smem(&s_bar);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.b32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar) : "memory");
+    }
+#pragma unroll 1
+    for (int k = 0; k < CV_TP / 8; k++) {
+        const int x = x0 + warp * (CV_TP / 8) + k;
+        if (x >= W) break;
+        const int p = rowbase + x;
+        float* row = A.cost + (size_t)A.pixel_node[p] * Dp;
+        const uchar4 m4 = me4[p];
+        const uint32_t me = (uint32_t)m4.x | ((uint32_t)m4.y << 8) | ((uint32_t)m4.z << 16);
+        const float me_g = meg[p];
+        const bool has_next = x + 1 < W;
+        const float me_gn = has_next ? meg[p + 1] : 0.0f;
+        // labels with a defined cost: left volume 0 <= d <= x (and x+1 < W); right volume d <= W-2-x
+        const int dvalid = VIEW == 0 ? (has_next ? x + 1 : 0) : W - 1 - x;
+        for (int d0 = 0; d0 < Dp; d0 += 32) {  // warp-uniform trip count: the colour-term shuffle needs every lane
+            const int d = d0 + lane;
+            // left volume at (d, x): ref = right(x-d), match = left(x); right volume at (d, x): ref = right(x), match = left(x+d)
+            const bool valid = d < D && d < dvalid;
+            const int wi = valid ? (VIEW == 0 ? x - d : x + d) - xs : 0;
+            const uint32_t o = s_win4[wi];
+            const float og = s_wing[wi], ogn = s_wing[wi + 1];
+            const int l1 = (int)__dp4a(__vabsdiffu4(o, me), 0x00010101u, 0u);
+            const float ctv = __shfl_sync(0xffffffffu, ct_lane, min(l1, 21));
+            // g = (match_gray - ref_gray) + (ref_gray_next - match_gray_next)
+            const float g = VIEW == 0 ? S3_FADD(S3_FSUB(me_g, og), S3_FSUB(ogn, me_gn)) : S3_FADD(S3_FSUB(og, me_g), S3_FSUB(me_gn, ogn));
+            const float ag = fabsf(g);
+            const float gterm = ag < 2.0f ? ag : 2.0f;
+            float c = 3.0f;  // bad_cost, and the value of never-written left entries (Q19)
+            if (valid) c = S3_FADD(ctv, S3_FMUL(0.89f, gterm));
+            if (A.ingest) c = s3_ingest(c, A.cap, A.offset, A.scale);
+            if (d >= D) c = 0.0f;  // row padding
+            if (d < Dp)
+                row[d] = c;
+        }
     }
 }
 
@@ -143,8 +198,10 @@ int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest) {
         A.left4 = ctx->v[0].raw4; A.right4 = ctx->v[1].raw4; A.lgray = ctx->v[0].gray; A.rgray = ctx->v[1].gray;
         A.pixel_node = V.pixel_node; A.cost = V.cost;
         A.ingest = apply_ingest; A.cap = ctx->P.cost_cap; A.offset = ctx->P.cost_offset; A.scale = ctx->P.cost_scale;
-        const long long threads = (long long)ctx->N * 32;
-        k_cost_adgrad<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(A);
+        if (V.Dp + CV_TP + 8 > CV_MAXWIN) return s3_fail(ctx, S3DMST_E_ARG, "build_cost_volume: D up to %d", CV_MAXWIN - CV_TP - 8);
+        const int segs = (ctx->W + CV_TP - 1) / CV_TP;
+        if (view == 0) k_cost_adgrad<0><<<(unsigned)(segs * ctx->H), 256, 0, ctx->stream>>>(A);
+        else k_cost_adgrad<1><<<(unsigned)(segs * ctx->H), 256, 0, ctx->stream>>>(A);
         S3_LAUNCH_CHECK();
         V.cost_ready = true;
         V.agg_ready = false;

@@ -742,12 +742,10 @@ int s3_fh_launch(s3dmst_ctx* ctx, int mask) {
         if (mask & (1 << view)) fill_fh_args(ctx, ctx->v[view], AA.v[nv++]);
     if (!nv) return 0;
     if (nv == 1) AA.v[1] = AA.v[0];
-    static int ctas_per_sm = -1;
-    if (ctas_per_sm < 0) {
-        int n = 0;
-        S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fh_merge, 1024, 0));
-        ctas_per_sm = n;
-    }
+    int threads = ctx->P.fh_threads > 0 ? ctx->P.fh_threads : 1024;
+    threads = std::max(64, std::min(1024, threads / 32 * 32));
+    int ctas_per_sm = 0;
+    S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fh_merge, threads, 0));
     if (ctas_per_sm < 1) return s3_fail(ctx, S3DMST_E_CUDA, "k_fh_merge does not fit on an SM");
     const int want = ctx->P.fh_ctas > 0 ? ctx->P.fh_ctas : ctx->num_sms;
     const int grid = std::max(nv, std::min(std::min(want, ctx->num_sms * ctas_per_sm), S3_FH_MAX_CTAS));
@@ -759,7 +757,7 @@ int s3_fh_launch(s3dmst_ctx* ctx, int mask) {
     AA.bar = reinterpret_cast<unsigned*>(ctx->fh_sync);
     AA.gcnt = ctx->fh_sync + 64;
     void* args[] = {&AA};
-    S3_CUDA(cudaLaunchCooperativeKernel((const void*)k_fh_merge, dim3(grid), dim3(1024), args, 0, ctx->stream));
+    S3_CUDA(cudaLaunchCooperativeKernel((const void*)k_fh_merge, dim3(grid), dim3(threads), args, 0, ctx->stream));
     ctx->launches++;
     return 0;
 }
