@@ -444,3 +444,70 @@ def test_label_sharded_two_gpus_nccl(api, oracle):
                         "--master-port", "29533", os.path.join(root, "tools", "label_sharded.py"), "--check"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"check": true' in r.stdout
+
+
+def test_full_size_c3_pms_properties(api, oracle):
+    """BASELINE config C3 (1920x1080, 256 disparities, injected proposal sequence) at full size: size-independent
+    properties of the proposal path plus oracle checks restricted to whole trees (a tree's update touches only its own
+    pixels, so a handful of trees can be checked against the CPU in milliseconds)."""
+    import time
+    W, H, D = 1920, 1080, 256
+    N = W * H
+    L, R, _ = synth.make_pair(W, H, D, seed=synth.BASE_SEED + 1)
+    eng = api.Stereo3DMST(cost_scale=1 / 6.0)
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    eng.build_cost_volume(D, ingest=True)
+    F = oracle.forest(L)
+    G = eng.get_forest(0)
+    assert G["T"] == F.T and np.array_equal(G["node_pixel"], F.node_pixel) and np.array_equal(G["parent"], F.parent)
+    T = F.T
+    rng = np.random.default_rng(synth.BASE_SEED + 2)
+    K = 12                                   # labels per tree per iteration, 2 iterations
+    trees = np.tile(np.repeat(np.arange(T, dtype=np.int32), K), 2)
+    n = trees.size
+    labels = np.stack([rng.uniform(-0.02, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0, D - 1, n)], 1).astype(np.float32)
+    eng.init_labels(0, D)
+    abc0 = eng.get_labels(0).copy()
+    t0 = time.perf_counter()
+    eng.pms_apply(0, trees, labels)
+    eng.sync()
+    dt = time.perf_counter() - t0
+    visits = 2 * K * N
+    print(f"C3 pms_apply: {n} proposals, {visits / 1e6:.0f} M node-visits in {dt * 1e3:.1f} ms (incl. upload) = {visits / dt / 1e9:.2f} G node-visits/s; "
+          f"device {eng.stage_ms(api.T_PMS):.1f} ms")
+    m1 = eng.get_min_cost(0).copy(); l1 = eng.get_labels(0).copy()
+    assert np.all(m1 < np.finfo(np.float64).max)
+    # (1) idempotence: the same list again cannot improve anything (strict '<')
+    eng.pms_apply(0, trees, labels)
+    assert np.array_equal(bits(eng.get_min_cost(0)), bits(m1)) and np.array_equal(bits(eng.get_labels(0)), bits(l1))
+    # (2) trees are independent: any interleaving that keeps each tree's own order gives the same state
+    perm = np.argsort(rng.integers(0, 1 << 30, n), kind="stable")
+    perm = perm[np.argsort(trees[perm], kind="stable")]          # grouped by tree ...
+    key = rng.permutation(T)[trees[perm]]
+    perm = perm[np.argsort(key, kind="stable")]                  # ... trees in a random order, own order kept
+    own = np.concatenate([np.sort(perm[trees[perm] == t]) for t in range(0, T, max(1, T // 7))])
+    assert np.array_equal(own, np.concatenate([np.nonzero(trees == t)[0] for t in range(0, T, max(1, T // 7))]))
+    eng.set_labels(0, abc0); eng.reset_min_cost(0)
+    order = np.concatenate([np.nonzero(trees == t)[0] for t in rng.permutation(T)])
+    eng.pms_apply(0, trees[order], labels[order])
+    assert np.array_equal(bits(eng.get_min_cost(0)), bits(m1)) and np.array_equal(bits(eng.get_labels(0)), bits(l1))
+    # (3) oracle on whole trees: the 3 smallest and one mid-sized tree
+    vol = eng.get_cost_volume(0)
+    sizes = np.diff(np.asarray(F.tree_start))
+    pick = list(np.argsort(sizes)[:3]) + [int(np.argsort(sizes)[T // 2])]
+    mn_o = np.full(N, np.finfo(np.float64).max); abc_o = abc0.copy()
+    for t in pick:
+        sel = np.nonzero(trees == t)[0]
+        oracle.pms_apply(F, vol, D, trees[sel], labels[sel], mn_o, abc_o)
+    tid = np.asarray(F.tree_id)
+    pix = np.isin(tid, pick)
+    assert np.array_equal(bits(m1[pix]), bits(mn_o[pix])) and np.array_equal(bits(l1.reshape(N, 3)[pix]), bits(abc_o.reshape(N, 3)[pix]))
+    # (4) Q10: an exactly-integer in-range disparity costs 0 everywhere, so it wins every pixel with aggregated cost 0
+    zl = np.tile(np.array([[0.0, 0.0, 7.0]], np.float32), (T, 1))
+    eng.pms_apply(0, np.arange(T, dtype=np.int32), zl)
+    assert np.all(eng.get_min_cost(0) == 0.0)
+    assert np.array_equal(eng.get_labels(0).reshape(N, 3), np.tile(zl[:1], (N, 1)))
+    eng.label_to_disp(0)
+    assert np.all(eng.get_disparity(0) == 7.0)
+    eng.close()
