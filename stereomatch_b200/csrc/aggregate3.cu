@@ -449,6 +449,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     if (d0 & 3) return 1;  // 16-byte row alignment of the lane's label pairs
     const int nl = d1 - d0;
     static const int force_nh = getenv("S3_AGG_NH") ? atoi(getenv("S3_AGG_NH")) : 0;
+    // (A tree is walked by one CTA per label slice and its time is proportional to its NODE count, so narrower slices do
+    // not shorten the largest tree — measured on the FLIR pair: 17.4 -> 14.8 ms — they only add instructions.)
     const int NH = force_nh ? force_nh : (nl > 64 ? 2 : 1);
     const int SW = 64 * NH;
     const int n_slices = (nl + SW - 1) / SW;

@@ -727,8 +727,8 @@ static void fill_fh_args(s3dmst_ctx* ctx, View& V, FHArgs& A) {
     A.parent = V.uf_parent; A.size = V.uf_size; A.lastw = V.uf_lastw; A.resv = V.uf_resv;
     A.pick[0] = V.uf_pick[0]; A.pick[1] = V.uf_pick[1];
     A.ent[0] = reinterpret_cast<FHEntry*>(V.fh_ent[0]); A.ent[1] = reinterpret_cast<FHEntry*>(V.fh_ent[1]);
-    static const int band_low = getenv("S3_FH_LOW") ? atoi(getenv("S3_FH_LOW")) : 8192;
-    static const int band_high = getenv("S3_FH_HIGH") ? atoi(getenv("S3_FH_HIGH")) : 32768;
+    static const int band_low = getenv("S3_FH_LOW") ? atoi(getenv("S3_FH_LOW")) : 16384;
+    static const int band_high = getenv("S3_FH_HIGH") ? atoi(getenv("S3_FH_HIGH")) : 65536;
     A.band_low = band_low; A.band_high = band_high;
     A.mask = V.mask; A.e_ra = V.e_ra; A.e_rb = V.e_rb; A.e_flag = V.e_flag; A.counters = V.counters;
 }

@@ -511,3 +511,43 @@ def test_full_size_c3_pms_properties(api, oracle):
     eng.label_to_disp(0)
     assert np.all(eng.get_disparity(0) == 7.0)
     eng.close()
+
+
+def test_full_size_c1_flir_pair(api):
+    """BASELINE config C1: the bundled FLIR pair 000020 (rectified as src/stereo_Yin.cpp:135-147 does; fixture made by
+    tests/golden/make_flir_fixture.py), native 2048x1536, Dmax = 100 (stereo_Yin.cpp:207): forests, cost volumes,
+    aggregated WTA and the final disparity maps are bit-identical to the oracle.  A natural image at 3.1 MP: ~500
+    trees, the largest > 200 000 nodes and thousands of levels deep — the regime the kernels' far paths exist for."""
+    import cv2
+    import time
+    from oracle.pyoracle import Oracle
+    O = Oracle(fast=True)
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    L = cv2.imread(os.path.join(g, "flir_000020_left.jpg")); R = cv2.imread(os.path.join(g, "flir_000020_right.jpg"))
+    assert L is not None and L.shape == (1536, 2048, 3) and R.shape == L.shape
+    H, W, D = L.shape[0], L.shape[1], 100
+    eng = api.Stereo3DMST()
+    eng.set_images(L, R)
+    t0 = time.perf_counter()
+    dl, dr = eng.run_dense(D, fill=True)
+    t_gpu = time.perf_counter() - t0
+    FL, FR = O.forest(L), O.forest(R)
+    for view, F in ((0, FL), (1, FR)):
+        check_forest(F, eng.get_forest(view))
+    sizes = np.diff(np.asarray(FL.tree_start))
+    print(f"FLIR C1: T = {FL.T}/{FR.T} trees, largest {sizes.max()} nodes, depth {FL.max_depth}; GPU run_dense {t_gpu * 1e3:.1f} ms "
+          f"(stages {[round(eng.stage_ms(s), 2) for s in range(4)]})")
+    lv, rv = O.cost_adgrad(L, R, D)
+    assert np.array_equal(bits(eng.get_cost_volume(0)), bits(lv))
+    assert np.array_equal(bits(eng.get_cost_volume(1)), bits(rv))
+    dlo, blo, _ = O.aggregate_dense(FL, lv)
+    dro, bro, _ = O.aggregate_dense(FR, rv)
+    del lv, rv
+    want, _ = O.lr_check(dlo.astype(np.float32), dro.astype(np.float32), W, H, D, True)
+    assert np.array_equal(bits(dr), bits(dro.astype(np.float32)))
+    assert np.array_equal(bits(dl), bits(want))
+    # the aggregated minima themselves (dense results stay in the context after run_dense)
+    for view, (do, bo) in enumerate(((dlo, blo), (dro, bro))):
+        disp, best = eng.aggregate_dense(view, 0, D)
+        assert np.array_equal(disp, do) and np.array_equal(bits(best), bits(bo))
+    eng.close()
