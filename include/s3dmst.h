@@ -131,6 +131,12 @@ int s3dmst_get_disparity(s3dmst_ctx* ctx, int view, float* disp);
 /* a14 leftRightConsistencyCheck (:632-710): invalid left pixels -> 0; fill != 0 runs the scan-line fill. */
 int s3dmst_lr_check(s3dmst_ctx* ctx, int fill);
 
+/* The step after the path in its caller (src/stereo_Yin.cpp:218-243): left disparities below disp_floor are raised to it
+ * (in the context's left map), then cv::reprojectImageTo3D(disp, xyz, Q, handle_missing) with the 4x4 row-major Q of
+ * stereoRectify — bit-identical to OpenCV's CV_32F path — and the packed colour of the point cloud
+ * (r << 16 | g << 8 | b of the left image).  xyz float[H*W][3], rgb uint32[H*W]; either may be NULL. */
+int s3dmst_reproject_to_3d(s3dmst_ctx* ctx, const double* Q, float disp_floor, int handle_missing, float* xyz, uint32_t* rgb);
+
 /* Whole dense pipeline on the current images: forests, cost volume, aggregation + WTA for both views,
  * LR check (+fill).  Outputs float[H][W] (NULL = leave on device). */
 int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp);

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def load_library():
     L.s3dmst_get_disparity.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_lr_check.argtypes = [c_p, C.c_int]
     L.s3dmst_run_dense.argtypes = [c_p, C.c_int, C.c_int, c_p, c_p]
+    L.s3dmst_reproject_to_3d.argtypes = [c_p, c_p, C.c_float, C.c_int, c_p, c_p]
     L.s3dmst_run_dense_batch.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_stage_ms.argtypes = [c_p, C.c_int]
     L.s3dmst_stage_ms.restype = C.c_double
@@ -277,6 +278,14 @@ class Stereo3DMST:
 
     def lr_check(self, fill=False):
         self._ck(self.L.s3dmst_lr_check(self.h, int(fill)))
+
+    def reproject_to_3d(self, Q, disp_floor=10.0, handle_missing=True, want_rgb=True):
+        """stereo_Yin.cpp:218-243: floor the left disparity map, cv::reprojectImageTo3D with Q, point-cloud colours."""
+        Q = np.ascontiguousarray(Q, np.float64).reshape(16)
+        xyz = np.empty((self.N, 3), np.float32)
+        rgb = np.empty(self.N, np.uint32) if want_rgb else None
+        self._ck(self.L.s3dmst_reproject_to_3d(self.h, _ptr(Q), float(disp_floor), int(handle_missing), _ptr(xyz), _ptr(rgb)))
+        return xyz, rgb
 
     def run_dense(self, D, fill=False, fetch=True):
         dl = np.empty(self.N, np.float32) if fetch else None

@@ -554,6 +554,12 @@ int s3dmst_lr_check(s3dmst_ctx* ctx, int fill) {
     return s3_lr_check(ctx, fill);
 }
 
+int s3dmst_reproject_to_3d(s3dmst_ctx* ctx, const double* Q, float disp_floor, int handle_missing, float* xyz, uint32_t* rgb) {
+    if (!Q || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "reproject_to_3d: Q and images required");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_reproject(ctx, Q, disp_floor, handle_missing, xyz, rgb);
+}
+
 int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp) {
     S3_CUDA(cudaSetDevice(ctx->device));
     memset(ctx->ev_set, 0, sizeof ctx->ev_set);

@@ -174,4 +174,5 @@ int s3_label_to_disp(s3dmst_ctx* ctx, int view);                  // post.cu
 int s3_dense_to_disp(s3dmst_ctx* ctx, int view);
 int s3_lr_check(s3dmst_ctx* ctx, int fill);
 int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
+int s3_reproject(s3dmst_ctx* ctx, const double* Q16, float disp_floor, int handle_missing, float* h_xyz, uint32_t* h_rgb);
 int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D);

@@ -161,3 +161,77 @@ int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev) {
     S3_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- the step after the path in its only caller (src/stereo_Yin.cpp:218-243): left disparities
+// below a floor are raised to it, cv::reprojectImageTo3D(disp, xyz, Q, handleMissingValues = true), and the RGB point
+// cloud is assembled.  Arithmetic of OpenCV's reprojectImageTo3D for a CV_32F map (checked bit for bit against cv2 by
+// tests/test_gpu_parity.py): P = Q * (x, y, d, 1) accumulated left to right in double; each of P.x, P.y, P.z is first
+// rounded to float, then scaled by the double 1 / P.w and rounded to float again; where |d - min(d)| <= FLT_EPSILON
+// the depth is the "missing value" marker 10000.
+__global__ void k_floor_min(int N, float floor_v, float* __restrict__ disp, unsigned* __restrict__ min_bits) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    float d = 3.0e38f;
+    if (p < N) {
+        d = disp[p];
+        if (d < floor_v) disp[p] = d = floor_v;  // :218-222
+    }
+    // non-negative floats order like their bit patterns
+    unsigned b = __float_as_uint(d < 0.0f ? 0.0f : d);
+    b = __reduce_min_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0) atomicMin(min_bits, b);
+}
+struct QMat {
+    double q[16];
+};
+__global__ void k_reproject(int W, int N, QMat Q, int handle_missing, const float* __restrict__ disp, const unsigned* __restrict__ min_bits,
+                            const uint8_t* __restrict__ bgr, float* __restrict__ xyz, uint32_t* __restrict__ rgb) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const double x = (double)(p % W), y = (double)(p / W), d = (double)disp[p];
+    double P[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        P[i] = S3_DADD(S3_DADD(S3_DADD(S3_DMUL(Q.q[4 * i], x), S3_DMUL(Q.q[4 * i + 1], y)), S3_DMUL(Q.q[4 * i + 2], d)), Q.q[4 * i + 3]);
+    const double iw = __ddiv_rn(1.0, P[3]);
+    float o[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) o[i] = (float)S3_DMUL((double)(float)P[i], iw);
+    if (handle_missing && fabs(d - (double)__uint_as_float(*min_bits)) <= (double)FLT_EPSILON) o[2] = 10000.0f;
+    if (xyz) {
+        xyz[3 * (size_t)p] = o[0];
+        xyz[3 * (size_t)p + 1] = o[1];
+        xyz[3 * (size_t)p + 2] = o[2];
+    }
+    if (rgb) {
+        const uint8_t* c = bgr + 3 * (size_t)p;  // (b, g, r) as set_images stored them; pcl::PointXYZRGB packing of stereo_Yin.cpp:240-241
+        rgb[p] = (uint32_t)c[2] * 0x10000u + (uint32_t)c[1] * 0x100u + (uint32_t)c[0];
+    }
+}
+
+int s3_reproject(s3dmst_ctx* ctx, const double* Q16, float disp_floor, int handle_missing, float* h_xyz, uint32_t* h_rgb) {
+    View& L = ctx->v[0];
+    const int N = ctx->N;
+    const size_t need = 16 + (size_t)N * 16;
+    if (ctx->pms_scratch_cap < need) {
+        if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
+        ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
+        S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
+        ctx->pms_scratch_cap = need;
+    }
+    unsigned* min_bits = reinterpret_cast<unsigned*>(ctx->pms_scratch);
+    float* d_xyz = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->pms_scratch) + 16);
+    uint32_t* d_rgb = reinterpret_cast<uint32_t*>(d_xyz + 3 * (size_t)N);
+    S3_CUDA(cudaMemsetAsync(min_bits, 0xFF, sizeof(unsigned), ctx->stream));
+    S3_EV_BEGIN(S3DMST_T_POST, 1);
+    k_floor_min<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, disp_floor, L.disp_f, min_bits);
+    S3_LAUNCH_CHECK();
+    QMat Q;
+    for (int i = 0; i < 16; i++) Q.q[i] = Q16[i];
+    k_reproject<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->W, N, Q, handle_missing, L.disp_f, min_bits, L.bgr, h_xyz ? d_xyz : nullptr, h_rgb ? d_rgb : nullptr);
+    S3_LAUNCH_CHECK();
+    S3_EV_END(S3DMST_T_POST, 1);
+    if (h_xyz) S3_CUDA(cudaMemcpyAsync(h_xyz, d_xyz, sizeof(float) * 3 * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_rgb) S3_CUDA(cudaMemcpyAsync(h_rgb, d_rgb, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

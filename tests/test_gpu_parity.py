@@ -551,3 +551,29 @@ def test_full_size_c1_flir_pair(api):
         disp, best = eng.aggregate_dense(view, 0, D)
         assert np.array_equal(disp, do) and np.array_equal(bits(best), bits(bo))
     eng.close()
+
+
+def test_reproject_to_3d_matches_opencv(api):
+    """SURVEY §8f rank 3 (src/stereo_Yin.cpp:218-243): disparity floor, cv::reprojectImageTo3D(..., Q, true) and the
+    packed point-cloud colour — bit-identical to OpenCV (cv2 is the oracle for this row)."""
+    import cv2
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    Q = np.load(os.path.join(g, "flir_000020_Q.npy"))
+    W, H = 333, 207
+    L, R, _ = make(W, H, 16, 77, 1)
+    rng = np.random.default_rng(8)
+    disp = rng.uniform(0, 99, (H, W)).astype(np.float32)
+    disp[rng.random((H, W)) < 0.2] = 0.0                     # what the LR check leaves for invalid pixels
+    eng = api.Stereo3DMST()
+    eng.set_images(L, R)
+    for floor, missing in ((10.0, True), (0.0, True), (10.0, False)):
+        eng.set_disparity(0, disp)
+        xyz, rgb = eng.reproject_to_3d(Q, disp_floor=floor, handle_missing=missing)
+        d = disp.copy()
+        d[d < floor] = floor                                # stereo_Yin.cpp:218-222
+        want = cv2.reprojectImageTo3D(d, Q, handleMissingValues=missing)
+        assert np.array_equal(bits(xyz), bits(want.reshape(-1, 3))), (floor, missing)
+        assert np.array_equal(bits(eng.get_disparity(0)), bits(d.ravel()))
+        Li = L.reshape(-1, 3).astype(np.uint32)
+        assert np.array_equal(rgb, Li[:, 2] * 0x10000 + Li[:, 1] * 0x100 + Li[:, 0])
+    eng.close()
