@@ -594,15 +594,20 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     std::vector<double> t_forest(n, 0.0);
+    static const bool joint_fh = getenv("S3_FH_JOINT") && atoi(getenv("S3_FH_JOINT")) != 0;
     std::vector<int> rc(n, 0);
     auto front = [&](int c) {
         s3dmst_ctx* cx = ctxs[c];
         rc[c] = [&]() -> int {
             s3dmst_ctx* ctx = cx;  // the error macros report into this frame's context
             S3_CUDA(cudaSetDevice(ctx->device));
-            memset(ctx->ev_set, 0, sizeof ctx->ev_set);
-            S3_EV_BEGIN(S3DMST_T_FOREST, 0);
-            S3_TRY(s3_forest_stage_mask(ctx, 3));
+            if (joint_fh)
+                S3_TRY(s3_forest_post(ctx, 3));
+            else {
+                memset(ctx->ev_set, 0, sizeof ctx->ev_set);
+                S3_EV_BEGIN(S3DMST_T_FOREST, 0);
+                S3_TRY(s3_forest_stage_mask(ctx, 3));
+            }
             S3_EV_END(S3DMST_T_FOREST, 0);
             if (dbg) { cudaStreamSynchronize(ctx->stream); t_forest[c] = now(); }
             S3_TRY(s3_cost_adgrad(ctx, D, 0));
@@ -610,6 +615,23 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
             return 0;
         }();
     };
+    // Optional (S3_FH_JOINT=1): image stages on the frames' own streams, then ONE forest-kernel launch per
+    // S3_FH_MAX_VIEWS / 2 frames.  Measured at C2, 8 frames: the joint launch is bound by L2 sector throughput
+    // (22.5 ms until all forests are done) and loses to per-frame launches overlapping on the streams (18 ms).
+    for (int c = 0; joint_fh && c < n; c++) {
+        s3dmst_ctx* cx = ctxs[c];
+        memset(cx->ev_set, 0, sizeof cx->ev_set);
+        int r = [&]() -> int {
+            s3dmst_ctx* ctx = cx;
+            S3_EV_BEGIN(S3DMST_T_FOREST, 0);
+            return s3_forest_pre(ctx, 3);
+        }();
+        if (r) return c == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frame %d: %s", c, cx->err.c_str());
+    }
+    for (int c0 = 0; joint_fh && c0 < n; c0 += S3_FH_MAX_VIEWS / 2) {
+        const int r = s3_fh_launch_multi(ctxs + c0, std::min(S3_FH_MAX_VIEWS / 2, n - c0), 3);
+        if (r) return c0 == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frames %d..: %s", c0, ctxs[c0]->err.c_str());
+    }
     if (n == 1)
         front(0);
     else {

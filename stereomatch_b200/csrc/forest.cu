@@ -35,7 +35,7 @@
 #define CNT_ROUNDS (S3_MAX_ROUNDS - 3)
 #define CNT_FIRSTS (S3_MAX_ROUNDS - 4)
 #define CNT_ACT (S3_MAX_ROUNDS - 20)  // [2] live-list lengths of the FH rounds
-#define ROUND_CAP (S3_MAX_ROUNDS - 32)
+#define ROUND_CAP (S3_FH_ROUNDS - 32)
 
 struct __align__(16) FHEntry {
     unsigned long long key;  // (w << 32) | edge id; bit 63 = accepted last round (ra = the root that hooked), bit 62 = rejected
@@ -118,11 +118,11 @@ __device__ __forceinline__ int block_sum_to_counter(int v, int* counter) {
 }
 
 struct FHArgs2 {
-    FHArgs v[2];
+    FHArgs v[S3_FH_MAX_VIEWS];
     int nviews;
     int seg_cap;         // capacity of one CTA's segment of the live-edge lists (entries)
     unsigned* bar;       // grid barrier counter (zeroed by the host)
-    int* gcnt;           // [S3_MAX_ROUNDS][2] per-round, per-view live counts (zeroed by the host)
+    int* gcnt;           // [S3_FH_ROUNDS][S3_FH_MAX_VIEWS] per-round, per-view live counts (zeroed by the host)
 };
 
 // Grid-wide barrier for a co-resident grid (cooperative launch): one arrive per CTA, thread 0 spins on the counter.
@@ -183,20 +183,20 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
 
     // ------------------------------------------------------------------ FH
     {
-        int n_live[2] = {0, 0};    // live entries per view after the previous round (all CTAs)
-        int lev[2] = {0, 0};       // weight levels ingested so far
-        int band_pos[2] = {0, 0};  // == lvl_off[lev]
+        int n_live[S3_FH_MAX_VIEWS], lev[S3_FH_MAX_VIEWS], band_pos[S3_FH_MAX_VIEWS];  // per view: live entries after the previous round
+        for (int v = 0; v < S3_FH_MAX_VIEWS; v++) n_live[v] = lev[v] = band_pos[v] = 0;       // (all CTAs), weight levels ingested, == lvl_off[lev]
         int my_src = 0;            // entries in this CTA's source segment (live + flagged ones of the previous round)
         int par = 0;
         const size_t seg = (size_t)crank * AA.seg_cap;
         while (true) {
-            int band_lo[2], work = 0;
+            int band_lo_vi = 0, work = 0;
             for (int v = 0; v < nviews; v++) {  // uniform across the grid: every thread tracks both views
-                band_lo[v] = band_pos[v];
+                const int blo = band_pos[v];
+                if (v == vi) band_lo_vi = blo;
                 if (n_live[v] < AA.v[v].band_low)
-                    while (lev[v] < S3_NUM_W && n_live[v] + (band_pos[v] - band_lo[v]) < AA.v[v].band_high)
+                    while (lev[v] < S3_NUM_W && n_live[v] + (band_pos[v] - blo) < AA.v[v].band_high)
                         band_pos[v] = AA.v[v].lvl_off[++lev[v]];
-                work += n_live[v] + (band_pos[v] - band_lo[v]);
+                work += n_live[v] + (band_pos[v] - blo);
             }
             if (work == 0) break;  // nothing live and nothing left to ingest in either view
             if (++round >= ROUND_CAP) {
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             unsigned long long* pick = A.pick[par];
             unsigned long long* pick_prev = A.pick[par ^ 1];
             // ---- phase 1: settle last round's decisions, re-root the survivors, post keys, compact
-            const int n_new = band_pos[vi] - band_lo[vi];
+            const int n_new = band_pos[vi] - band_lo_vi;
             const int share = (n_new + nblk - 1) / nblk;
             const int new_lo = min(n_new, crank * share), new_hi = min(n_new, (crank + 1) * share);
             const int total = my_src + (new_hi - new_lo);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                         live = en.ra != en.rb;
                     }
                 } else if (pos < total) {
-                    const uint32_t e = A.elist[band_lo[vi] + new_lo + (pos - my_src)];
+                    const uint32_t e = A.elist[band_lo_vi + new_lo + (pos - my_src)];
                     en.key = ((unsigned long long)A.ew[e] << 32) | e;
                     en.ra = (int)(e >> 1);
                     en.rb = en.ra + ((e & 1u) ? A.W : 1);
@@ -255,11 +255,11 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             }
             __syncthreads();
             const int my_cnt = s_cnt;
-            if (threadIdx.x == 0 && my_cnt) atomicAdd(AA.gcnt + 2 * round + vi, my_cnt);
+            if (threadIdx.x == 0 && my_cnt) atomicAdd(AA.gcnt + S3_FH_MAX_VIEWS * round + vi, my_cnt);
             FH_T(tA);
             FH_BAR();
             FH_T(tS);
-            for (int v = 0; v < nviews; v++) n_live[v] = __ldcg(AA.gcnt + 2 * round + v);
+            for (int v = 0; v < nviews; v++) n_live[v] = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round + v);
             // ---- phase 2: decide every edge that is the minimum of one of its components
             for (int pos = threadIdx.x; pos < my_cnt; pos += blockDim.x) {
                 FHEntry en = dst[pos];
@@ -351,9 +351,9 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             live++;
         }
         round++;
-        block_sum_to_counter(live, AA.gcnt + 2 * round);  // both views add into one counter: the loop ends for both together
+        block_sum_to_counter(live, AA.gcnt + S3_FH_MAX_VIEWS * round);  // every view adds into one counter: the loop ends for all together
         FH_BAR();
-        const int nlive = __ldcg(AA.gcnt + 2 * round);
+        const int nlive = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round);
         if (nlive == 0) break;
         for (int pos = gtid; pos < nlist; pos += gstride) {
             const uint32_t e = A.elist[pos];
@@ -733,34 +733,51 @@ static void fill_fh_args(s3dmst_ctx* ctx, View& V, FHArgs& A) {
     A.mask = V.mask; A.e_ra = V.e_ra; A.e_rb = V.e_rb; A.e_flag = V.e_flag; A.counters = V.counters;
 }
 
-// FH + min-size merge for the views in `mask`: one cooperative launch, one CTA per SM, the grid split between the views
-int s3_fh_launch(s3dmst_ctx* ctx, int mask) {
+// FH + min-size merge for the views in `mask` of every context in `ctxs` (one device): ONE cooperative launch on
+// ctxs[0]'s stream, the grid split evenly between the views.  A batch of frames shares the ~150 barrier rounds.
+int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask) {
+    s3dmst_ctx* ctx = ctxs[0];
     FHArgs2 AA;
     memset(&AA, 0, sizeof AA);
     int nv = 0;
-    for (int view = 0; view < 2; view++)
-        if (mask & (1 << view)) fill_fh_args(ctx, ctx->v[view], AA.v[nv++]);
+    for (int c = 0; c < nctx; c++)
+        for (int view = 0; view < 2; view++)
+            if (mask & (1 << view)) {
+                if (nv >= S3_FH_MAX_VIEWS) return s3_fail(ctx, S3DMST_E_ARG, "forest kernel: at most %d views per launch", S3_FH_MAX_VIEWS);
+                fill_fh_args(ctxs[c], ctxs[c]->v[view], AA.v[nv++]);
+            }
     if (!nv) return 0;
-    if (nv == 1) AA.v[1] = AA.v[0];
     int threads = ctx->P.fh_threads > 0 ? ctx->P.fh_threads : 1024;
     threads = std::max(64, std::min(1024, threads / 32 * 32));
     int ctas_per_sm = 0;
     S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fh_merge, threads, 0));
     if (ctas_per_sm < 1) return s3_fail(ctx, S3DMST_E_CUDA, "k_fh_merge does not fit on an SM");
-    const int want = ctx->P.fh_ctas > 0 ? ctx->P.fh_ctas : ctx->num_sms;
-    const int grid = std::max(nv, std::min(std::min(want, ctx->num_sms * ctas_per_sm), S3_FH_MAX_CTAS));
-    const int per_view = grid / nv;
+    const int want = (nctx > 1 || ctx->P.fh_ctas <= 0) ? ctx->num_sms : ctx->P.fh_ctas;  // a joint launch takes every SM
+    const int per_view = std::max(1, std::min(std::min(want, ctx->num_sms * ctas_per_sm), S3_FH_MAX_CTAS) / nv);
+    const int grid = per_view * nv;  // every view gets the same number of CTAs (and list segments of one size)
+    if (grid > ctx->num_sms * ctas_per_sm) return s3_fail(ctx, S3DMST_E_ARG, "forest kernel: %d views do not fit the GPU in one cooperative launch", nv);
     AA.nviews = nv;
     AA.seg_cap = (2 * ctx->N + per_view - 1) / per_view + S3_FH_SEG_SLACK;
-    if (!ctx->fh_sync) S3_CUDA(cudaMalloc(&ctx->fh_sync, sizeof(int) * (2 * S3_MAX_ROUNDS + 64)));
-    S3_CUDA(cudaMemsetAsync(ctx->fh_sync, 0, sizeof(int) * (2 * S3_MAX_ROUNDS + 64), ctx->stream));
+    const size_t sync_ints = 64 + (size_t)S3_FH_ROUNDS * S3_FH_MAX_VIEWS;
+    if (!ctx->fh_sync) S3_CUDA(cudaMalloc(&ctx->fh_sync, sizeof(int) * sync_ints));
+    S3_CUDA(cudaMemsetAsync(ctx->fh_sync, 0, sizeof(int) * sync_ints, ctx->stream));
     AA.bar = reinterpret_cast<unsigned*>(ctx->fh_sync);
     AA.gcnt = ctx->fh_sync + 64;
+    for (int c = 1; c < nctx; c++) {  // the other frames' image stages come first
+        S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
+        S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[c]->ev_xctx, 0));
+    }
     void* args[] = {&AA};
     S3_CUDA(cudaLaunchCooperativeKernel((const void*)k_fh_merge, dim3(grid), dim3(threads), args, 0, ctx->stream));
     ctx->launches++;
+    if (nctx > 1) {
+        S3_CUDA(cudaEventRecord(ctx->ev_xctx, ctx->stream));
+        for (int c = 1; c < nctx; c++) S3_CUDA(cudaStreamWaitEvent(ctxs[c]->stream, ctx->ev_xctx, 0));
+    }
     return 0;
 }
+
+int s3_fh_launch(s3dmst_ctx* ctx, int mask) { return s3_fh_launch_multi(&ctx, 1, mask); }
 
 // tree sizes straight from the union-find (exact: every union added the hooked size)
 __global__ void k_label_sizes(int T, const int* __restrict__ rootpix, const int* __restrict__ root_of,
@@ -779,8 +796,9 @@ __global__ void k_label_ids2(int N, const int* __restrict__ root_of, const int* 
 // Forest construction for the views in `mask` (bit 0 left, bit 1 right).  The views are independent, so each
 // device stage is ONE launch covering both (FH+merge: one cluster per view; BFS: one CTA per tree of either
 // view) and the two host round trips (tree count, tree sizes -> offsets and work order) are shared.
-int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
-    const int N = ctx->N, W = ctx->W, H = ctx->H;
+// image stage + union-find initialisation of the views in `mask` (asynchronous on the context's stream)
+int s3_forest_pre(s3dmst_ctx* ctx, int mask) {
+    const int N = ctx->N;
     const int TB = 256;
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
@@ -792,7 +810,13 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
         S3_CUDA(cudaMemsetAsync(V.counters, 0, sizeof(int) * S3_MAX_ROUNDS, ctx->stream));
         S3_CUDA(cudaMemsetAsync(V.mask, 0, 2 * (size_t)N, ctx->stream));
     }
-    S3_TRY(s3_fh_launch(ctx, mask));
+    return 0;
+}
+
+// everything after the forest kernel: tree ids, sizes, BFS re-indexing (reads tree counts back: host-synchronous)
+int s3_forest_post(s3dmst_ctx* ctx, int mask) {
+    const int N = ctx->N, W = ctx->W, H = ctx->H;
+    const int TB = 256;
     int hc[2][16];
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
@@ -900,6 +924,12 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
             V.agg_ready = false;
         }
     return 0;
+}
+
+int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
+    S3_TRY(s3_forest_pre(ctx, mask));
+    S3_TRY(s3_fh_launch(ctx, mask));
+    return s3_forest_post(ctx, mask);
 }
 
 int s3_forest_stage(s3dmst_ctx* ctx, int view) { return s3_forest_stage_mask(ctx, 1 << view); }

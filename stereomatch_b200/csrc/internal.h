@@ -124,6 +124,8 @@ struct s3dmst_ctx {
 };
 
 #define S3_MAX_ROUNDS 65536
+#define S3_FH_MAX_VIEWS 16        // views (2 per frame) one forest-kernel launch serves
+#define S3_FH_ROUNDS 8192         // round cap of the forest kernel (per-round counters)
 #define S3_FH_MAX_CTAS 256        // upper bound on the cooperative grid of the forest kernel
 #define S3_FH_SEG_SLACK 1024      // per-CTA slack of the live-edge list segments (one ingest event adds < 1 entry per CTA beyond its share)
 
@@ -159,6 +161,9 @@ int s3_image_stage(s3dmst_ctx* ctx, int view);                    // image.cu: m
 int s3_forest_stage(s3dmst_ctx* ctx, int view);                   // forest.cu: FH + merge + labels + BFS
 int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask);              // both views in shared launches
 int s3_fh_launch(s3dmst_ctx* ctx, int mask);
+int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask);   // one launch over several frames
+int s3_forest_pre(s3dmst_ctx* ctx, int mask);                     // image stage + union-find init (async)
+int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (host-synchronous)
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);           // forest.cu: unit order, depths
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
