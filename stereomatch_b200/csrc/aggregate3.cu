@@ -65,8 +65,8 @@ struct Agg3Args {
     const int4* units;  // {view, tree, first label, slice index}, longest tree first
     int Dp, d1, N, n_slices;
     int unit0;          // first unit of this launch
-    const double* lut_w;
-    const double* lut_w2;
+    const void* lut_w;   // exp(-w*gamma) and 1 - w*w tables in the state type
+    const void* lut_w2;
     int keep;
     int sleep_ns;       // back-off of a waiting warp between two polls
 };
@@ -116,14 +116,75 @@ __device__ __forceinline__ double a3_dkey_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
+// ---- the two state types: double (exact: the reference's arithmetic, bit for bit) and float (fast: 12 instead of 20
+// bytes of HBM traffic per pixel-label; results within rounding of the exact ones, no bit-exactness promise)
+template <typename T> struct A3T;
+template <> struct A3T<double> {
+    typedef double2 T2;
+    static __device__ __forceinline__ T2 zero2() { return make_double2(0.0, 0.0); }
+    static __device__ __forceinline__ double maxv() { return DBL_MAX; }
+    static __device__ __forceinline__ double add(double a, double b) { return S3_DADD(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return S3_DMUL(a, b); }
+    static __device__ __forceinline__ double ldsw(uint32_t a) { return a3_lds_d(a); }
+    static __device__ __forceinline__ T2 lds2(uint32_t a) { return a3_lds_d2(a); }
+    static __device__ __forceinline__ void sts2(uint32_t a, T2 v) { a3_sts_d2(a, v); }
+    static __device__ __forceinline__ T2 ldcg2(const char* p) { return a3_ldcg_d2(reinterpret_cast<const double*>(p)); }
+    // warp arg-min with three 32-bit REDUX steps: (cost hi, cost lo, label); ties -> lowest label
+    static __device__ __forceinline__ unsigned warp_argmin(double bc, int bd, double& mc) {
+        const unsigned long long key = a3_dkey(bc);
+        const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
+        const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
+        mc = a3_dkey_inv(((unsigned long long)mhi << 32) | mlo);
+        return md;
+    }
+};
+template <> struct A3T<float> {
+    typedef float2 T2;
+    static __device__ __forceinline__ T2 zero2() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float maxv() { return FLT_MAX; }
+    static __device__ __forceinline__ float add(float a, float b) { return S3_FADD(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return S3_FMUL(a, b); }
+    static __device__ __forceinline__ float ldsw(uint32_t a) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ T2 lds2(uint32_t a) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+        return v;
+    }
+    static __device__ __forceinline__ void sts2(uint32_t a, T2 v) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+    }
+    static __device__ __forceinline__ T2 ldcg2(const char* p) {
+        float2 v;
+        asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+        return v;
+    }
+    static __device__ __forceinline__ unsigned warp_argmin(float bc, int bd, double& mc) {
+        const unsigned b = __float_as_uint(bc);
+        const unsigned key = (b >> 31) ? ~b : (b | 0x80000000u);
+        const unsigned mk = __reduce_min_sync(0xffffffffu, key);
+        const unsigned md = __reduce_min_sync(0xffffffffu, key == mk ? (unsigned)bd : 0x7fffffffu);
+        mc = (double)__uint_as_float((mk >> 31) ? (mk & 0x7fffffffu) : ~mk);
+        return md;
+    }
+};
+
 // FULL: every lane's label pairs are real labels in every half (no per-lane predication in the loops)
 // BIG: 32 warps per tree, one CTA per SM (the biggest trees: enough warps that a level's nodes do not need every warp)
-template <int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR>
+template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR>
 __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3Args A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    double* s_w = reinterpret_cast<double*>(s_raw);                 // [S3_NUM_W] exp(-w*gamma)
-    double* s_w2 = s_w + S3_NUM_W;                                  // [S3_NUM_W] 1 - w*w
-    double2* s_ring = reinterpret_cast<double2*>(s_w2 + S3_NUM_W);  // [A3_R][NH][32]
+    using TT = A3T<T>;
+    using T2 = typename TT::T2;
+    constexpr uint32_t HB = 64 * sizeof(T);                         // bytes of 64 labels (one half) of a running-sum row
+    T* s_w = reinterpret_cast<T*>(s_raw);                           // [S3_NUM_W] exp(-w*gamma)
+    T* s_w2 = s_w + S3_NUM_W;                                       // [S3_NUM_W] 1 - w*w
+    T2* s_ring = reinterpret_cast<T2*>(s_raw + ((2 * S3_NUM_W * sizeof(T) + 15) / 16) * 16);  // [A3_R][NH][32]
     int* s_prog = reinterpret_cast<int*>(s_ring + A3_R * NH * 32);  // [32] progress words
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, WM = W - 1;
 
@@ -137,25 +198,26 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;  // the lane's pair holds at least one real label
 
     for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
-        s_w[i] = A.lut_w[i];
-        s_w2[i] = A.lut_w2[i];
+        s_w[i] = reinterpret_cast<const T*>(A.lut_w)[i];
+        s_w2[i] = reinterpret_cast<const T*>(A.lut_w2)[i];
     }
     if (tid < 32) s_prog[tid] = end;  // up pass: node c is done iff its owner's word is <= c
     __syncthreads();
     const uint32_t prog_a = a3_smem(s_prog);
     const unsigned sleep_ns = (unsigned)A.sleep_ns;
-    const uint32_t ring_a = a3_smem(s_ring) + 16u * lane;  // this lane's column of the ring
+    const uint32_t ring_a = a3_smem(s_ring) + (uint32_t)sizeof(T2) * lane;  // this lane's column of the ring
     const uint32_t w_a = a3_smem(s_w);
-    constexpr uint32_t ROWB = NH * 512;                     // bytes of one ring row
-    const long long strideC = (long long)W * (long long)Dp * 4, strideA = 2 * strideC;  // bytes between a warp's consecutive rows
+    constexpr uint32_t ROWB = NH * HB;                      // bytes of one ring row
+    const long long strideC = (long long)W * (long long)Dp * 4, strideA = (long long)W * (long long)Dp * (long long)sizeof(T);  // bytes between a warp's consecutive rows
+    T* const aupT = reinterpret_cast<T*>(V.aup);  // running sums in the state type (the buffer is sized for doubles)
 
     // ================================================================== leaf -> root
     {
         int v = top - w;
         const char* nup_p = reinterpret_cast<const char*>(V.node_up + v);
         const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + l0 + 2 * lane);
-        char* aup_p = reinterpret_cast<char*>(V.aup + (size_t)v * Dp + l0 + 2 * lane);
-        const char* aup_lane0 = reinterpret_cast<const char*>(V.aup + l0 + 2 * lane);  // + c * Dp * 8 for a far child
+        char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * Dp + l0 + 2 * lane);
+        const char* aup_lane0 = reinterpret_cast<const char*>(aupT + l0 + 2 * lane);  // + c * Dp * 8 for a far child
         int4 nu_n = make_int4(0, 0, 0, 0);
         float2 cf_n[NH];
 #pragma unroll
@@ -181,30 +243,30 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             for (int h = 0; h < NH; h++) cf[h] = cf_n[h];
             const int vn = v - W;
             const int cc = nu.y & 7, cb = nu.x;
-            double2 acc[NH];
+            T2 acc[NH];
 #pragma unroll
-            for (int h = 0; h < NH; h++) acc[h] = make_double2(0.0, 0.0);
+            for (int h = 0; h < NH; h++) acc[h] = TT::zero2();
             // (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost — children in reverse BFS order (Stereo3DMST.cpp:125-137)
 #define A3_CHILD(K, IW)                                                                                              \
     if (cc > K) {                                                                                                    \
         const int c = cb + K;                                                                                        \
-        const double wk = a3_lds_d(w_a + 8u * (IW));                                                                 \
+        const T wk = TT::ldsw(w_a + (uint32_t)sizeof(T) * (IW));                                                                 \
         const uint32_t pa = prog_a + 4u * (uint32_t)((top - c) & WM);                                                \
         A3_CLK(q_pre);                                                                                               \
         while (a3_ld_acquire(pa) > c) __nanosleep(sleep_ns);                                                         \
         A3_CLK(q_poll);                                                                                              \
-        double2 cv[NH];                                                                                              \
+        T2 cv[NH];                                                                                              \
         if (c - v < A3_NEAR) {                                                                                       \
             const uint32_t ra = ring_a + (uint32_t)(c & (A3_R - 1)) * ROWB;                                          \
-            _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = a3_lds_d2(ra + h * 512);                          \
+            _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = TT::lds2(ra + h * HB);                          \
         } else {                                                                                                     \
-            const char* gp = aup_lane0 + (size_t)c * Dp * 8;                                                         \
+            const char* gp = aup_lane0 + (size_t)c * Dp * sizeof(T);                                                         \
             _Pragma("unroll") for (int h = 0; h < NH; h++)                                                           \
-                cv[h] = act[h] ? a3_ldcg_d2(reinterpret_cast<const double*>(gp + h * 512)) : make_double2(0.0, 0.0); \
+                cv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2(); \
         }                                                                                                            \
         _Pragma("unroll") for (int h = 0; h < NH; h++) {                                                             \
-            acc[h].x = S3_DADD(acc[h].x, S3_DMUL(wk, cv[h].x));                                                      \
-            acc[h].y = S3_DADD(acc[h].y, S3_DMUL(wk, cv[h].y));                                                      \
+            acc[h].x = TT::add(acc[h].x, TT::mul(wk, cv[h].x));                                                      \
+            acc[h].y = TT::add(acc[h].y, TT::mul(wk, cv[h].y));                                                      \
         }                                                                                                            \
     }
             A3_CHILD(3, (uint32_t)nu.w >> 16)
@@ -214,14 +276,14 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #undef A3_CHILD
 #pragma unroll
             for (int h = 0; h < NH; h++) {
-                acc[h].x = S3_DADD(acc[h].x, (double)cf[h].x);
-                acc[h].y = S3_DADD(acc[h].y, (double)cf[h].y);
+                acc[h].x = TT::add(acc[h].x, (T)cf[h].x);
+                acc[h].y = TT::add(acc[h].y, (T)cf[h].y);
             }
             const bool far_parent = nu.y & S3_NU_FARPARENT;
             if (far_parent) {  // a parent beyond the ring reads this row from L2: it has to be out before the publish
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = acc[h];
+                    if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = acc[h];
             }
             A3_CLK(q_dep);
             // ring row v last held node v + R, which only nodes > v + R - NEAR may still read
@@ -241,7 +303,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             {
                 const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
 #pragma unroll
-                for (int h = 0; h < NH; h++) a3_sts_d2(ra + h * 512, acc[h]);
+                for (int h = 0; h < NH; h++) TT::sts2(ra + h * HB, acc[h]);
             }
             __syncwarp();
             if (lane == 0) a3_st_release(prog_a + 4u * w, v);
@@ -260,7 +322,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             if (!far_parent) {  // read back on the way down
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = acc[h];
+                    if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = acc[h];
             }
             nup_p -= (long long)W * 16;
             cost_p -= strideC;
@@ -280,23 +342,23 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     {
         int v = base + w;
         const char* ndn_p = reinterpret_cast<const char*>(V.node_dn + v);
-        char* aup_p = reinterpret_cast<char*>(V.aup + (size_t)v * Dp + l0 + 2 * lane);
-        const char* aup_lane0 = reinterpret_cast<const char*>(V.aup + l0 + 2 * lane);
+        char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * Dp + l0 + 2 * lane);
+        const char* aup_lane0 = reinterpret_cast<const char*>(aupT + l0 + 2 * lane);
         int4 nd_n = make_int4(0, 0, 0, 0);
-        double2 au_n[NH];
+        T2 au_n[NH];
 #pragma unroll
-        for (int h = 0; h < NH; h++) au_n[h] = make_double2(0.0, 0.0);
+        for (int h = 0; h < NH; h++) au_n[h] = TT::zero2();
         if (v < end) {
             nd_n = *reinterpret_cast<const int4*>(ndn_p);
 #pragma unroll
             for (int h = 0; h < NH; h++)
-                if (act[h]) au_n[h] = *reinterpret_cast<const double2*>(aup_p + h * 512);
+                if (act[h]) au_n[h] = *reinterpret_cast<const T2*>(aup_p + h * HB);
         } else if (lane == 0)
             a3_st_release(prog_a + 4u * w, end);
         int guard_ok = base - 1;  // writing ring row v is known to be safe for every v <= guard_ok
         // WTA over a node's labels held by this warp: strict '<', lowest label wins ties
-        auto wta = [&](const double2* f, int vv, int pix) {
-            double bc = DBL_MAX;  // the oracle's initial best (cost < DBL_MAX is required to win)
+        auto wta = [&](const T2* f, int vv, int pix) {
+            T bc = TT::maxv();  // the oracle's initial best is DBL_MAX (a cost below it is required to win)
             int bd = 0x7fffffff;
 #pragma unroll
             for (int h = 0; h < NH; h++) {
@@ -304,13 +366,9 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 if ((FULL || lab < A.d1) && f[h].x < bc) { bc = f[h].x; bd = lab; }
                 if ((FULL || lab + 1 < A.d1) && f[h].y < bc) { bc = f[h].y; bd = lab + 1; }
             }
-            const unsigned long long key = a3_dkey(bc);
-            const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
-            const unsigned mhi = __reduce_min_sync(0xffffffffu, khi);
-            const unsigned mlo = __reduce_min_sync(0xffffffffu, khi == mhi ? klo : 0xffffffffu);
-            const unsigned md = __reduce_min_sync(0xffffffffu, (khi == mhi && klo == mlo) ? (unsigned)bd : 0x7fffffffu);
+            double mc;
+            const unsigned md = TT::warp_argmin(bc, bd, mc);
             if (lane == 0) {
-                const double mc = a3_dkey_inv(((unsigned long long)mhi << 32) | mlo);
                 if (A.n_slices == 1) {
                     V.disp[pix] = (int)md;
                     V.best[pix] = mc;
@@ -320,43 +378,43 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 }
             }
         };
-        double2 fin_prev[NH];
+        T2 fin_prev[NH];
 #pragma unroll
-        for (int h = 0; h < NH; h++) fin_prev[h] = make_double2(0.0, 0.0);
+        for (int h = 0; h < NH; h++) fin_prev[h] = TT::zero2();
         int v_prev = -1, pix_prev = 0;
         while (v < end) {
             const int4 nd = nd_n;  // {parent, parent weight, level | far-child flag, pixel}
-            double2 au[NH];
+            T2 au[NH];
 #pragma unroll
             for (int h = 0; h < NH; h++) au[h] = au_n[h];
             const int vn = v + W;
             if (v_prev >= 0) wta(fin_prev, v_prev, pix_prev);
             const int p = nd.x;
-            double2 fin[NH];
+            T2 fin[NH];
             if (p != v) {
                 // A[c] = w * A[parent] + (1 - w*w) * A_up[c]   (Stereo3DMST.cpp:155)
-                const double wp = a3_lds_d(w_a + 8u * (uint32_t)nd.y), wq = a3_lds_d(w_a + 8u * (uint32_t)(S3_NUM_W + nd.y));
+                const T wp = TT::ldsw(w_a + (uint32_t)sizeof(T) * (uint32_t)nd.y), wq = TT::ldsw(w_a + (uint32_t)sizeof(T) * (uint32_t)(S3_NUM_W + nd.y));
 #pragma unroll
                 for (int h = 0; h < NH; h++) {  // the half that does not depend on the parent, before the wait
-                    au[h].x = S3_DMUL(wq, au[h].x);
-                    au[h].y = S3_DMUL(wq, au[h].y);
+                    au[h].x = TT::mul(wq, au[h].x);
+                    au[h].y = TT::mul(wq, au[h].y);
                 }
                 const uint32_t pa = prog_a + 4u * (uint32_t)((p - base) & WM);
                 while (a3_ld_acquire(pa) < p) __nanosleep(sleep_ns);
-                double2 pv[NH];
+                T2 pv[NH];
                 if (v - p < A3_NEAR) {
                     const uint32_t ra = ring_a + (uint32_t)(p & (A3_R - 1)) * ROWB;
 #pragma unroll
-                    for (int h = 0; h < NH; h++) pv[h] = a3_lds_d2(ra + h * 512);
+                    for (int h = 0; h < NH; h++) pv[h] = TT::lds2(ra + h * HB);
                 } else {
-                    const char* gp = aup_lane0 + (size_t)p * Dp * 8;
+                    const char* gp = aup_lane0 + (size_t)p * Dp * sizeof(T);
 #pragma unroll
-                    for (int h = 0; h < NH; h++) pv[h] = act[h] ? a3_ldcg_d2(reinterpret_cast<const double*>(gp + h * 512)) : make_double2(0.0, 0.0);
+                    for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2();
                 }
 #pragma unroll
                 for (int h = 0; h < NH; h++) {
-                    fin[h].x = S3_DADD(S3_DMUL(wp, pv[h].x), au[h].x);
-                    fin[h].y = S3_DADD(S3_DMUL(wp, pv[h].y), au[h].y);
+                    fin[h].x = TT::add(TT::mul(wp, pv[h].x), au[h].x);
+                    fin[h].y = TT::add(TT::mul(wp, pv[h].y), au[h].y);
                 }
             } else {
 #pragma unroll
@@ -365,7 +423,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             if ((nd.z & S3_ND_FAR) || A.keep) {  // children further than NEAR read the final value from L2
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) *reinterpret_cast<double2*>(aup_p + h * 512) = fin[h];
+                    if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = fin[h];
             }
             if (v > guard_ok && v - A3_R >= base) {
                 int m;
@@ -379,7 +437,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             {
                 const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
 #pragma unroll
-                for (int h = 0; h < NH; h++) a3_sts_d2(ra + h * 512, fin[h]);
+                for (int h = 0; h < NH; h++) TT::sts2(ra + h * HB, fin[h]);
             }
             __syncwarp();
             if (lane == 0) a3_st_release(prog_a + 4u * w, v);
@@ -388,10 +446,10 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 nd_n = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) au_n[h] = *reinterpret_cast<const double2*>(aup_p + strideA + h * 512);
+                    if (act[h]) au_n[h] = *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
             }
-            if (lane < NH * 4 && v + A3_PF * W < end)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * 8 + A3_PF * strideA + lane * 128));
+            if (lane < NH * (int)sizeof(T) / 2 && v + A3_PF * W < end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * (int)sizeof(T) + A3_PF * strideA + lane * 128));
             // the WTA of this node is done at the top of the next iteration, in the shadow of the next wait
 #pragma unroll
             for (int h = 0; h < NH; h++) fin_prev[h] = fin[h];
@@ -405,7 +463,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     }
 }
 
-static size_t agg3_smem_bytes(int NH, int R) { return 2 * S3_NUM_W * sizeof(double) + (size_t)R * NH * 32 * sizeof(double2) + 32 * sizeof(int); }
+static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
 
 __global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node_dn, const int32_t* __restrict__ pdisp,
                               const double* __restrict__ pbest, int32_t* __restrict__ disp, double* __restrict__ best) {
@@ -519,7 +577,9 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.views = reinterpret_cast<const Agg3View*>(ubase);
     A.units = reinterpret_cast<const int4*>(ubase + tbytes);
     A.Dp = Dp; A.d1 = d1; A.N = ctx->N; A.n_slices = n_slices;
-    A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
+    const bool exact = ctx->P.exact != 0;
+    A.lut_w = exact ? (const void*)ctx->lut_w : (const void*)ctx->lut_wf;
+    A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env ? sleep_env : 20;
@@ -531,12 +591,17 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     const int n_small = (int)u.size() - n_big;
     const bool full = nl % SW == 0;  // every slice covers SW real labels
     S3_EV_BEGIN(S3DMST_T_AGG, first);
+#define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                           \
+    do {                                                                                                                       \
+        const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(T_));                                                              \
+        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_><<<GRID_, THREADS_, smem, ctx->stream>>>(A);                                \
+        S3_LAUNCH_CHECK();                                                                                                     \
+    } while (0)
 #define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                                 \
     do {                                                                                                                       \
-        const size_t smem = agg3_smem_bytes(NH_, R_);                                                                          \
-        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<NH_, FULL_, BIG_, R_, NEAR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_agg_flow<NH_, FULL_, BIG_, R_, NEAR_><<<GRID_, THREADS_, smem, ctx->stream>>>(A);                                    \
-        S3_LAUNCH_CHECK();                                                                                                     \
+        if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_);                                          \
+        else A3_LAUNCH_T(float, NH_, FULL_, BIG_, (R_) * 2, NEAR_, GRID_, THREADS_);                                           \
     } while (0)
     // ring geometry: rows R and hand-over distance NEAR (>= S3_AGG_NEAR, the distance the forest stage flags nodes by).
     // A warp may not run more than (R - NEAR) / W rounds ahead of the slowest one, so R - NEAR >= ~2 W.
@@ -558,6 +623,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     }
 #undef A3_DISPATCH
 #undef A3_LAUNCH
+#undef A3_LAUNCH_T
     if (n_slices > 1) {
         for (int c = 0; c < nctx; c++)
             for (int view = 0; view < 2; view++) {

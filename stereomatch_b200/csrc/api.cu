@@ -457,11 +457,13 @@ int s3dmst_get_aggregated(s3dmst_ctx* ctx, int view, double* agg) {
     const size_t N = ctx->N;
     std::vector<double> h(N * V.Dp);
     std::vector<int> np(N);
-    S3_CUDA(cudaMemcpyAsync(h.data(), V.aup, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const bool f32 = !ctx->P.exact && ctx->P.agg_kernel == 0;  // the fast mode keeps its running sums in fp32
+    S3_CUDA(cudaMemcpyAsync(h.data(), V.aup, h.size() * (f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDeviceToHost, ctx->stream));
     S3_CUDA(cudaMemcpyAsync(np.data(), V.node_pixel, N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    const float* hf = reinterpret_cast<const float*>(h.data());
     for (size_t v = 0; v < N; v++)
-        for (int d = 0; d < V.D; d++) agg[(size_t)d * N + np[v]] = h[v * V.Dp + d];
+        for (int d = 0; d < V.D; d++) agg[(size_t)d * N + np[v]] = f32 ? (double)hf[v * V.Dp + d] : h[v * V.Dp + d];
     return 0;
 }
 

@@ -577,3 +577,31 @@ def test_reproject_to_3d_matches_opencv(api):
         Li = L.reshape(-1, 3).astype(np.uint32)
         assert np.array_equal(rgb, Li[:, 2] * 0x10000 + Li[:, 1] * 0x100 + Li[:, 0])
     eng.close()
+
+
+def test_fast_mode_fp32_state_within_tolerance(api, oracle):
+    """params.exact = 0: the dense aggregation keeps fp32 running sums (12 instead of 20 bytes of HBM traffic per
+    pixel-label).  North-star tolerance for aggregated float costs: 1e-4 relative (stated here); the disparity must
+    equal the oracle's wherever the oracle's winning margin exceeds that tolerance."""
+    W, H, D = 320, 200, 40
+    L, R, _ = make(W, H, D, 5, 0)
+    F = oracle.forest(L)
+    lv, _ = oracle.cost_adgrad(L, R, D)
+    do, bo, ao = oracle.aggregate_dense(F, lv, want_agg=True)
+    eng = api.Stereo3DMST(exact=0, keep_aggregated=1)
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    eng.build_cost_volume(D)
+    disp, best = eng.aggregate_dense(0)
+    agg = eng.get_aggregated(0)
+    tol = 1e-4
+    assert np.all(np.abs(agg - ao) <= tol * np.abs(ao) + 1e-12)
+    assert np.all(np.abs(best - bo) <= tol * np.abs(bo) + 1e-12)
+    srt = np.sort(ao, axis=0)
+    clear = (srt[1] - srt[0]) > 2 * tol * srt[1]          # the winner is separated from the runner-up by more than the tolerance
+    assert clear.mean() > 0.5
+    assert np.array_equal(disp[clear], do[clear])
+    # wherever the label differs it is a near-tie: the exact cost of the chosen label is within the tolerance of the minimum
+    chosen = ao[disp, np.arange(W * H)]
+    assert np.all(chosen - bo <= 2 * tol * np.abs(bo) + 1e-12)
+    eng.close()
