@@ -149,6 +149,11 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
  * batch fill the GPU where a single pair waits on its deepest tree), then LR check/fill per frame.
  * left_disp[i] / right_disp[i]: float[H][W] per frame (the arrays or any entry may be NULL). */
 int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp);
+/* The two halves of s3dmst_run_dense_batch, for software pipelining over consecutive batches (two sets of contexts,
+ * two host threads): front = forests + cost volumes of every frame (latency-bound, many small kernels), back = the
+ * joint aggregation launch (HBM-bound), LR check/fill and the copies.  front(k+1) may run while back(k) does. */
+int s3dmst_batch_front(s3dmst_ctx** ctxs, int n, int D);
+int s3dmst_batch_back(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp);
 
 /* Per-stage device time of the most recent call, in ms (CUDA events on the context's stream). */
 enum {

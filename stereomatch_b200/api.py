@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
 ]
 
 _lib = None
@@ -91,6 +91,8 @@ def load_library():
     L.s3dmst_run_dense.argtypes = [c_p, C.c_int, C.c_int, c_p, c_p]
     L.s3dmst_reproject_to_3d.argtypes = [c_p, c_p, C.c_float, C.c_int, c_p, c_p]
     L.s3dmst_run_dense_batch.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
+    L.s3dmst_batch_front.argtypes = [C.POINTER(c_p), C.c_int, C.c_int]
+    L.s3dmst_batch_back.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_stage_ms.argtypes = [c_p, C.c_int]
     L.s3dmst_stage_ms.restype = C.c_double
     L.s3dmst_launch_count.argtypes = [c_p]
@@ -321,6 +323,32 @@ def run_dense_batch(engines, D, fill=False, fetch=True, out=None):
     rc = L.s3dmst_run_dense_batch(hs, n, int(D), int(fill), pl, pr)
     if rc != 0:
         raise S3Error(f"s3dmst error {rc}: {L.s3dmst_last_error(engines[0].h).decode()}")
+    for e in engines:
+        e.D = D
+    return out
+
+
+def batch_front(engines, D):
+    """Forests + cost volumes of every frame (first half of run_dense_batch)."""
+    n = len(engines)
+    hs = (c_p * n)(*[e.h for e in engines])
+    rc = engines[0].L.s3dmst_batch_front(hs, n, int(D))
+    if rc != 0:
+        raise S3Error(f"s3dmst error {rc}: {engines[0].L.s3dmst_last_error(engines[0].h).decode()}")
+
+
+def batch_back(engines, D, fill=False, out=None):
+    """Joint aggregation + LR check (+ copies into `out`) of frames whose batch_front has run."""
+    n = len(engines)
+    hs = (c_p * n)(*[e.h for e in engines])
+    if out is not None:
+        pl = (c_p * n)(*[c_p(_addr(o[0])) for o in out])
+        pr = (c_p * n)(*[c_p(_addr(o[1])) for o in out])
+    else:
+        pl = pr = None
+    rc = engines[0].L.s3dmst_batch_back(hs, n, int(D), int(fill), pl, pr)
+    if rc != 0:
+        raise S3Error(f"s3dmst error {rc}: {engines[0].L.s3dmst_last_error(engines[0].h).decode()}")
     for e in engines:
         e.D = D
     return out

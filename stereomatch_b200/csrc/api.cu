@@ -585,7 +585,8 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     return 0;
 }
 
-int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {
+// phases: bit 0 = front (forests + cost volumes of every frame), bit 1 = back (joint aggregation, LR check, copies)
+static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp, int phases) {
     if (!ctxs || n < 1) return S3DMST_E_ARG;
     s3dmst_ctx* ctx = ctxs[0];
     for (int c = 0; c < n; c++)
@@ -620,7 +621,7 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
     // Optional (S3_FH_JOINT=1): image stages on the frames' own streams, then ONE forest-kernel launch per
     // S3_FH_MAX_VIEWS / 2 frames.  Measured at C2, 8 frames: the joint launch is bound by L2 sector throughput
     // (22.5 ms until all forests are done) and loses to per-frame launches overlapping on the streams (18 ms).
-    for (int c = 0; joint_fh && c < n; c++) {
+    for (int c = 0; (phases & 1) && joint_fh && c < n; c++) {
         s3dmst_ctx* cx = ctxs[c];
         memset(cx->ev_set, 0, sizeof cx->ev_set);
         int r = [&]() -> int {
@@ -630,11 +631,12 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
         }();
         if (r) return c == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frame %d: %s", c, cx->err.c_str());
     }
-    for (int c0 = 0; joint_fh && c0 < n; c0 += S3_FH_MAX_VIEWS / 2) {
+    for (int c0 = 0; (phases & 1) && joint_fh && c0 < n; c0 += S3_FH_MAX_VIEWS / 2) {
         const int r = s3_fh_launch_multi(ctxs + c0, std::min(S3_FH_MAX_VIEWS / 2, n - c0), 3);
         if (r) return c0 == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frames %d..: %s", c0, ctxs[c0]->err.c_str());
     }
-    if (n == 1)
+    if (!(phases & 1)) {
+    } else if (n == 1)
         front(0);
     else {
         std::vector<std::thread> th;
@@ -645,6 +647,7 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
         if (rc[c]) return c == 0 ? rc[c] : s3_fail(ctx, rc[c], "run_dense_batch: frame %d: %s", c, ctxs[c]->err.c_str());
     S3_CUDA(cudaSetDevice(ctx->device));
     const double t_front = now();
+    if (!(phases & 2)) return 0;
     {
         int r = ctx->P.agg_kernel == 0 ? s3_aggregate_flow_multi(ctxs, n, 3, 0, D) : 1;
         if (r == 1) {
@@ -674,6 +677,14 @@ int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** le
         fprintf(stderr, "[batch %d] forests done +%.2f ms, cost volumes done +%.2f ms, total %.2f ms\n", n, tf - t_begin, t_front - t_begin, now() - t_begin);
     }
     return 0;
+}
+
+int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {
+    return run_dense_batch_impl(ctxs, n, D, fill, left_disp, right_disp, 3);
+}
+int s3dmst_batch_front(s3dmst_ctx** ctxs, int n, int D) { return run_dense_batch_impl(ctxs, n, D, 0, nullptr, nullptr, 1); }
+int s3dmst_batch_back(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {
+    return run_dense_batch_impl(ctxs, n, D, fill, left_disp, right_disp, 2);
 }
 
 }  // extern "C"

@@ -121,7 +121,7 @@ struct FHArgs2 {
     FHArgs v[S3_FH_MAX_VIEWS];
     int nviews;
     int seg_cap;         // capacity of one CTA's segment of the live-edge lists (entries)
-    unsigned* bar;       // grid barrier counter (zeroed by the host)
+    unsigned* bar;       // [S3_FH_MAX_VIEWS][32] one barrier counter per view (zeroed by the host)
     int* gcnt;           // [S3_FH_ROUNDS][S3_FH_MAX_VIEWS] per-round, per-view live counts (zeroed by the host)
 };
 
@@ -172,33 +172,28 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
     const int gstride = nblk * blockDim.x;
     const int cbase = crank * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const int nviews = AA.nviews;
     unsigned bar_target = 0;
     int round = 0;
     long long tA = 0, tB = 0, tS = 0, t0 = clock64(), t1;
     long long visits = 0;
     __shared__ int s_cnt;
 #define FH_T(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
-#define FH_BAR() fh_grid_bar(AA.bar, bar_target, (unsigned)nblk_all)
+#define FH_BAR() fh_grid_bar(AA.bar + 32 * vi, bar_target, (unsigned)nblk)  // the views never wait for each other
 
     // ------------------------------------------------------------------ FH
     {
-        int n_live[S3_FH_MAX_VIEWS], lev[S3_FH_MAX_VIEWS], band_pos[S3_FH_MAX_VIEWS];  // per view: live entries after the previous round
-        for (int v = 0; v < S3_FH_MAX_VIEWS; v++) n_live[v] = lev[v] = band_pos[v] = 0;       // (all CTAs), weight levels ingested, == lvl_off[lev]
-        int my_src = 0;            // entries in this CTA's source segment (live + flagged ones of the previous round)
+        int n_live = 0;    // live entries of this view after the previous round (all its CTAs)
+        int lev = 0;       // weight levels ingested so far
+        int band_pos = 0;  // == lvl_off[lev]
+        int my_src = 0;    // entries in this CTA's source segment (live + flagged ones of the previous round)
         int par = 0;
         const size_t seg = (size_t)crank * AA.seg_cap;
         while (true) {
-            int band_lo_vi = 0, work = 0;
-            for (int v = 0; v < nviews; v++) {  // uniform across the grid: every thread tracks both views
-                const int blo = band_pos[v];
-                if (v == vi) band_lo_vi = blo;
-                if (n_live[v] < AA.v[v].band_low)
-                    while (lev[v] < S3_NUM_W && n_live[v] + (band_pos[v] - blo) < AA.v[v].band_high)
-                        band_pos[v] = AA.v[v].lvl_off[++lev[v]];
-                work += n_live[v] + (band_pos[v] - blo);
-            }
-            if (work == 0) break;  // nothing live and nothing left to ingest in either view
+            const int band_lo_vi = band_pos;
+            if (n_live < A.band_low)
+                while (lev < S3_NUM_W && n_live + (band_pos - band_lo_vi) < A.band_high) band_pos = A.lvl_off[++lev];
+            const int work = n_live + (band_pos - band_lo_vi);
+            if (work == 0) break;  // nothing live and nothing left to ingest
             if (++round >= ROUND_CAP) {
                 if (gtid == 0) A.counters[CNT_ERR] = 1;
                 return;
@@ -208,7 +203,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             unsigned long long* pick = A.pick[par];
             unsigned long long* pick_prev = A.pick[par ^ 1];
             // ---- phase 1: settle last round's decisions, re-root the survivors, post keys, compact
-            const int n_new = band_pos[vi] - band_lo_vi;
+            const int n_new = band_pos - band_lo_vi;
             const int share = (n_new + nblk - 1) / nblk;
             const int new_lo = min(n_new, crank * share), new_hi = min(n_new, (crank + 1) * share);
             const int total = my_src + (new_hi - new_lo);
@@ -259,7 +254,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             FH_T(tA);
             FH_BAR();
             FH_T(tS);
-            for (int v = 0; v < nviews; v++) n_live[v] = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round + v);
+            n_live = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round + vi);
             // ---- phase 2: decide every edge that is the minimum of one of its components
             for (int pos = threadIdx.x; pos < my_cnt; pos += blockDim.x) {
                 FHEntry en = dst[pos];
@@ -351,9 +346,9 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             live++;
         }
         round++;
-        block_sum_to_counter(live, AA.gcnt + S3_FH_MAX_VIEWS * round);  // every view adds into one counter: the loop ends for all together
+        block_sum_to_counter(live, AA.gcnt + S3_FH_MAX_VIEWS * round + vi);
         FH_BAR();
-        const int nlive = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round);
+        const int nlive = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round + vi);
         if (nlive == 0) break;
         for (int pos = gtid; pos < nlist; pos += gstride) {
             const uint32_t e = A.elist[pos];
@@ -758,11 +753,11 @@ int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask) {
     if (grid > ctx->num_sms * ctas_per_sm) return s3_fail(ctx, S3DMST_E_ARG, "forest kernel: %d views do not fit the GPU in one cooperative launch", nv);
     AA.nviews = nv;
     AA.seg_cap = (2 * ctx->N + per_view - 1) / per_view + S3_FH_SEG_SLACK;
-    const size_t sync_ints = 64 + (size_t)S3_FH_ROUNDS * S3_FH_MAX_VIEWS;
+    const size_t sync_ints = 32 * S3_FH_MAX_VIEWS + (size_t)S3_FH_ROUNDS * S3_FH_MAX_VIEWS;  // one barrier word (own 128-byte line) per view + counters
     if (!ctx->fh_sync) S3_CUDA(cudaMalloc(&ctx->fh_sync, sizeof(int) * sync_ints));
     S3_CUDA(cudaMemsetAsync(ctx->fh_sync, 0, sizeof(int) * sync_ints, ctx->stream));
     AA.bar = reinterpret_cast<unsigned*>(ctx->fh_sync);
-    AA.gcnt = ctx->fh_sync + 64;
+    AA.gcnt = ctx->fh_sync + 32 * S3_FH_MAX_VIEWS;
     for (int c = 1; c < nctx; c++) {  // the other frames' image stages come first
         S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
         S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[c]->ev_xctx, 0));

@@ -3,6 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stereomatch_b200 import api, synth
 W, H, D = 1280, 720, 128
+if len(sys.argv) > 4:
+    W, H = int(sys.argv[3]), int(sys.argv[4])
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 engs = []
