@@ -424,20 +424,20 @@ __global__ void k_label_ids(int N, const int* __restrict__ root_of, const int* _
     atomicAdd(tree_size + t, 1);
 }
 
-// ---- per-pixel forest adjacency, pre-sorted: four 16-bit entries (w << 2) | direction (0 up, 1 left, 2 right, 3 down) in
+// ---- per-pixel forest adjacency, pre-sorted: four 16-bit entries (w << 3) | direction (0 up, 1 left, 2 right, 3 down) in
 // ascending order = the order the reference's per-vertex adjacency lists hold them (edges are inserted in sorted-edge
 // order (w, a, b), Stereo3DMST.cpp:436-445; for equal w the edge ids order the directions up < left < right < down);
-// 0xFFFF = no forest edge.  One 8-byte record per BFS node instead of 4 mask + 4 weight gathers and a sort.
+// 0xFFFF = no forest edge (its direction field, 7, matches no parent direction).  One 8-byte record per BFS node instead of 4 mask + 4 weight gathers and a sort.
 __global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const uint8_t* __restrict__ mask,
                           unsigned long long* __restrict__ adjw) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= W * H) return;
     const int x = p % W, y = p / W;
     uint32_t e[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
-    if (y > 0 && mask[2 * (p - W) + 1]) e[0] = ((uint32_t)ew[2 * (p - W) + 1] << 2) | 0u;
-    if (x > 0 && mask[2 * (p - 1)]) e[1] = ((uint32_t)ew[2 * (p - 1)] << 2) | 1u;
-    if (x < W - 1 && mask[2 * p]) e[2] = ((uint32_t)ew[2 * p] << 2) | 2u;
-    if (y < H - 1 && mask[2 * p + 1]) e[3] = ((uint32_t)ew[2 * p + 1] << 2) | 3u;
+    if (y > 0 && mask[2 * (p - W) + 1]) e[0] = ((uint32_t)ew[2 * (p - W) + 1] << 3) | 0u;
+    if (x > 0 && mask[2 * (p - 1)]) e[1] = ((uint32_t)ew[2 * (p - 1)] << 3) | 1u;
+    if (x < W - 1 && mask[2 * p]) e[2] = ((uint32_t)ew[2 * p] << 3) | 2u;
+    if (y < H - 1 && mask[2 * p + 1]) e[3] = ((uint32_t)ew[2 * p + 1] << 3) | 3u;
 #define S3_CSWAP(i, j) { const uint32_t lo = min(e[i], e[j]), hi = max(e[i], e[j]); e[i] = lo; e[j] = hi; }
     S3_CSWAP(0, 1) S3_CSWAP(2, 3) S3_CSWAP(0, 2) S3_CSWAP(1, 3) S3_CSWAP(1, 2)
 #undef S3_CSWAP
@@ -485,29 +485,23 @@ struct BfsArgs2 {
 #if BFS_INSTR
 __device__ long long g_dummy;
 #endif
-// One node of one BFS level: decode the frontier word, fetch the adjacency record, drop the parent entry.
-// Returns the child count; `kids` = the (at most 4) child entries in order, 0xFFFF-padded.
-__device__ __forceinline__ int bfs_expand(uint32_t fw, const unsigned long long* __restrict__ adjw, int& pix, unsigned long long& kids, long long& g_ldg_cycles) {
+// One node of one BFS level: decode the frontier word, fetch the adjacency record, drop the parent's entry.
+// Returns the child count; k0..k3 = the child entries in order, 0xFFFF-padded (kept in four registers: every use below
+// is straight-line code — the per-level instruction count of ONE warp is what bounds this kernel).
+__device__ __forceinline__ int bfs_expand(uint32_t fw, const unsigned long long* __restrict__ adjw, int& pix, uint32_t& k0, uint32_t& k1, uint32_t& k2,
+                                          uint32_t& k3) {
     pix = (int)(fw & 0x0FFFFFFFu);
-    const uint32_t pdir = (fw >> 28) & 7u;  // bit 31: the parent is S3_AGG_NEAR or more nodes back
-#if BFS_INSTR
-    const long long tl0 = clock64();
-#endif
+    const uint32_t pdir = (fw >> 28) & 7u;  // 4 = no parent (root); bit 31: the parent is S3_AGG_NEAR or more nodes back
     const unsigned long long rec = __ldg(adjw + pix);
-#if BFS_INSTR
-    if (rec == 0x1234567812345678ull) pix++;
-    g_ldg_cycles += clock64() - tl0;
-#endif
-    // position of the parent's entry (4 = none: the root, whose pdir is 4)
-    const uint32_t e0 = (uint32_t)rec & 0xFFFFu, e1 = (uint32_t)(rec >> 16) & 0xFFFFu, e2 = (uint32_t)(rec >> 32) & 0xFFFFu, e3 = (uint32_t)(rec >> 48);
-    const int pp = (e0 != 0xFFFFu && (e0 & 3u) == pdir) ? 0 : (e1 != 0xFFFFu && (e1 & 3u) == pdir) ? 1 : (e2 != 0xFFFFu && (e2 & 3u) == pdir) ? 2
-                   : (e3 != 0xFFFFu && (e3 & 3u) == pdir) ? 3 : 4;
-    const int nvalid = (e0 != 0xFFFFu) + (e1 != 0xFFFFu) + (e2 != 0xFFFFu) + (e3 != 0xFFFFu);
-    // delete element pp from the sorted list (invalid entries sort last, so the rest stays in order)
-    const unsigned long long lowmask = pp >= 4 ? ~0ull : ((1ull << (16 * pp)) - 1ull);
-    const unsigned long long hi = pp >= 3 ? 0ull : (rec >> (16 * (pp + 1))) << (16 * pp);
-    kids = pp >= 4 ? rec : ((rec & lowmask) | hi | (0xFFFFull << 48));
-    return nvalid - (pp < 4 ? 1 : 0);
+    const uint32_t lo = (uint32_t)rec, hi = (uint32_t)(rec >> 32);
+    const uint32_t e0 = lo & 0xFFFFu, e1 = lo >> 16, e2 = hi & 0xFFFFu, e3 = hi >> 16;
+    // f_k: the parent's entry sits at a position <= k; the list without it is e_k below it and e_{k+1} from there on
+    const bool f0 = (e0 & 7u) == pdir, f1 = f0 || (e1 & 7u) == pdir, f2 = f1 || (e2 & 7u) == pdir, f3 = f2 || (e3 & 7u) == pdir;
+    k0 = f0 ? e1 : e0;
+    k1 = f1 ? e2 : e1;
+    k2 = f2 ? e3 : e2;
+    k3 = f3 ? 0xFFFFu : e3;
+    return (k0 != 0xFFFFu) + (k1 != 0xFFFFu) + (k2 != 0xFFFFu) + (k3 != 0xFFFFu);
 }
 
 // Level-synchronous BFS from the tree's minimum pixel.  The reference's queue order (Stereo3DMST.cpp:477-518) is:
@@ -551,33 +545,44 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
         __syncthreads();
         int a = base, b = base + 1, L = 0, cur = 0;
         const long long tb0 = clock64();
-        long long tq = tb0, q_load = 0, q_scan = 0, q_store = 0, q_sync = 0, q_ldg = 0;
-        (void)q_ldg; (void)tq; (void)q_load; (void)q_scan; (void)q_store; (void)q_sync;
+        long long tq = tb0, q_load = 0, q_scan = 0, q_store = 0, q_sync = 0;
+        (void)tq; (void)q_load; (void)q_scan; (void)q_store; (void)q_sync;
         // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record
-        auto emit = [&](int g, int pix, int cc, unsigned long long kids, int cb, int bnext, int Lc, int curc, uint32_t fwg) {
-            NodeUp nu;
-            nu.child_begin = cb;
-            nu.child_count = cc | ((fwg >> 31) ? S3_NU_FARPARENT : 0);
-            const uint32_t k0 = (uint32_t)kids & 0xFFFFu, k1 = (uint32_t)(kids >> 16) & 0xFFFFu, k2 = (uint32_t)(kids >> 32) & 0xFFFFu, k3 = (uint32_t)(kids >> 48);
-            nu.cw01 = (cc > 0 ? k0 >> 2 : 0u) | ((cc > 1 ? k1 >> 2 : 0u) << 16);
-            nu.cw23 = (cc > 2 ? k2 >> 2 : 0u) | ((cc > 3 ? k3 >> 2 : 0u) << 16);
-            node_up[g] = nu;
-            if (cc == 0) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_LEAF;
-            else if (cb + cc - 1 - g >= S3_AGG_NEAR) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_FAR;
-            unsigned long long kk = kids;
-            for (int k = 0; k < cc; k++, kk >>= 16) {
-                const uint32_t en = (uint32_t)kk & 0xFFFFu;
-                const int dir = (int)(en & 3u);
-                const int q = pix + (dir == 0 ? -W : dir == 1 ? -1 : dir == 2 ? 1 : W);
-                const int h = cb + k;
-                const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28) | (h - g >= S3_AGG_NEAR ? 0x80000000u : 0u);  // the parent lies in the opposite direction
-                if (h - bnext < BFS_FRONT) s_front[curc ^ 1][h - bnext] = fw;
-                else front[h] = fw;
-                pixel_node[q] = h;
-                node_dn[h] = make_int4(g, (int)(en >> 2), Lc + 1, q);
-                if (warm) {  // q's possible children: rows above and below (q +- 1 share q's line)
-                    if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
-                    if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
+        // one child of node g: frontier word, pixel -> node, root->leaf record, warm-up of its own children's lines
+        auto emit_child = [&](int g, int pix, uint32_t en, int h, int bnext, int Lc, int curc) {
+            const int dir = (int)(en & 7u);
+            const int q = pix + ((dir & 2) ? 1 : -1) * ((dir == 0 || dir == 3) ? W : 1);  // 0 up, 1 left, 2 right, 3 down
+            const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28) | (h - g >= S3_AGG_NEAR ? 0x80000000u : 0u);  // the parent lies in the opposite direction
+            if (h - bnext < BFS_FRONT) s_front[curc ^ 1][h - bnext] = fw;
+            else front[h] = fw;
+            pixel_node[q] = h;
+            node_dn[h] = make_int4(g, (int)(en >> 3), Lc + 1, q);
+            if (warm) {  // q's possible children: rows above and below (q +- 1 share q's line)
+                if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
+                if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
+            }
+        };
+        // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record; `active` is false
+        // for lanes without a node (they only take part in the warp-uniform votes)
+        auto emit = [&](bool active, int g, int pix, int cc, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, int cb, int bnext, int Lc, int curc, uint32_t fwg) {
+            if (active) {
+                NodeUp nu;
+                nu.child_begin = cb;
+                nu.child_count = cc | ((fwg >> 31) ? S3_NU_FARPARENT : 0);
+                nu.cw01 = (cc > 0 ? k0 >> 3 : 0u) | ((cc > 1 ? k1 >> 3 : 0u) << 16);
+                nu.cw23 = (cc > 2 ? k2 >> 3 : 0u) | ((cc > 3 ? k3 >> 3 : 0u) << 16);
+                node_up[g] = nu;
+                if (cc == 0) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_LEAF;
+                else if (cb + cc - 1 - g >= S3_AGG_NEAR) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_FAR;
+            }
+            if (__any_sync(0xffffffffu, active && cc > 0)) {
+                if (active && cc > 0) emit_child(g, pix, k0, cb, bnext, Lc, curc);
+                if (__any_sync(0xffffffffu, active && cc > 1)) {
+                    if (active && cc > 1) emit_child(g, pix, k1, cb + 1, bnext, Lc, curc);
+                    if (__any_sync(0xffffffffu, active && cc > 2)) {
+                        if (active && cc > 2) emit_child(g, pix, k2, cb + 2, bnext, Lc, curc);
+                        if (active && cc > 3) emit_child(g, pix, k3, cb + 3, bnext, Lc, curc);
+                    }
                 }
             }
         };
@@ -586,17 +591,17 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             if (wid == 0) {
                 while (a < b && b - a <= 32) {
                     int cc = 0, pix = 0;
-                    unsigned long long kids = 0;
+                    uint32_t k0 = 0xFFFFu, k1 = 0xFFFFu, k2 = 0xFFFFu, k3 = 0xFFFFu;
                     const int g = a + lane;
                     uint32_t fwg = 0;
-                    if (g < b) { fwg = s_front[cur][lane]; cc = bfs_expand(fwg, adjw, pix, kids, q_ldg); }
+                    if (g < b) { fwg = s_front[cur][lane]; cc = bfs_expand(fwg, adjw, pix, k0, k1, k2, k3); }
                     BFS_CLK(q_load);
                     // exclusive prefix of cc (0..4) from three independent ballots
                     const uint32_t b0 = __ballot_sync(0xffffffffu, cc & 1), b1 = __ballot_sync(0xffffffffu, cc & 2), b2 = __ballot_sync(0xffffffffu, cc & 4);
                     const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
                     const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
                     BFS_CLK(q_scan);
-                    if (g < b) emit(g, pix, cc, kids, b + excl, b, L, cur, fwg);
+                    emit(g < b, g, pix, cc, k0, k1, k2, k3, b + excl, b, L, cur, fwg);
                     a = b;
                     b += total;
                     L++;
@@ -616,9 +621,9 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             for (int chunk = a; chunk < b; chunk += BFS_THREADS) {
                 const int g = chunk + tid;
                 int cc = 0, pix = 0;
-                unsigned long long kids = 0;
+                uint32_t k0 = 0xFFFFu, k1 = 0xFFFFu, k2 = 0xFFFFu, k3 = 0xFFFFu;
                 uint32_t fwg = 0;
-                if (g < b) { fwg = g - a < BFS_FRONT ? s_front[cur][g - a] : front[g]; cc = bfs_expand(fwg, adjw, pix, kids, q_ldg); }
+                if (g < b) { fwg = g - a < BFS_FRONT ? s_front[cur][g - a] : front[g]; cc = bfs_expand(fwg, adjw, pix, k0, k1, k2, k3); }
                 int incl = cc;
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -633,7 +638,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                     if (i < wid) wbase += v;
                     chunk_total += v;
                 }
-                if (g < b) emit(g, pix, cc, kids, b + run + incl - cc + wbase, b, L, cur, fwg);
+                emit(g < b, g, pix, cc, k0, k1, k2, k3, b + run + incl - cc + wbase, b, L, cur, fwg);
                 run += chunk_total;
                 __syncthreads();  // s_warp reuse; frontier words visible to the block
             }
@@ -695,7 +700,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
         }
         __syncthreads();
 #if BFS_INSTR
-        if (u == 0 && tid == 0) printf("bfs cycles/level: load %lld (ldg %lld) scan %lld store %lld sync %lld\n", q_load / L, q_ldg / L, q_scan / L, q_store / L, q_sync / L);
+        if (u == 0 && tid == 0) printf("bfs cycles/level: load %lld scan %lld store %lld sync %lld\n", q_load / L, q_scan / L, q_store / L, q_sync / L);
 #endif
         if (u == 0 && tid == 0) { B.dbg_out[0] = (int)((tb1 - tb0) >> 4); B.dbg_out[1] = (int)((clock64() - tb1) >> 4); B.dbg_out[2] = L; B.dbg_out[3] = b - base; }
     }
