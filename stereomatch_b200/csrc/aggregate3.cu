@@ -218,15 +218,17 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + l0 + 2 * lane);
         char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * Dp + l0 + 2 * lane);
         const char* aup_lane0 = reinterpret_cast<const char*>(aupT + l0 + 2 * lane);  // + c * Dp * 8 for a far child
-        int4 nu_n = make_int4(0, 0, 0, 0);
-        float2 cf_n[NH];
+        // the node's record and cost row live in these registers from the end of the previous iteration (the loads are
+        // issued right after the previous publish, so they are in flight during this warp's wait for the children)
+        int4 nu = make_int4(0, 0, 0, 0);  // {child_begin, child_count, cw01, cw23}
+        float2 cf[NH];
 #pragma unroll
-        for (int h = 0; h < NH; h++) cf_n[h] = make_float2(0.f, 0.f);
+        for (int h = 0; h < NH; h++) cf[h] = make_float2(0.f, 0.f);
         if (v >= base) {
-            nu_n = *reinterpret_cast<const int4*>(nup_p);
+            nu = *reinterpret_cast<const int4*>(nup_p);
 #pragma unroll
             for (int h = 0; h < NH; h++)
-                if (act[h]) cf_n[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
+                if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
         } else if (lane == 0)
             a3_st_release(prog_a + 4u * w, base);  // a warp without nodes never holds anybody back
         int guard_ok = top + 1;  // writing ring row v is known to be safe for every v >= guard_ok
@@ -237,10 +239,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #if A3_INSTR
             n_nodes++;
 #endif
-            const int4 nu = nu_n;  // {child_begin, child_count, cw01, cw23}
-            float2 cf[NH];
-#pragma unroll
-            for (int h = 0; h < NH; h++) cf[h] = cf_n[h];
             const int vn = v - W;
             const int cc = nu.y & 7, cb = nu.x;
             T2 acc[NH];
@@ -310,16 +308,17 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             A3_CLK(q_pub);
             // Global accesses are issued only AFTER the publish: the release fence waits for every memory operation the warp
             // has in flight, and a load still on its way from HBM would put its latency on every level of the tree.
-            if (vn >= base) {  // next node of this warp: record and cost row, one iteration ahead
-                nu_n = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
+            const bool store_late = !far_parent;
+            if (vn >= base) {  // next node of this warp: record and cost row
+                nu = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) cf_n[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
+                    if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
             if (lane < NH * 2 && v - A3_PF * W >= base)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - 2 * lane * 4 - A3_PF * strideC + lane * 128));
-            if (!far_parent) {  // read back on the way down
+            if (store_late) {  // read back on the way down
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = acc[h];
@@ -344,15 +343,15 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         const char* ndn_p = reinterpret_cast<const char*>(V.node_dn + v);
         char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * Dp + l0 + 2 * lane);
         const char* aup_lane0 = reinterpret_cast<const char*>(aupT + l0 + 2 * lane);
-        int4 nd_n = make_int4(0, 0, 0, 0);
-        T2 au_n[NH];
+        int4 nd = make_int4(0, 0, 0, 0);  // {parent, parent weight, level | flags, pixel}
+        T2 au[NH];
 #pragma unroll
-        for (int h = 0; h < NH; h++) au_n[h] = TT::zero2();
+        for (int h = 0; h < NH; h++) au[h] = TT::zero2();
         if (v < end) {
-            nd_n = *reinterpret_cast<const int4*>(ndn_p);
+            nd = *reinterpret_cast<const int4*>(ndn_p);
 #pragma unroll
             for (int h = 0; h < NH; h++)
-                if (act[h]) au_n[h] = *reinterpret_cast<const T2*>(aup_p + h * HB);
+                if (act[h]) au[h] = *reinterpret_cast<const T2*>(aup_p + h * HB);
         } else if (lane == 0)
             a3_st_release(prog_a + 4u * w, end);
         int guard_ok = base - 1;  // writing ring row v is known to be safe for every v <= guard_ok
@@ -378,17 +377,8 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 }
             }
         };
-        T2 fin_prev[NH];
-#pragma unroll
-        for (int h = 0; h < NH; h++) fin_prev[h] = TT::zero2();
-        int v_prev = -1, pix_prev = 0;
         while (v < end) {
-            const int4 nd = nd_n;  // {parent, parent weight, level | far-child flag, pixel}
-            T2 au[NH];
-#pragma unroll
-            for (int h = 0; h < NH; h++) au[h] = au_n[h];
             const int vn = v + W;
-            if (v_prev >= 0) wta(fin_prev, v_prev, pix_prev);
             const int p = nd.x;
             T2 fin[NH];
             if (p != v) {
@@ -441,25 +431,22 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             }
             __syncwarp();
             if (lane == 0) a3_st_release(prog_a + 4u * w, v);
-            // next node's loads: after the publish (see the leaf->root pass)
+            // next node's loads: after the publish (see the leaf->root pass), into the registers this node is done with
+            const int pix = nd.w;
             if (vn < end) {
-                nd_n = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
+                nd = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) au_n[h] = *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
+                    if (act[h]) au[h] = *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
             }
             if (lane < NH * (int)sizeof(T) / 2 && v + A3_PF * W < end)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * (int)sizeof(T) + A3_PF * strideA + lane * 128));
-            // the WTA of this node is done at the top of the next iteration, in the shadow of the next wait
-#pragma unroll
-            for (int h = 0; h < NH; h++) fin_prev[h] = fin[h];
-            v_prev = v;
-            pix_prev = nd.w;
+            // the WTA of this node runs while those loads are in flight and the next parent is still being computed
+            wta(fin, v, pix);
             ndn_p += (long long)W * 16;
             aup_p += strideA;
             v = vn;
         }
-        if (v_prev >= 0) wta(fin_prev, v_prev, pix_prev);
     }
 }
 
