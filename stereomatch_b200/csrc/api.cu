@@ -39,7 +39,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 
 static void free_view(View& V) {
     DFREE(V.bgr); DFREE(V.raw4); DFREE(V.med); DFREE(V.gray); DFREE(V.ew);
-    DFREE(V.uf_parent); DFREE(V.uf_size); DFREE(V.uf_lastw); DFREE(V.adjw); DFREE(V.bfs_front); DFREE(V.uf_pick[0]); DFREE(V.uf_pick[1]); DFREE(V.fh_ent[0]); DFREE(V.fh_ent[1]); DFREE(V.uf_resv);
+    DFREE(V.uf_comp); DFREE(V.uf_parent); DFREE(V.adjw); DFREE(V.bfs_front); DFREE(V.fh_ent[0]); DFREE(V.fh_ent[1]); DFREE(V.uf_resv);
     DFREE(V.mask); DFREE(V.elist); DFREE(V.e_ra); DFREE(V.e_rb); DFREE(V.e_flag);
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
@@ -56,9 +56,10 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     const size_t n = N;
     S3_CUDA(dalloc(&V.bgr, 3 * n)); S3_CUDA(dalloc(&V.raw4, n)); S3_CUDA(dalloc(&V.med, n)); S3_CUDA(dalloc(&V.gray, n));
     S3_CUDA(dalloc(&V.ew, 2 * n));
-    S3_CUDA(dalloc(&V.uf_parent, n)); S3_CUDA(dalloc(&V.uf_size, n)); S3_CUDA(dalloc(&V.uf_lastw, n));
+    { unsigned char* b = nullptr; S3_CUDA(dalloc(&b, 32 * n)); V.uf_comp = b; }
+    S3_CUDA(dalloc(&V.uf_parent, n));
     S3_CUDA(dalloc(&V.adjw, n)); S3_CUDA(dalloc(&V.bfs_front, n));
-    S3_CUDA(dalloc(&V.uf_pick[0], n)); S3_CUDA(dalloc(&V.uf_pick[1], n)); S3_CUDA(dalloc(&V.uf_resv, n));
+    S3_CUDA(dalloc(&V.uf_resv, n));
     for (int i = 0; i < 2; i++) { unsigned char* b = nullptr; S3_CUDA(dalloc(&b, 32 * n + 16 * (size_t)S3_FH_MAX_CTAS * (S3_FH_SEG_SLACK + 1))); V.fh_ent[i] = b; }
     S3_CUDA(dalloc(&V.mask, 2 * n)); S3_CUDA(dalloc(&V.elist, 2 * n)); S3_CUDA(dalloc(&V.e_ra, 2 * n));
     S3_CUDA(dalloc(&V.e_rb, 2 * n)); S3_CUDA(dalloc(&V.e_flag, 2 * n));

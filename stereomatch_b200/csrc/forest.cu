@@ -37,6 +37,19 @@
 #define CNT_ACT (S3_MAX_ROUNDS - 20)  // [2] live-list lengths of the FH rounds
 #define ROUND_CAP (S3_FH_ROUNDS - 32)
 
+// Component record: everything a round reads about a component (a root) sits in ONE 32-byte sector (the forest kernel
+// is bound by random sector traffic: L2 for one pair, DRAM for a batch).  The union-find parents stay in a compact int
+// array: the find chains walk ordinary pixels, whose neighbours share sectors (packing them too was measured 2x slower).  The kernels address the fields
+// through strided pointers: int fields stride FHC_I ints, 64-bit fields stride FHC_L.
+struct __align__(32) FHComp {
+    unsigned long long pick[2];  // minimum live edge key of the component, by round parity
+    int size;                    // pixels of the component (valid at the root)
+    int lastw;                   // weight of the last accepted edge (valid at the root)
+    int pad[2];
+};
+#define FHC_I 8
+#define FHC_L 4
+
 struct __align__(16) FHEntry {
     unsigned long long key;  // (w << 32) | edge id; bit 63 = accepted last round (ra = the root that hooked), bit 62 = rejected
     int ra, rb;              // endpoint components when the entry was last looked at
@@ -106,7 +119,7 @@ __device__ __forceinline__ void uf_find2(int* parent, int& x, int& y) {
 
 // segment-graph.h:27,80 — THRESHOLD(size,c) is a float division (Q2), added to a double w
 __device__ __forceinline__ bool uf_open(const FHArgs& A, int r, int w) {
-    const double thr = (double)__ldcg(A.lastw + r) + (double)__fdiv_rn(A.c, (float)__ldcg(A.size + r));
+    const double thr = (double)__ldcg(A.lastw + FHC_I * r) + (double)__fdiv_rn(A.c, (float)__ldcg(A.size + FHC_I * r));
     return (double)w <= thr;
 }
 
@@ -216,13 +229,13 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                 en.key = FH_NOKEY; en.ra = 0; en.rb = 0;
                 if (pos < my_src) {
                     en = src[pos];
-                    __stcg(pick_prev + en.ra, FH_NOKEY);  // clean the buffer the previous round posted into
-                    __stcg(pick_prev + en.rb, FH_NOKEY);
+                    __stcg(pick_prev + FHC_L * en.ra, FH_NOKEY);  // clean the buffer the previous round posted into
+                    __stcg(pick_prev + FHC_L * en.rb, FH_NOKEY);
                     if (en.key & FH_HOOKED) {
                         // accepted last round, en.ra hooked: its size flows to the root it ended under
                         const int R = uf_find(A.parent, en.ra);
-                        atomicAdd(A.size + R, __ldcg(A.size + en.ra));
-                        __stcg(A.lastw + R, (int)((en.key >> 32) & 0x3FFu));
+                        atomicAdd(A.size + FHC_I * R, __ldcg(A.size + FHC_I * en.ra));
+                        __stcg(A.lastw + FHC_I * R, (int)((en.key >> 32) & 0x3FFu));
                     } else if (!(en.key & FH_REJECT)) {
                         uf_find2(A.parent, en.ra, en.rb);
                         live = en.ra != en.rb;
@@ -236,8 +249,8 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                     live = en.ra != en.rb;
                 }
                 if (live) {
-                    atomicMin(pick + en.ra, en.key);
-                    atomicMin(pick + en.rb, en.key);
+                    atomicMin(pick + FHC_L * en.ra, en.key);
+                    atomicMin(pick + FHC_L * en.rb, en.key);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, live);
                 if (bal) {
@@ -258,7 +271,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
             // ---- phase 2: decide every edge that is the minimum of one of its components
             for (int pos = threadIdx.x; pos < my_cnt; pos += blockDim.x) {
                 FHEntry en = dst[pos];
-                const unsigned long long ka = __ldcg(pick + en.ra), kb = __ldcg(pick + en.rb);
+                const unsigned long long ka = __ldcg(pick + FHC_L * en.ra), kb = __ldcg(pick + FHC_L * en.rb);
                 const int wa = (int)(ka >> 32), wb = (int)(kb >> 32), w = (int)(en.key >> 32);
                 if (!uf_open(A, en.ra, wa) || !uf_open(A, en.rb, wb)) {  // (1): a dead endpoint
                     dst[pos].key = en.key | FH_REJECT;
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                     A.mask[(uint32_t)en.key] = 1;
                     int frm, to;
                     if (pa && pb) {  // only one side of a mutual pick hooks: the smaller component goes under the larger (shorter paths)
-                        const int sa = __ldcg(A.size + en.ra), sb = __ldcg(A.size + en.rb);
+                        const int sa = __ldcg(A.size + FHC_I * en.ra), sb = __ldcg(A.size + FHC_I * en.rb);
                         const bool a_hooks = sa < sb || (sa == sb && en.ra > en.rb);
                         frm = a_hooks ? en.ra : en.rb; to = a_hooks ? en.rb : en.ra;
                     }
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
         if (e < E2 && A.ew[e] != S3_NO_EDGE) {
             int ra = e >> 1, rb = ra + ((e & 1) ? A.W : 1);
             uf_find2(A.parent, ra, rb);
-            cand = ra != rb && (__ldcg(A.size + ra) < A.m || __ldcg(A.size + rb) < A.m);
+            cand = ra != rb && (__ldcg(A.size + FHC_I * ra) < A.m || __ldcg(A.size + FHC_I * rb) < A.m);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         if (bal) {
@@ -332,7 +345,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                 A.elist[pos] = S3_DEAD;
                 continue;
             }
-            const bool fa = __ldcg(A.size + ra) < A.m, fb = __ldcg(A.size + rb) < A.m;
+            const bool fa = __ldcg(A.size + FHC_I * ra) < A.m, fb = __ldcg(A.size + FHC_I * rb) < A.m;
             if (!fa && !fb) {
                 A.elist[pos] = S3_DEAD;  // big-big: can never fire (sizes only grow)
                 continue;
@@ -364,7 +377,7 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
                 const bool a_hooks = (fa && !fb) || (fa && fb && ra > rb);
                 const int frm = a_hooks ? ra : rb, to = a_hooks ? rb : ra;
                 __stcg(A.parent + frm, to);
-                atomicAdd(A.size + to, __ldcg(A.size + frm));
+                atomicAdd(A.size + FHC_I * to, __ldcg(A.size + FHC_I * frm));
                 A.e_flag[pos] = fl | 4;
             }
         }
@@ -382,15 +395,17 @@ __global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
     if (gtid == 0) { A.counters[CNT_ROUNDS] = round; A.counters[S3_MAX_ROUNDS - 11] = (int)(tA >> 10); }
 }
 
-__global__ void k_uf_init(int N, int* parent, int* size, int* lastw, unsigned long long* pick0, unsigned long long* pick1,
-                          unsigned long long* resv, int* minpix) {
+__global__ void k_uf_init(int N, FHComp* comp, int* parent, unsigned long long* resv, int* minpix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    FHComp c;
+    c.pick[0] = FH_NOKEY;
+    c.pick[1] = FH_NOKEY;
+    c.size = 1;
+    c.lastw = 0;
+    c.pad[0] = c.pad[1] = 0;
+    comp[i] = c;
     parent[i] = i;
-    size[i] = 1;
-    lastw[i] = 0;
-    pick0[i] = FH_NOKEY;
-    pick1[i] = FH_NOKEY;
     resv[i] = ~0ull;
     minpix[i] = 0x7fffffff;
 }
@@ -724,8 +739,9 @@ __global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __res
 static void fill_fh_args(s3dmst_ctx* ctx, View& V, FHArgs& A) {
     A.W = ctx->W; A.N = ctx->N; A.c = ctx->P.fh_c; A.m = std::max(2, ctx->P.min_cc_size);
     A.ew = V.ew; A.elist = V.elist; A.lvl_off = V.lvl_off;
-    A.parent = V.uf_parent; A.size = V.uf_size; A.lastw = V.uf_lastw; A.resv = V.uf_resv;
-    A.pick[0] = V.uf_pick[0]; A.pick[1] = V.uf_pick[1];
+    FHComp* comp = reinterpret_cast<FHComp*>(V.uf_comp);
+    A.parent = V.uf_parent; A.size = &comp->size; A.lastw = &comp->lastw; A.resv = V.uf_resv;
+    A.pick[0] = &comp->pick[0]; A.pick[1] = &comp->pick[1];
     A.ent[0] = reinterpret_cast<FHEntry*>(V.fh_ent[0]); A.ent[1] = reinterpret_cast<FHEntry*>(V.fh_ent[1]);
     static const int band_low = getenv("S3_FH_LOW") ? atoi(getenv("S3_FH_LOW")) : 16384;
     static const int band_high = getenv("S3_FH_HIGH") ? atoi(getenv("S3_FH_HIGH")) : 65536;
@@ -785,7 +801,7 @@ __global__ void k_label_sizes(int T, const int* __restrict__ rootpix, const int*
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     tid_at[rootpix[t]] = t;
-    tree_size[t] = uf_size[root_of[rootpix[t]]];
+    tree_size[t] = uf_size[FHC_I * root_of[rootpix[t]]];
 }
 __global__ void k_label_ids2(int N, const int* __restrict__ root_of, const int* __restrict__ minpix,
                              const int* __restrict__ tid_at, int* tree_id) {
@@ -805,7 +821,7 @@ int s3_forest_pre(s3dmst_ctx* ctx, int mask) {
         View& V = ctx->v[view];
         V.forest_ready = false;
         S3_TRY(s3_image_stage(ctx, view));
-        k_uf_init<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.uf_parent, V.uf_size, V.uf_lastw, V.uf_pick[0], V.uf_pick[1], V.uf_resv, V.minpix);
+        k_uf_init<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, reinterpret_cast<FHComp*>(V.uf_comp), V.uf_parent, V.uf_resv, V.minpix);
         S3_LAUNCH_CHECK();
         S3_CUDA(cudaMemsetAsync(V.counters, 0, sizeof(int) * S3_MAX_ROUNDS, ctx->stream));
         S3_CUDA(cudaMemsetAsync(V.mask, 0, 2 * (size_t)N, ctx->stream));
@@ -851,7 +867,7 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
         std::sort(rootpix[view].begin(), rootpix[view].end());  // tree ids = first-seen raster order = by minimum pixel
         S3_CUDA(cudaMemcpyAsync(V.tree_rootpix, rootpix[view].data(), sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
         int* tid_at = V.pixel_node;  // scratch until BFS fills it: [N]
-        k_label_sizes<<<(T + TB - 1) / TB, TB, 0, ctx->stream>>>(T, V.tree_rootpix, V.scan_tmp, V.uf_size, tid_at, V.tree_size);
+        k_label_sizes<<<(T + TB - 1) / TB, TB, 0, ctx->stream>>>(T, V.tree_rootpix, V.scan_tmp, &reinterpret_cast<FHComp*>(V.uf_comp)->size, tid_at, V.tree_size);
         S3_LAUNCH_CHECK();
         k_label_ids2<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.scan_tmp, V.minpix, tid_at, V.tree_id);
         S3_LAUNCH_CHECK();

@@ -35,10 +35,8 @@ struct View {
     float* gray = nullptr;     // [N] s3_gray of the RAW image (cost kernel)
     uint16_t* ew = nullptr;    // [2N] edge weights by canonical id
     // ---- union-find / forest construction
-    int* uf_parent = nullptr;  // [N]
-    int* uf_size = nullptr;    // [N]
-    int* uf_lastw = nullptr;   // [N]
-    unsigned long long* uf_pick[2] = {nullptr, nullptr};  // [N] minimum live edge key per component (FH rounds, by parity)
+    void* uf_comp = nullptr;   // [N] x 32 B component records (forest.cu: FHComp)
+    int* uf_parent = nullptr;  // [N] union-find parents
     void* fh_ent[2] = {nullptr, nullptr};                 // [2N] x 16 B live-edge lists of the FH rounds (ping-pong)
     unsigned long long* uf_resv = nullptr;  // [N] merge reservation key
     uint8_t* mask = nullptr;   // [2N] 0/1/2
