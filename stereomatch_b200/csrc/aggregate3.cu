@@ -52,6 +52,7 @@ struct Agg3View {
     const int* tree_start;
     const NodeUp* node_up;
     const int4* node_dn;
+    const int* node_pixel;
     const float* cost;
     double* aup;
     int32_t* disp;    // pixel order: final results when the launch has one slice
@@ -68,7 +69,14 @@ struct Agg3Args {
     const void* lut_w;   // exp(-w*gamma) and 1 - w*w tables in the state type
     const void* lut_w2;
     int keep;
-    int sleep_ns;       // back-off of a waiting warp between two polls
+    int sleep_ns;
+    // proposal mode (PMS = true): labels are 3D planes tested on whole trees (MSTCostAggregationAndLabelUpdate, :160-186)
+    const int* prop_off;   // [T+1] proposals of tree t: [prop_off[t], prop_off[t+1]) of `labels`, in list order
+    const float* labels;   // [n][3] (a, b, c)
+    double* min_cost;      // [N] pixel order
+    float* abc;            // [N][3] pixel order
+    int img_w, D;          // image width, labels of the cost rows
+    float oob;             // label cost outside [0, D)       // back-off of a waiting warp between two polls
 };
 
 __device__ __forceinline__ uint32_t a3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -176,7 +184,10 @@ template <> struct A3T<float> {
 
 // FULL: every lane's label pairs are real labels in every half (no per-lane predication in the loops)
 // BIG: 32 warps per tree, one CTA per SM (the biggest trees: enough warps that a level's nodes do not need every warp)
-template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR>
+// PMS: the "labels" of a pass are up to 64 injected proposals of the tree (two per lane); the cost of (node, proposal)
+// is compute3DLabelCost on the node's cost row; the epilogue is the label update instead of the WTA; a tree with more
+// than 64 proposals runs its passes once per batch of 64, in list order.
+template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS>
 __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3Args A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     using TT = A3T<T>;
@@ -190,12 +201,13 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 
     const int4 unit = A.units[A.unit0 + blockIdx.x];
     const Agg3View V = A.views[unit.x];
-    const int t = unit.y, l0 = unit.z, slice = unit.w;
+    const int t = unit.y, slice = unit.w;
     const int base = V.tree_start[t], end = V.tree_start[t + 1], top = end - 1;
-    const size_t Dp = (size_t)A.Dp;
-    bool act[NH];
-#pragma unroll
-    for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;  // the lane's pair holds at least one real label
+    const size_t Dp = (size_t)A.Dp;                 // cost row length
+    const size_t DA = PMS ? (size_t)64 : Dp;        // running-sum row length (proposal mode: a [node][64] scratch)
+    __shared__ float s_lab[PMS ? 64 * 3 : 1];
+    const int p_lo = PMS ? A.prop_off[t] : 0, p_hi = PMS ? A.prop_off[t + 1] : 1;
+    const int lim = PMS ? p_hi : A.d1;              // first label / proposal index that does not exist
 
     for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
         s_w[i] = reinterpret_cast<const T*>(A.lut_w)[i];
@@ -208,16 +220,40 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     const uint32_t ring_a = a3_smem(s_ring) + (uint32_t)sizeof(T2) * lane;  // this lane's column of the ring
     const uint32_t w_a = a3_smem(s_w);
     constexpr uint32_t ROWB = NH * HB;                      // bytes of one ring row
-    const long long strideC = (long long)W * (long long)Dp * 4, strideA = (long long)W * (long long)Dp * (long long)sizeof(T);  // bytes between a warp's consecutive rows
+    const long long strideC = (long long)W * (long long)Dp * 4, strideA = (long long)W * (long long)(PMS ? 64 : A.Dp) * (long long)sizeof(T);  // bytes between a warp's consecutive rows
     T* const aupT = reinterpret_cast<T*>(V.aup);  // running sums in the state type (the buffer is sized for doubles)
+
+    for (int b0 = p_lo; b0 < p_hi; b0 += 64) {  // dense mode: one trip
+    const int l0 = PMS ? b0 : unit.z;   // first label (dense) / proposal (PMS) of this pass
+    const int aoff = PMS ? 0 : l0;      // column of l0 in the running-sum rows
+    bool act[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < lim;  // the lane's pair holds at least one real label
+    if (PMS) {
+        __syncthreads();  // the previous batch is done with s_lab, the ring and the progress words
+        for (int i = tid; i < 3 * min(64, p_hi - b0); i += blockDim.x) s_lab[i] = A.labels[3 * (size_t)b0 + i];
+        if (tid < 32) s_prog[tid] = end;
+        __syncthreads();
+    }
+    // proposal mode: cost of this lane's two proposals at node vv (compute3DLabelCost, :103-118)
+    auto pms_cost = [&](int vv) -> float2 {
+        const int pix = V.node_pixel[vv];
+        const int x = pix % A.img_w, y = pix / A.img_w;
+        const float* row = V.cost + (size_t)vv * Dp;
+        const int k = 2 * lane;
+        float2 c = make_float2(0.f, 0.f);
+        if (b0 + k < p_hi) c.x = s3_label_cost(row, s_lab[3 * k], s_lab[3 * k + 1], s_lab[3 * k + 2], x, y, A.D, A.oob);
+        if (b0 + k + 1 < p_hi) c.y = s3_label_cost(row, s_lab[3 * k + 3], s_lab[3 * k + 4], s_lab[3 * k + 5], x, y, A.D, A.oob);
+        return c;
+    };
 
     // ================================================================== leaf -> root
     {
         int v = top - w;
         const char* nup_p = reinterpret_cast<const char*>(V.node_up + v);
-        const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + l0 + 2 * lane);
-        char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * Dp + l0 + 2 * lane);
-        const char* aup_lane0 = reinterpret_cast<const char*>(aupT + l0 + 2 * lane);  // + c * Dp * 8 for a far child
+        const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + (PMS ? 0 : l0 + 2 * lane));
+        char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * DA + aoff + 2 * lane);
+        const char* aup_lane0 = reinterpret_cast<const char*>(aupT + aoff + 2 * lane);  // + c * DA * sizeof(T) for a far child
         // the node's record and cost row live in these registers from the end of the previous iteration (the loads are
         // issued right after the previous publish, so they are in flight during this warp's wait for the children)
         int4 nu = make_int4(0, 0, 0, 0);  // {child_begin, child_count, cw01, cw23}
@@ -226,9 +262,12 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         for (int h = 0; h < NH; h++) cf[h] = make_float2(0.f, 0.f);
         if (v >= base) {
             nu = *reinterpret_cast<const int4*>(nup_p);
+            if constexpr (PMS) cf[0] = pms_cost(v);
+            else {
 #pragma unroll
-            for (int h = 0; h < NH; h++)
-                if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
+            }
         } else if (lane == 0)
             a3_st_release(prog_a + 4u * w, base);  // a warp without nodes never holds anybody back
         int guard_ok = top + 1;  // writing ring row v is known to be safe for every v >= guard_ok
@@ -258,7 +297,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             const uint32_t ra = ring_a + (uint32_t)(c & (A3_R - 1)) * ROWB;                                          \
             _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = TT::lds2(ra + h * HB);                          \
         } else {                                                                                                     \
-            const char* gp = aup_lane0 + (size_t)c * Dp * sizeof(T);                                                         \
+            const char* gp = aup_lane0 + (size_t)c * DA * sizeof(T);                                                         \
             _Pragma("unroll") for (int h = 0; h < NH; h++)                                                           \
                 cv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2(); \
         }                                                                                                            \
@@ -311,13 +350,16 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             const bool store_late = !far_parent;
             if (vn >= base) {  // next node of this warp: record and cost row
                 nu = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
+                if constexpr (PMS) cf[0] = pms_cost(vn);
+                else {
 #pragma unroll
-                for (int h = 0; h < NH; h++)
-                    if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
+                    for (int h = 0; h < NH; h++)
+                        if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
+                }
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
-            if (lane < NH * 2 && v - A3_PF * W >= base)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - 2 * lane * 4 - A3_PF * strideC + lane * 128));
+            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * W >= base)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - (PMS ? 0 : 2 * lane * 4) - A3_PF * strideC + lane * 128));
             if (store_late) {  // read back on the way down
 #pragma unroll
                 for (int h = 0; h < NH; h++)
@@ -341,8 +383,8 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     {
         int v = base + w;
         const char* ndn_p = reinterpret_cast<const char*>(V.node_dn + v);
-        char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * Dp + l0 + 2 * lane);
-        const char* aup_lane0 = reinterpret_cast<const char*>(aupT + l0 + 2 * lane);
+        char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * DA + aoff + 2 * lane);
+        const char* aup_lane0 = reinterpret_cast<const char*>(aupT + aoff + 2 * lane);
         int4 nd = make_int4(0, 0, 0, 0);  // {parent, parent weight, level | flags, pixel}
         T2 au[NH];
 #pragma unroll
@@ -362,12 +404,22 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #pragma unroll
             for (int h = 0; h < NH; h++) {
                 const int lab = l0 + h * 64 + 2 * lane;
-                if ((FULL || lab < A.d1) && f[h].x < bc) { bc = f[h].x; bd = lab; }
-                if ((FULL || lab + 1 < A.d1) && f[h].y < bc) { bc = f[h].y; bd = lab + 1; }
+                if ((FULL || lab < lim) && f[h].x < bc) { bc = f[h].x; bd = lab; }
+                if ((FULL || lab + 1 < lim) && f[h].y < bc) { bc = f[h].y; bd = lab + 1; }
             }
             double mc;
             const unsigned md = TT::warp_argmin(bc, bd, mc);
-            if (lane == 0) {
+            if (PMS) {
+                // label update (:173-185): proposals in list order, strict '<' == the first proposal attaining the minimum, if
+                // it beats what the pixel holds (batches run in list order too)
+                if (lane == 0 && md != 0x7fffffffu && mc < A.min_cost[pix]) {
+                    A.min_cost[pix] = mc;
+                    const float* l = s_lab + 3 * ((int)md - b0);
+                    A.abc[3 * (size_t)pix] = l[0];
+                    A.abc[3 * (size_t)pix + 1] = l[1];
+                    A.abc[3 * (size_t)pix + 2] = l[2];
+                }
+            } else if (lane == 0) {
                 if (A.n_slices == 1) {
                     V.disp[pix] = (int)md;
                     V.best[pix] = mc;
@@ -397,7 +449,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #pragma unroll
                     for (int h = 0; h < NH; h++) pv[h] = TT::lds2(ra + h * HB);
                 } else {
-                    const char* gp = aup_lane0 + (size_t)p * Dp * sizeof(T);
+                    const char* gp = aup_lane0 + (size_t)p * DA * sizeof(T);
 #pragma unroll
                     for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2();
                 }
@@ -410,7 +462,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #pragma unroll
                 for (int h = 0; h < NH; h++) fin[h] = au[h];  // the root keeps its leaf->root sum
             }
-            if ((nd.z & S3_ND_FAR) || A.keep) {  // children further than NEAR read the final value from L2
+            if ((nd.z & S3_ND_FAR) || (!PMS && A.keep)) {  // children further than NEAR read the final value from L2
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = fin[h];
@@ -448,6 +500,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             v = vn;
         }
     }
+    }  // batches of 64 proposals
 }
 
 static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
@@ -538,7 +591,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         for (int view = 0; view < 2; view++) {
             View& V = cx->v[view];
             Agg3View& G = table[2 * c + view];
-            G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn;
+            G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
             G.cost = V.cost; G.aup = V.aup;
             G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
         }
@@ -581,8 +634,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
 #define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                           \
     do {                                                                                                                       \
         const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(T_));                                                              \
-        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_><<<GRID_, THREADS_, smem, ctx->stream>>>(A);                                \
+        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false><<<GRID_, THREADS_, smem, ctx->stream>>>(A);                         \
         S3_LAUNCH_CHECK();                                                                                                     \
     } while (0)
 #define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                                 \
@@ -638,3 +691,64 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
 }
 
 int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) { return s3_aggregate_flow_multi(&ctx, 1, views_mask, d0, d1); }
+
+// Proposal mode of the dataflow kernel: evaluates a tree-grouped proposal list (labels_dev [n][3] grouped by tree, order
+// inside a tree preserved; prop_off_dev [T+1]; h_prop_off = the same offsets on the host) on one view.  scratch_dev:
+// N * 64 doubles.  Returns 1 if it cannot serve the request (the caller then uses the simple kernel).
+int s3_pms_apply_flow(s3dmst_ctx* ctx, int view, const int* h_prop_off, const int* prop_off_dev, const float* labels_dev, double* scratch_dev) {
+    View& V = ctx->v[view];
+    if (!ctx->P.exact) return 1;  // proposals are always evaluated in the reference's arithmetic
+    std::vector<std::pair<int, int4>> u;
+    for (int t = 0; t < V.T; t++)
+        if (h_prop_off[t + 1] > h_prop_off[t]) u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(0, t, 0, 0)});
+    if (u.empty()) return 0;
+    std::stable_sort(u.begin(), u.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    std::vector<int4> units(u.size());
+    for (size_t i = 0; i < u.size(); i++) units[i] = u[i].second;
+    Agg3View G;
+    memset(&G, 0, sizeof G);
+    G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
+    G.cost = V.cost; G.aup = scratch_dev;
+    const size_t ubytes = units.size() * sizeof(int4), tbytes = (sizeof(Agg3View) + 15) / 16 * 16;
+    if (ctx->units_cap < ubytes + tbytes) {
+        if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
+        ctx->units_dev = nullptr; ctx->units_cap = 0;
+        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes + tbytes));
+        ctx->units_cap = ubytes + tbytes;
+    }
+    char* ubase = reinterpret_cast<char*>(ctx->units_dev);
+    S3_CUDA(cudaMemcpyAsync(ubase, &G, sizeof G, cudaMemcpyHostToDevice, ctx->stream));
+    S3_CUDA(cudaMemcpyAsync(ubase + tbytes, units.data(), ubytes, cudaMemcpyHostToDevice, ctx->stream));
+    Agg3Args A;
+    memset(&A, 0, sizeof A);
+    A.views = reinterpret_cast<const Agg3View*>(ubase);
+    A.units = reinterpret_cast<const int4*>(ubase + tbytes);
+    A.Dp = V.Dp; A.d1 = 0; A.N = ctx->N; A.n_slices = 1;
+    A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
+    A.keep = 0;
+    A.sleep_ns = 20;
+    A.prop_off = prop_off_dev; A.labels = labels_dev; A.min_cost = V.min_cost; A.abc = V.abc;
+    A.img_w = ctx->W; A.D = V.D; A.oob = ctx->P.oob_cost;
+    static const int big_nodes = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
+    int n_big = 0;
+    while (n_big < (int)u.size() && u[n_big].first >= big_nodes) n_big++;
+    const int n_small = (int)u.size() - n_big;
+    S3_EV_BEGIN(S3DMST_T_PMS, view);
+    if (n_big) {
+        const size_t smem = agg3_smem_bytes(1, 256, sizeof(double));
+        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<double, 1, false, true, 256, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        A.unit0 = 0;
+        k_agg_flow<double, 1, false, true, 256, 64, true><<<n_big, 1024, smem, ctx->stream>>>(A);
+        S3_LAUNCH_CHECK();
+    }
+    if (n_small) {
+        const size_t smem = agg3_smem_bytes(1, 128, sizeof(double));
+        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<double, 1, false, false, 128, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        A.unit0 = n_big;
+        k_agg_flow<double, 1, false, false, 128, 32, true><<<n_small, 512, smem, ctx->stream>>>(A);
+        S3_LAUNCH_CHECK();
+    }
+    S3_EV_END(S3DMST_T_PMS, view);
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging (units) is read by the async copy above
+    return 0;
+}

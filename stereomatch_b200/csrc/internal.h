@@ -169,6 +169,7 @@ int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
 int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined, level-synchronous tiles)
 int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1);    // aggregate3.cu (dataflow, default)
+int s3_pms_apply_flow(s3dmst_ctx* ctx, int view, const int* h_prop_off, const int* prop_off_dev, const float* labels_dev, double* scratch_dev);
 int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1);  // one launch over several frames
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
 int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax);          // pms.cu: the reference's random plane initialisation

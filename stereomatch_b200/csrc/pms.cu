@@ -150,11 +150,12 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
             lab[3 * (size_t)pos + 2] = h_labels[3 * i + 2];
         }
     }
-    const size_t scr_bytes = (size_t)ctx->N * PMS_KB * sizeof(double);
+    const size_t scr_bytes = (size_t)ctx->N * 64 * sizeof(double);  // [node][64] (dataflow kernel) / [node][PMS_KB] (simple kernel)
     const size_t lab_bytes = (3 * n * sizeof(float) + 255) / 256 * 256;
     const size_t off_bytes = ((T + 1) * sizeof(int) + 255) / 256 * 256;
-    const size_t need = scr_bytes + lab_bytes + off_bytes;
-    if (ctx->pms_scratch_cap < need) {
+    const size_t lab_cap = std::max<size_t>(lab_bytes, 1 << 20) * 2;  // head-room: the proposal count changes from round to round
+    const size_t need = scr_bytes + lab_cap + off_bytes;
+    if (ctx->pms_scratch_cap < scr_bytes + lab_bytes + off_bytes) {
         if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
         ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
         S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
@@ -163,10 +164,15 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
     char* basep = (char*)ctx->pms_scratch;
     double* scr = (double*)basep;
     float* d_lab = (float*)(basep + scr_bytes);
-    int* d_off = (int*)(basep + scr_bytes + lab_bytes);
+    int* d_off = (int*)(basep + ctx->pms_scratch_cap - off_bytes);
     S3_CUDA(cudaMemcpyAsync(d_lab, lab.data(), 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     S3_CUDA(cudaMemcpyAsync(d_off, off.data(), (T + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 
+    static const bool simple = getenv("S3_PMS_SIMPLE") && atoi(getenv("S3_PMS_SIMPLE")) != 0;
+    if (!simple) {
+        const int r = s3_pms_apply_flow(ctx, view, off.data(), d_off, d_lab, scr);
+        if (r != 1) return r;
+    }
     PmsArgs A;
     A.W = ctx->W; A.D = V.D; A.Dp = V.Dp; A.oob = ctx->P.oob_cost;
     A.unit_tree = V.unit_tree; A.tree_start = V.tree_start; A.tree_depth = V.tree_depth; A.lvl_start = V.lvl_start;
