@@ -596,6 +596,10 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
     // forest + cost volume per frame: independent streams, one host thread each (the forest stage reads tree counts back)
     const bool dbg = getenv("S3_DEBUG_BATCH") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    if (dbg)
+        for (int c = 0; c < n; c++)
+            for (int i = 0; i < 8; i++)
+                if (!ctxs[c]->dbg_ev[i]) cudaEventCreate(&ctxs[c]->dbg_ev[i]);
     const double t_begin = now();
     std::vector<double> t_forest(n, 0.0);
     static const bool joint_fh = getenv("S3_FH_JOINT") && atoi(getenv("S3_FH_JOINT")) != 0;
@@ -615,6 +619,7 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
             S3_EV_END(S3DMST_T_FOREST, 0);
             if (dbg) { cudaStreamSynchronize(ctx->stream); t_forest[c] = now(); }
             S3_TRY(s3_cost_adgrad(ctx, D, 0));
+            if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[5], ctx->stream);
             if (dbg) cudaStreamSynchronize(ctx->stream);
             return 0;
         }();
@@ -675,6 +680,13 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
     if (dbg) {
         double tf = 0.0;
         for (int c = 0; c < n; c++) tf = std::max(tf, t_forest[c]);
+        for (int c = 0; c < n && (phases & 1); c++) {
+            float t[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], ctxs[0]->dbg_ev[0], ctxs[c]->dbg_ev[i]);
+            float t0 = 0;
+            cudaEventElapsedTime(&t0, ctxs[0]->dbg_ev[0], ctxs[c]->dbg_ev[0]);
+            fprintf(stderr, "  frame %d: start %.2f | image %.2f | FH %.2f | labels %.2f | BFS %.2f | cost %.2f (ms since frame 0 started)\n", c, t0, t[1], t[2], t[3], t[4], t[5]);
+        }
         fprintf(stderr, "[batch %d] forests done +%.2f ms, cost volumes done +%.2f ms, total %.2f ms\n", n, tf - t_begin, t_front - t_begin, now() - t_begin);
     }
     return 0;

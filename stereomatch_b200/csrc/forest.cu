@@ -174,7 +174,7 @@ __device__ __forceinline__ void fh_grid_bar(unsigned* bar, unsigned& target, uns
 // 4-8 byte accesses: the kernel is bound by L2 sector throughput and by the two barriers per round, so it wants
 // every GPC's L2 ports, not one cluster's).  Every CTA keeps its OWN segment of the live list (survivors stay with
 // the CTA that looked at them, new levels are dealt out evenly), so compaction needs no global cursor.
-__global__ void __launch_bounds__(1024) k_fh_merge(FHArgs2 AA) {
+__global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
     const int nblk_all = gridDim.x;
     const int per_view = nblk_all / AA.nviews;
     const int vi = min((int)blockIdx.x / per_view, AA.nviews - 1);
@@ -460,7 +460,7 @@ __global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const u
 }
 
 // ---- BFS re-indexing, one CTA per tree
-#define BFS_THREADS 256
+#define BFS_THREADS 64
 #ifndef BFS_INSTR
 #define BFS_INSTR 0
 #endif
@@ -469,7 +469,7 @@ __global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const u
 #else
 #define BFS_CLK(acc) do { } while (0)
 #endif
-#define BFS_FRONT 2048  // frontier entries kept in shared memory per level (wider levels go through global memory)
+#define BFS_FRONT 512   // frontier entries kept in shared memory per level (wider levels go through global memory)
 struct BfsArgs {
     int T;
     const int* unit_tree;
@@ -875,6 +875,7 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
         S3_CUDA(cudaMemcpyAsync(tsize[view].data(), V.tree_size, sizeof(int) * T, cudaMemcpyDeviceToHost, ctx->stream));
     }
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[3], ctx->stream);
     BfsArgs2 BA;
     memset(&BA, 0, sizeof BA);
     BA.W = W; BA.H = H; BA.NN = N;
@@ -897,7 +898,7 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
         B.node_pixel = V.node_pixel; B.pixel_node = V.pixel_node; B.parent = V.parent; B.level = V.level; B.pw = V.pw;
         B.node_up = V.node_up; B.node_dn = V.node_dn; B.lvl_start = V.lvl_start; B.tree_depth = V.tree_depth;
         B.tile_desc = V.tile_desc; B.tree_ntiles = V.tree_ntiles;
-        const int g = std::min(T, ctx->num_sms * 8);
+        const int g = std::min(T, ctx->num_sms * 16);
         if (nv == 0) BA.grid0 = g;
         grid += g;
         nv++;
@@ -917,6 +918,7 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
             k_bfs_unpack<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_dn, V.node_pixel, V.parent, V.level, V.pw, V.leaf_bits);
             S3_LAUNCH_CHECK();
         }
+    if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[4], ctx->stream);
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) {
             View& V = ctx->v[view];
@@ -942,9 +944,13 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
     return 0;
 }
 
+#define S3_DBG_MARK(i) do { if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[i], ctx->stream); } while (0)
 int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
+    S3_DBG_MARK(0);
     S3_TRY(s3_forest_pre(ctx, mask));
+    S3_DBG_MARK(1);
     S3_TRY(s3_fh_launch(ctx, mask));
+    S3_DBG_MARK(2);
     return s3_forest_post(ctx, mask);
 }
 

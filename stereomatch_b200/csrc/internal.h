@@ -113,6 +113,7 @@ struct s3dmst_ctx {
     long long launches = 0;
     std::string err;
     // scratch for PMS
+    cudaEvent_t dbg_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // S3_DEBUG_BATCH timeline marks
     cudaEvent_t ev_xctx = nullptr;  // orders this context's stream against another context's in batched launches
     uint32_t* units_dev = nullptr;  // aggregation work units + view table of the current launch
     size_t units_cap = 0;
