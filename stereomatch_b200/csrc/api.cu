@@ -249,7 +249,10 @@ int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth
     View& V = ctx->v[view];
     if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "forest_info: no forest");
     if (num_trees) *num_trees = V.T;
-    if (max_depth) *max_depth = V.max_depth;
+    if (max_depth) {
+        S3_TRY(s3_forest_depths(ctx, view));
+        *max_depth = V.max_depth;
+    }
     if (adj_size) {
         std::vector<int> ap, a;
         S3_TRY(host_adjacency(ctx, view, ap, a));

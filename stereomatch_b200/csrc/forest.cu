@@ -418,11 +418,16 @@ __global__ void k_label_roots(int N, int* parent, int* root_of, int* minpix) {
     root_of[p] = r;
     atomicMin(minpix + r, p);
 }
-__global__ void k_label_firsts(int N, const int* __restrict__ root_of, const int* __restrict__ minpix, int* firsts,
-                               int* counter) {
+__global__ void k_label_firsts(int N, const int* __restrict__ root_of, const int* __restrict__ minpix, const int* __restrict__ uf_size,
+                               int* firsts, int* sizes, int* counter) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
-    if (minpix[root_of[p]] == p) firsts[atomicAdd(counter, 1)] = p;
+    const int r = root_of[p];
+    if (minpix[r] == p) {  // the minimum pixel of its tree: one record (pixel, tree size) per tree, in arrival order
+        const int i = atomicAdd(counter, 1);
+        firsts[i] = p;
+        sizes[i] = uf_size[FHC_I * r];
+    }
 }
 __global__ void k_label_mark(int T, const int* __restrict__ rootpix, int* tid_at, int* tree_size) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -833,18 +838,26 @@ int s3_forest_pre(s3dmst_ctx* ctx, int mask) {
 int s3_forest_post(s3dmst_ctx* ctx, int mask) {
     const int N = ctx->N, W = ctx->W, H = ctx->H;
     const int TB = 256;
+    // ONE host round trip: per tree its minimum pixel and size (unordered), plus the kernel's counters.  A tree has at
+    // least max(2, min_cc_size) pixels unless the whole image is one small component.
+    const int Tmax = std::min(N, N / std::max(2, ctx->P.min_cc_size) + 2);
     int hc[2][16];
+    std::vector<int> rootpix[2], tsize[2];
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
         View& V = ctx->v[view];
         k_label_roots<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.uf_parent, V.scan_tmp, V.minpix);
         S3_LAUNCH_CHECK();
-        k_label_firsts<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.scan_tmp, V.minpix, V.tree_rootpix, V.counters + CNT_FIRSTS);
+        k_label_firsts<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.scan_tmp, V.minpix, &reinterpret_cast<FHComp*>(V.uf_comp)->size, V.tree_rootpix,
+                                                                  V.tree_size, V.counters + CNT_FIRSTS);
         S3_LAUNCH_CHECK();
+        rootpix[view].resize(Tmax);
+        tsize[view].resize(Tmax);
         S3_CUDA(cudaMemcpyAsync(hc[view], V.counters + S3_MAX_ROUNDS - 16, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaMemcpyAsync(rootpix[view].data(), V.tree_rootpix, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaMemcpyAsync(tsize[view].data(), V.tree_size, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
     }
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> rootpix[2];
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
         View& V = ctx->v[view];
@@ -853,28 +866,23 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
             fprintf(stderr, "[fh view %d] fh-rounds %d total-rounds %d visits/thread %d | kcycles phase1 %d phase2 %d sync %d merge %d\n", view, hc[view][6],
                     hc[view][13], hc[view][10], hc[view][8], hc[view][9], hc[view][11], hc[view][5]);
         const int T = hc[view][16 - (S3_MAX_ROUNDS - CNT_FIRSTS)];
-        if (T <= 0 || T > N) return s3_fail(ctx, S3DMST_E_CUDA, "labelling produced T=%d", T);
+        if (T <= 0 || T > Tmax) return s3_fail(ctx, S3DMST_E_CUDA, "labelling produced T=%d (bound %d)", T, Tmax);
         V.T = T;
-        rootpix[view].resize(T);
-        S3_CUDA(cudaMemcpyAsync(rootpix[view].data(), V.tree_rootpix, sizeof(int) * T, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> tsize[2];
-    for (int view = 0; view < 2; view++) {
-        if (!(mask & (1 << view))) continue;
-        View& V = ctx->v[view];
-        const int T = V.T;
-        std::sort(rootpix[view].begin(), rootpix[view].end());  // tree ids = first-seen raster order = by minimum pixel
+        // tree ids = first-seen raster order = by minimum pixel (Stereo3DMST.cpp:352-367)
+        std::vector<int> ord(T);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::sort(ord.begin(), ord.end(), [&](int a, int b) { return rootpix[view][a] < rootpix[view][b]; });
+        std::vector<int> rp(T), ts(T);
+        for (int t = 0; t < T; t++) { rp[t] = rootpix[view][ord[t]]; ts[t] = tsize[view][ord[t]]; }
+        rootpix[view].swap(rp);
+        tsize[view].swap(ts);
         S3_CUDA(cudaMemcpyAsync(V.tree_rootpix, rootpix[view].data(), sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
         int* tid_at = V.pixel_node;  // scratch until BFS fills it: [N]
         k_label_sizes<<<(T + TB - 1) / TB, TB, 0, ctx->stream>>>(T, V.tree_rootpix, V.scan_tmp, &reinterpret_cast<FHComp*>(V.uf_comp)->size, tid_at, V.tree_size);
         S3_LAUNCH_CHECK();
         k_label_ids2<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.scan_tmp, V.minpix, tid_at, V.tree_id);
         S3_LAUNCH_CHECK();
-        tsize[view].resize(T);
-        S3_CUDA(cudaMemcpyAsync(tsize[view].data(), V.tree_size, sizeof(int) * T, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[3], ctx->stream);
     BfsArgs2 BA;
     memset(&BA, 0, sizeof BA);
@@ -919,24 +927,22 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
             S3_LAUNCH_CHECK();
         }
     if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[4], ctx->stream);
-    for (int view = 0; view < 2; view++)
-        if (mask & (1 << view)) {
-            View& V = ctx->v[view];
-            V.h_tree_depth.resize(V.T);
-            S3_CUDA(cudaMemcpyAsync(V.h_tree_depth.data(), V.tree_depth, sizeof(int) * V.T, cudaMemcpyDeviceToHost, ctx->stream));
-            if (getenv("S3_DEBUG_FH")) {
+    if (getenv("S3_DEBUG_FH")) {
+        for (int view = 0; view < 2; view++)
+            if (mask & (1 << view)) {
+                View& V = ctx->v[view];
                 int d[4];
                 S3_CUDA(cudaMemcpy(d, V.counters + S3_MAX_ROUNDS - 30, sizeof d, cudaMemcpyDeviceToHost));
                 fprintf(stderr, "[bfs view %d] largest tree: %d nodes, %d levels, bfs %d kcycles (%.0f cycles/level), tiles %d kcycles\n", view, d[3], d[2], d[0] >> 6,
                         16.0 * d[0] / std::max(1, d[2]), d[1] >> 6);
             }
-        }
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    // (the host-side staging vectors above are pageable: an asynchronous H2D copy from pageable memory returns once the
+    // data is staged, so nothing here has to outlive this function)
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) {
             View& V = ctx->v[view];
-            V.max_depth = 0;
-            for (int d : V.h_tree_depth) V.max_depth = std::max(V.max_depth, d);
+            V.max_depth = -1;  // tree depths stay on the device until somebody asks (s3_forest_finalize_host)
             V.forest_ready = true;
             V.cost_ready = false;
             V.agg_ready = false;
@@ -955,6 +961,18 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
 }
 
 int s3_forest_stage(s3dmst_ctx* ctx, int view) { return s3_forest_stage_mask(ctx, 1 << view); }
+
+// tree depths -> host (forest_info / parity dumps); the pipeline itself never needs them on the host
+int s3_forest_depths(s3dmst_ctx* ctx, int view) {
+    View& V = ctx->v[view];
+    if (V.max_depth >= 0) return 0;
+    V.h_tree_depth.resize(V.T);
+    S3_CUDA(cudaMemcpyAsync(V.h_tree_depth.data(), V.tree_depth, sizeof(int) * V.T, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    V.max_depth = 0;
+    for (int d : V.h_tree_depth) V.max_depth = std::max(V.max_depth, d);
+    return 0;
+}
 
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view) {
     View& V = ctx->v[view];

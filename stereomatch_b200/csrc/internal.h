@@ -163,7 +163,8 @@ int s3_fh_launch(s3dmst_ctx* ctx, int mask);
 int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask);   // one launch over several frames
 int s3_forest_pre(s3dmst_ctx* ctx, int mask);                     // image stage + union-find init (async)
 int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (host-synchronous)
-int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);           // forest.cu: unit order, depths
+int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);
+int s3_forest_depths(s3dmst_ctx* ctx, int view);                  // forest.cu: lazy D2H of the tree depths           // forest.cu: unit order, depths
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
