@@ -73,6 +73,11 @@ int s3dmst_sync(s3dmst_ctx* ctx);
 int s3dmst_set_images(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H,
                       int stride_bytes);
 
+/* The same without the final synchronisation: the copies are queued on the context's stream (truly asynchronous from
+ * pinned host memory) and the buffers must stay untouched until the next synchronising call on the context
+ * (e.g. s3dmst_run_dense* with output pointers, s3dmst_sync).  Lets a batch overlap its uploads with compute. */
+int s3dmst_set_images_async(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride_bytes);
+
 /* a3,a4,a5,a7 (Stereo3DMST.cpp:226-307, :342-384, :434-522; segment-graph.h:54-89): median, edge
  * weights, FH forest (level-synchronous Boruvka), min-size merge, tree ids, BFS re-indexing. */
 int s3dmst_build_forest(s3dmst_ctx* ctx, int view);

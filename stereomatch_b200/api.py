@@ -38,7 +38,7 @@ class S3Params(C.Structure):
 
 # every symbol include/s3dmst.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
-    "s3dmst_default_params", "s3dmst_create", "s3dmst_destroy", "s3dmst_last_error", "s3dmst_sync", "s3dmst_set_images",
+    "s3dmst_default_params", "s3dmst_create", "s3dmst_destroy", "s3dmst_last_error", "s3dmst_sync", "s3dmst_set_images", "s3dmst_set_images_async",
     "s3dmst_build_forest", "s3dmst_forest_info", "s3dmst_get_forest", "s3dmst_set_forest", "s3dmst_build_cost_volume",
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
@@ -65,6 +65,7 @@ def load_library():
     L.s3dmst_last_error.restype = C.c_char_p
     L.s3dmst_sync.argtypes = [c_p]
     L.s3dmst_set_images.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int]
+    L.s3dmst_set_images_async.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int]
     L.s3dmst_build_forest.argtypes = [c_p, C.c_int]
     L.s3dmst_forest_info.argtypes = [c_p, C.c_int, c_p, c_p, c_p]
     L.s3dmst_get_forest.argtypes = [c_p, C.c_int] + [c_p] * 12
@@ -152,14 +153,19 @@ class Stereo3DMST:
             raise S3Error(f"s3dmst error {rc}: {self.L.s3dmst_last_error(self.h).decode()}")
 
     # -- inputs -------------------------------------------------------------------------------------
-    def set_images(self, left_bgr, right_bgr):
+    def set_images(self, left_bgr, right_bgr, sync=True):
+        """sync=False: s3dmst_set_images_async — the arrays (pinned for a truly asynchronous copy) must stay alive and
+        untouched until the next synchronising call on this handle."""
         left_bgr = np.ascontiguousarray(left_bgr, np.uint8)
         right_bgr = np.ascontiguousarray(right_bgr, np.uint8)
         if left_bgr.ndim != 3 or left_bgr.shape[2] != 3 or left_bgr.shape != right_bgr.shape:
             raise ValueError("images must be two HxWx3 uint8 BGR arrays of the same size")
         self.H, self.W = left_bgr.shape[:2]
         self.N = self.W * self.H
-        self._ck(self.L.s3dmst_set_images(self.h, _ptr(left_bgr), _ptr(right_bgr), self.W, self.H, 3 * self.W))
+        fn = self.L.s3dmst_set_images if sync else self.L.s3dmst_set_images_async
+        self._ck(fn(self.h, _ptr(left_bgr), _ptr(right_bgr), self.W, self.H, 3 * self.W))
+        if not sync:
+            self._keep = (left_bgr, right_bgr)
 
     # -- forest -------------------------------------------------------------------------------------
     def build_forest(self, view):

@@ -195,7 +195,14 @@ double s3dmst_stage_ms(s3dmst_ctx* ctx, int stage) {
     return total;
 }
 
+static int set_images_impl(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride, bool sync);
 int s3dmst_set_images(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride) {
+    return set_images_impl(ctx, left_bgr, right_bgr, W, H, stride, true);
+}
+int s3dmst_set_images_async(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride) {
+    return set_images_impl(ctx, left_bgr, right_bgr, W, H, stride, false);
+}
+static int set_images_impl(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride, bool sync) {
     if (!left_bgr || !right_bgr || stride < 3 * W) return s3_fail(ctx, S3DMST_E_ARG, "set_images: bad pointers/stride");
     S3_CUDA(cudaSetDevice(ctx->device));
     S3_TRY(set_size(ctx, W, H));
@@ -205,7 +212,7 @@ int s3dmst_set_images(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* r
                                   ctx->stream));
         ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
     }
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
+    if (sync) S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
     return 0;
 }
 
