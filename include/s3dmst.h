@@ -57,8 +57,10 @@ typedef struct s3dmst_params {
     int agg_cache_nodes;/* 0 = auto; nodes of a tree level cached in shared memory per CTA          */
     int agg_ring_nodes; /* 0 = auto; node rows staged ahead per CTA by the bulk-copy (TMA) pipeline      */
     int agg_kernel;     /* 0 = auto (dataflow kernel), 1 = simple level-synchronous kernel, 2 = TMA tile kernel */
-    int fh_ctas;        /* 0 = one CTA per SM (one pair alone on the GPU); > 0: CTAs of the cooperative forest kernel per frame, for contexts that run beside others in a batch (also selects the narrower live-edge band, see forest.cu fill_fh_args) */
-    int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel (batches: 256, so that several frames' kernels share the SMs) */
+    int fh_ctas;        /* 0 = one CTA per SM (one pair alone on the GPU); > 0: CTAs of the cooperative forest kernel per
+                           frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
+                           frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
+    int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel */
 } s3dmst_params;
 
 void s3dmst_default_params(s3dmst_params* p);
