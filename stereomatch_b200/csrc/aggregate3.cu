@@ -679,7 +679,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         S3_CUDA(cudaEventRecord(ctx->ev_xctx, ctx->stream));
         for (int c = 1; c < nctx; c++) S3_CUDA(cudaStreamWaitEvent(ctxs[c]->stream, ctx->ev_xctx, 0));
     }
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host staging vectors are read by the async copies above
+    // No host synchronisation: the staging vectors above are pageable, so the asynchronous copies returned once their
+    // contents were staged; the callers queue the post-processing behind this launch while it runs.
     for (int c = 0; c < nctx; c++)
         for (int view = 0; view < 2; view++)
             if (views_mask & (1 << view)) {
