@@ -80,6 +80,23 @@ int s3dmst_set_images(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* r
  * (e.g. s3dmst_run_dense* with output pointers, s3dmst_sync).  Lets a batch overlap its uploads with compute. */
 int s3dmst_set_images_async(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int stride_bytes);
 
+/* Rectification front-end: the caller's per-frame cv::remap(img, imgr, map1, map2, INTER_LINEAR) of
+ * src/stereo_Yin.cpp:143-144 on the device.  map_xy / map_fxy are the CV_16SC2 / CV_16UC1 pair that
+ * initUndistortRectifyMap(..., CV_16SC2, map1, map2) returns (:139-140): int16 [H][W][2] source corner (x, y) and
+ * uint16 [H][W] fraction index fy*32+fx.  Uploaded once per camera and kept on the device; W x H is the rectified size. */
+int s3dmst_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const uint16_t* map_fxy, int W, int H);
+
+/* Raw (unrectified) BGR u8 pair, both src_w x src_h: H2D copy + fixed-point bilinear remap (bit-identical to cv::remap
+ * with INTER_LINEAR, BORDER_CONSTANT 0) straight into the context's images; afterwards as after s3dmst_set_images. */
+int s3dmst_set_raw_images(s3dmst_ctx* ctx, const uint8_t* left_raw_bgr, const uint8_t* right_raw_bgr, int src_w, int src_h,
+                          int stride_bytes);
+
+/* The image of a view as the path sees it (after s3dmst_set_images / s3dmst_set_raw_images): BGR u8, W*H*3 bytes. */
+int s3dmst_get_image(s3dmst_ctx* ctx, int view, uint8_t* bgr);
+
+/* The 1024 x 4 int16 bilinear weight table of the remap (host-side; no device needed): parity dumps. */
+void s3dmst_remap_table(int16_t* tab);
+
 /* a3,a4,a5,a7 (Stereo3DMST.cpp:226-307, :342-384, :434-522; segment-graph.h:54-89): median, edge
  * weights, FH forest (level-synchronous Boruvka), min-size merge, tree ids, BFS re-indexing. */
 int s3dmst_build_forest(s3dmst_ctx* ctx, int view);

@@ -39,6 +39,7 @@ class S3Params(C.Structure):
 # every symbol include/s3dmst.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
     "s3dmst_default_params", "s3dmst_create", "s3dmst_destroy", "s3dmst_last_error", "s3dmst_sync", "s3dmst_set_images", "s3dmst_set_images_async",
+    "s3dmst_set_rectify_maps", "s3dmst_set_raw_images", "s3dmst_get_image", "s3dmst_remap_table",
     "s3dmst_build_forest", "s3dmst_forest_info", "s3dmst_get_forest", "s3dmst_set_forest", "s3dmst_build_cost_volume",
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
@@ -47,6 +48,13 @@ ABI_SYMBOLS = [
 ]
 
 _lib = None
+
+
+def remap_table():
+    """int16 [1024][4]: the fixed-point bilinear weights the device remap uses (host-side call, no GPU needed)."""
+    tab = np.empty((1024, 4), np.int16)
+    load_library().s3dmst_remap_table(tab.ctypes.data_as(c_p))
+    return tab
 
 
 def load_library():
@@ -66,6 +74,11 @@ def load_library():
     L.s3dmst_sync.argtypes = [c_p]
     L.s3dmst_set_images.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int]
     L.s3dmst_set_images_async.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int]
+    L.s3dmst_set_rectify_maps.argtypes = [c_p, C.c_int, c_p, c_p, C.c_int, C.c_int]
+    L.s3dmst_set_raw_images.argtypes = [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int]
+    L.s3dmst_get_image.argtypes = [c_p, C.c_int, c_p]
+    L.s3dmst_remap_table.argtypes = [c_p]
+    L.s3dmst_remap_table.restype = None
     L.s3dmst_build_forest.argtypes = [c_p, C.c_int]
     L.s3dmst_forest_info.argtypes = [c_p, C.c_int, c_p, c_p, c_p]
     L.s3dmst_get_forest.argtypes = [c_p, C.c_int] + [c_p] * 12
@@ -166,6 +179,31 @@ class Stereo3DMST:
         self._ck(fn(self.h, _ptr(left_bgr), _ptr(right_bgr), self.W, self.H, 3 * self.W))
         if not sync:
             self._keep = (left_bgr, right_bgr)
+
+    def set_rectify_maps(self, view, map_xy, map_fxy):
+        """The CV_16SC2 / CV_16UC1 pair of cv2.initUndistortRectifyMap(..., cv2.CV_16SC2) for one view (kept on the device)."""
+        map_xy = np.ascontiguousarray(map_xy, np.int16)
+        map_fxy = np.ascontiguousarray(map_fxy, np.uint16)
+        if map_xy.ndim != 3 or map_xy.shape[2] != 2 or map_fxy.shape != map_xy.shape[:2]:
+            raise ValueError("maps must be int16 HxWx2 and uint16 HxW")
+        self._ck(self.L.s3dmst_set_rectify_maps(self.h, view, _ptr(map_xy), _ptr(map_fxy), map_xy.shape[1], map_xy.shape[0]))
+        self._map_size = (map_xy.shape[1], map_xy.shape[0])
+
+    def set_raw_images(self, left_raw, right_raw):
+        """Unrectified BGR pair -> rectified images on the device (cv2.remap INTER_LINEAR, bit-identical)."""
+        left_raw = np.ascontiguousarray(left_raw, np.uint8)
+        right_raw = np.ascontiguousarray(right_raw, np.uint8)
+        if left_raw.ndim != 3 or left_raw.shape[2] != 3 or left_raw.shape != right_raw.shape:
+            raise ValueError("images must be two HxWx3 uint8 BGR arrays of the same size")
+        sh, sw = left_raw.shape[:2]
+        self._ck(self.L.s3dmst_set_raw_images(self.h, _ptr(left_raw), _ptr(right_raw), sw, sh, 3 * sw))
+        self.W, self.H = self._map_size
+        self.N = self.W * self.H
+
+    def get_image(self, view):
+        out = np.empty((self.H, self.W, 3), np.uint8)
+        self._ck(self.L.s3dmst_get_image(self.h, view, _ptr(out)))
+        return out
 
     # -- forest -------------------------------------------------------------------------------------
     def build_forest(self, view):

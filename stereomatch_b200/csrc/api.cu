@@ -165,6 +165,7 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
+    s3_rectify_free(ctx);
     DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev); DFREE(ctx->fh_sync);
     for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
         if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
@@ -213,6 +214,34 @@ static int set_images_impl(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8
         ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
     }
     if (sync) S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
+    return 0;
+}
+
+void s3dmst_remap_table(int16_t* tab) { s3_remap_table(tab); }
+
+int s3dmst_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const uint16_t* map_fxy, int W, int H) {
+    if (view < 0 || view > 1 || !map_xy || !map_fxy || W < 1 || H < 1) return s3_fail(ctx, S3DMST_E_ARG, "set_rectify_maps: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_set_rectify_maps(ctx, view, map_xy, map_fxy, W, H);
+}
+
+int s3dmst_set_raw_images(s3dmst_ctx* ctx, const uint8_t* left_raw_bgr, const uint8_t* right_raw_bgr, int src_w, int src_h, int stride) {
+    if (!left_raw_bgr || !right_raw_bgr || src_w < 1 || src_h < 1 || stride < 3 * src_w) return s3_fail(ctx, S3DMST_E_ARG, "set_raw_images: bad pointers/stride");
+    if (!ctx->map_xy[0] || !ctx->map_xy[1]) return s3_fail(ctx, S3DMST_E_STATE, "set_raw_images: rectification maps of both views required");
+    if (ctx->map_w[0] != ctx->map_w[1] || ctx->map_h[0] != ctx->map_h[1]) return s3_fail(ctx, S3DMST_E_ARG, "set_raw_images: the two views' maps differ in size");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(set_size(ctx, ctx->map_w[0], ctx->map_h[0]));
+    for (int i = 0; i < 2; i++) ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
+    S3_TRY(s3_remap_raw_pair(ctx, left_raw_bgr, right_raw_bgr, src_w, src_h, stride));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
+    return 0;
+}
+
+int s3dmst_get_image(s3dmst_ctx* ctx, int view, uint8_t* bgr) {
+    if (view < 0 || view > 1 || !bgr || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "get_image: bad view or no images");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_CUDA(cudaMemcpyAsync(bgr, ctx->v[view].bgr, 3 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -120,6 +120,13 @@ struct s3dmst_ctx {
     int* fh_sync = nullptr;         // grid barrier + per-round live counters of the forest kernel
     void* pms_scratch = nullptr;
     size_t pms_scratch_cap = 0;
+    // rectification front-end (rectify.cu): per-view fixed-point maps, the weight table, staging for the raw pair
+    int16_t* map_xy[2] = {nullptr, nullptr};    // [mh][mw][2] integer source corner (x, y)
+    uint16_t* map_fxy[2] = {nullptr, nullptr};  // [mh][mw] fy * 32 + fx
+    int map_w[2] = {0, 0}, map_h[2] = {0, 0};
+    int16_t* remap_tab = nullptr;               // [1024][4] bilinear weights, sum 32768
+    uint8_t* raw_stage = nullptr;               // 2 raw BGR images
+    size_t raw_stage_cap = 0;
 };
 
 #define S3_MAX_ROUNDS 65536
@@ -165,6 +172,10 @@ int s3_forest_pre(s3dmst_ctx* ctx, int mask);                     // image stage
 int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (host-synchronous)
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);
 int s3_forest_depths(s3dmst_ctx* ctx, int view);                  // forest.cu: lazy D2H of the tree depths           // forest.cu: unit order, depths
+int s3_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const uint16_t* map_fxy, int W, int H);  // rectify.cu
+int s3_remap_raw_pair(s3dmst_ctx* ctx, const uint8_t* left_raw, const uint8_t* right_raw, int sw, int sh, int stride);
+void s3_rectify_free(s3dmst_ctx* ctx);
+void s3_remap_table(int16_t* tab);  // [1024][4]
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);

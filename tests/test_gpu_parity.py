@@ -605,3 +605,43 @@ def test_fast_mode_fp32_state_within_tolerance(api, oracle):
     chosen = ao[disp, np.arange(W * H)]
     assert np.all(chosen - bo <= 2 * tol * np.abs(bo) + 1e-12)
     eng.close()
+
+
+def test_remap_matches_opencv(api, oracle):
+    """SURVEY 8f-1: raw pair -> rectified images on the device == cv::remap(INTER_LINEAR) with the caller's CV_16SC2 maps
+    (stereo_Yin.cpp:139-144), bit for bit; then the path runs on them."""
+    from oracle import remap_oracle as ro
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "remap_small.npz"))
+    e = api.Stereo3DMST()
+    # golden vectors made by OpenCV from the reference's calibration (tests/golden/make_remap_fixture.py)
+    for lk, rk in (("00", "10"), ("01", "11")):
+        e.set_rectify_maps(0, g["xy_" + lk], g["fxy_" + lk])
+        e.set_rectify_maps(1, g["xy_" + rk], g["fxy_" + rk])
+        e.set_raw_images(g["src_" + lk], g["src_" + rk])
+        assert np.array_equal(e.get_image(0), g["exp_" + lk])
+        assert np.array_equal(e.get_image(1), g["exp_" + rk])
+    # random maps with footprints leaving the source on every side, against the oracle (and OpenCV when it is importable)
+    rng = np.random.default_rng(9)
+    Hs, Ws, H, W = 70, 90, 64, 96
+    srcs = [rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8) for _ in range(2)]
+    maps = [(np.stack([rng.integers(-4, Ws + 4, (H, W)), rng.integers(-4, Hs + 4, (H, W))], -1).astype(np.int16),
+             rng.integers(0, 1024, (H, W)).astype(np.uint16)) for _ in range(2)]
+    for v in range(2):
+        e.set_rectify_maps(v, *maps[v])
+    e.set_raw_images(*srcs)
+    for v in range(2):
+        want = ro.remap_fixed(srcs[v], *maps[v])
+        assert np.array_equal(e.get_image(v), want)
+        try:
+            import cv2
+            assert np.array_equal(want, cv2.remap(srcs[v], maps[v][0], maps[v][1], cv2.INTER_LINEAR))
+        except ImportError:
+            pass
+    # the rectified pair feeds the path like an uploaded one
+    left, right = e.get_image(0), e.get_image(1)
+    dl, dr = e.run_dense(16, fill=True)
+    e2 = api.Stereo3DMST()
+    e2.set_images(left, right)
+    dl2, dr2 = e2.run_dense(16, fill=True)
+    assert np.array_equal(dl, dl2) and np.array_equal(dr, dr2)
+    e.close(); e2.close()
