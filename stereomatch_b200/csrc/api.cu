@@ -134,6 +134,7 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
     }
     for (int i = 0; ok && i < S3DMST_T_COUNT * 4; i++) ok = cudaEventCreate(&ctx->ev[i / 4][(i / 2) & 1][i & 1]) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_xctx, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     if (ok) {
         // weights (Stereo3DMST.cpp:444, :513): exp(-w*gamma) in double with gamma promoted from float
         std::vector<double> w(S3_NUM_W), w2(S3_NUM_W);
@@ -170,6 +171,8 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
         if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
     if (ctx->ev_xctx) cudaEventDestroy(ctx->ev_xctx);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -848,6 +848,17 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
     const int Tmax = std::min(N, N / std::max(2, ctx->P.min_cc_size) + 2);
     int hc[2][16];
     std::vector<int> rootpix[2], tsize[2];
+    // A context that runs beside others (a batch: one host thread per frame, several ranks per host) must not spin through
+    // the forest kernel's ~8 ms: the copies go to pinned memory and the thread sleeps on a blocking-sync event.  One pair
+    // alone keeps the spinning wait (lowest wake-up latency).
+    const bool sleep_wait = ctx->P.fh_ctas > 0;
+    const size_t pin_view = 16 + 2 * (size_t)Tmax;
+    if (sleep_wait && ctx->h_pin_cap < 2 * pin_view) {
+        if (ctx->h_pin) S3_CUDA(cudaFreeHost(ctx->h_pin));
+        ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+        S3_CUDA(cudaHostAlloc(&ctx->h_pin, 2 * pin_view * sizeof(int), cudaHostAllocDefault));
+        ctx->h_pin_cap = 2 * pin_view;
+    }
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
         View& V = ctx->v[view];
@@ -858,11 +869,23 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
         S3_LAUNCH_CHECK();
         rootpix[view].resize(Tmax);
         tsize[view].resize(Tmax);
-        S3_CUDA(cudaMemcpyAsync(hc[view], V.counters + S3_MAX_ROUNDS - 16, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        S3_CUDA(cudaMemcpyAsync(rootpix[view].data(), V.tree_rootpix, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
-        S3_CUDA(cudaMemcpyAsync(tsize[view].data(), V.tree_size, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
+        int* pin = sleep_wait ? ctx->h_pin + view * pin_view : nullptr;
+        S3_CUDA(cudaMemcpyAsync(sleep_wait ? pin : hc[view], V.counters + S3_MAX_ROUNDS - 16, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaMemcpyAsync(sleep_wait ? pin + 16 : rootpix[view].data(), V.tree_rootpix, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaMemcpyAsync(sleep_wait ? pin + 16 + Tmax : tsize[view].data(), V.tree_size, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (sleep_wait) {
+        S3_CUDA(cudaEventRecord(ctx->ev_block, ctx->stream));
+        S3_CUDA(cudaEventSynchronize(ctx->ev_block));
+        for (int view = 0; view < 2; view++) {
+            if (!(mask & (1 << view))) continue;
+            const int* pin = ctx->h_pin + view * pin_view;
+            memcpy(hc[view], pin, sizeof(int) * 16);
+            memcpy(rootpix[view].data(), pin + 16, sizeof(int) * Tmax);
+            memcpy(tsize[view].data(), pin + 16 + Tmax, sizeof(int) * Tmax);
+        }
+    } else
+        S3_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
         View& V = ctx->v[view];

@@ -115,6 +115,9 @@ struct s3dmst_ctx {
     // scratch for PMS
     cudaEvent_t dbg_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // S3_DEBUG_BATCH timeline marks
     cudaEvent_t ev_xctx = nullptr;  // orders this context's stream against another context's in batched launches
+    cudaEvent_t ev_block = nullptr; // blocking-sync event: batched contexts SLEEP through the forest kernel instead of spinning
+    int* h_pin = nullptr;           // pinned staging for the forest stage's host round trip
+    size_t h_pin_cap = 0;           // ints
     uint32_t* units_dev = nullptr;  // aggregation work units + view table of the current launch
     size_t units_cap = 0;
     int* fh_sync = nullptr;         // grid barrier + per-round live counters of the forest kernel
