@@ -122,11 +122,13 @@ int s3dmst_set_cost_volume(s3dmst_ctx* ctx, int view, const float* vol_dmajor, i
 int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol_dmajor);
 
 /* a9,a10 + WTA, dense-label mode: labels [d0,d1), two-pass tree filter, strict '<'
- * so the lowest d wins ties.  disp [N] int32 and best_cost [N] double by pixel (NULL = leave on device). */
+ * so the lowest d wins ties.  disp [N] int32 and best_cost [N] double by pixel (NULL = leave on device; with both
+ * NULL the call only queues the work on the context's stream and returns without waiting for it). */
 int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* disp, double* best_cost);
 /* Final aggregated volume of the last dense call, double[D][H][W] (needs params.keep_aggregated). */
 int s3dmst_get_aggregated(s3dmst_ctx* ctx, int view, double* agg_dmajor);
-/* Device pointers of the dense result (pixel order) for collectives: best cost f64 [N], disparity i32 [N]. */
+/* Device pointers of the dense result (pixel order) for collectives: best cost f64 [N], disparity i32 [N].  Written in
+ * the order of the context's stream: s3dmst_sync() before another stream (e.g. NCCL's) reads them. */
 int s3dmst_dense_result_dev(s3dmst_ctx* ctx, int view, double** best_cost_dev, int32_t** disp_dev);
 /* After an all-reduce(MIN) of best cost into global_min_dev: disp := INT32_MAX where the local cost is not
  * the global minimum, so that a second all-reduce(MIN) on disp yields the lowest d attaining the minimum. */
