@@ -61,6 +61,8 @@ typedef struct s3dmst_params {
                            frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
                            frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
     int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel */
+    int agg_cluster_nodes; /* 0 = auto (8192): trees of at least this many nodes are walked by a thread-block cluster of
+                           8 CTAs (256 warps) instead of one CTA; < 0: never */
 } s3dmst_params;
 
 void s3dmst_default_params(s3dmst_params* p);
@@ -147,9 +149,13 @@ int s3dmst_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* tree_ids, const f
 /* a6 random plane initialisation (:390-430), bit-identical to the reference (same libstdc++ engine and
  * distribution, raster order); also resets min_cost to DBL_MAX (:820-821). */
 int s3dmst_init_labels(s3dmst_ctx* ctx, int view, int Dmax);
-/* a12 MST_PMS (:546-629) x n_iter with the library's own proposal generator (neighbour-tree labels, then the
- * refinement ladder).  Labels are initialised as above if none were set.  Parity for this stage is by injection
- * (s3dmst_pms_apply); the generator's two defined deviations are stated in csrc/pms.cu. */
+/* a12 MST_PMS (:546-629) x n_iter with the library's own proposal generator, on the device and without host
+ * synchronisation between rounds: per tree one proposal per neighbouring tree (ascending id: the label of a random
+ * pixel of that tree), then the refinement ladder around a random pixel of the tree itself, generated inside the
+ * proposal kernel from the label the tree holds AFTER its propagation proposals (as :584-595).  Labels are initialised
+ * as above if none were set.  Parity for this stage is by injection (s3dmst_pms_apply); the generator's defined
+ * deviations (round-start snapshot for the propagation labels, counter-based random numbers) are stated in
+ * csrc/pms.cu; tests/test_gpu_parity.py replays the generator's own proposal stream through s3dmst_pms_apply. */
 int s3dmst_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed);
 /* a13 LabelToDisp (:189-201) followed by the *(Dmax-1) of :900-902. */
 int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view);
@@ -168,6 +174,15 @@ int s3dmst_reproject_to_3d(s3dmst_ctx* ctx, const double* Q, float disp_floor, i
 /* Whole dense pipeline on the current images: forests, cost volume, aggregation + WTA for both views,
  * LR check (+fill).  Outputs float[H][W] (NULL = leave on device). */
 int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp);
+
+/* a1: the reference's own pipeline (stereo3dmst, Stereo3DMST.cpp:805-904) on the current images: forests (built if
+ * missing), random plane initialisation (:390-430), params.num_iter rounds of MST_PMS per view with the library's
+ * on-device proposal generator (:858-889; s3dmst_pms_iterate), LabelToDisp and *(Dmax-1) (:189-201, :900-902), left-right
+ * check (:904; the reference passes fill = 0).  Volumes given through s3dmst_set_cost_volume (mc-cnn's left.bin /
+ * right.bin) are used as they are; otherwise the a2' volume is built and ingested.  Outputs float[H][W] (NULL = leave on
+ * the device; with both NULL the call returns without waiting).  This is what the header-compatible stereo3dmst() of
+ * csrc/stereo3dmst_shim.cpp calls. */
+int s3dmst_run(s3dmst_ctx* ctx, int Dmax, unsigned seed, int fill, float* left_disp, float* right_disp);
 
 /* The same pipeline over a batch of frames, one context per frame (all on one device, same image size; images set
  * with s3dmst_set_images on each).  Forest and cost stages of the frames run concurrently on the contexts' streams

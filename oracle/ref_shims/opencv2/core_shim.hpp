@@ -56,6 +56,18 @@ public:
         data = buf_->data();
     }
     int type() const { return type_; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    bool isContinuous() const { return true; }                                  // this stand-in never pads rows
+    struct MatStep {                                                            // cv::Mat::step converts to size_t (bytes per row)
+        const Mat* m;
+        operator size_t() const { return (size_t)m->cols * m->elemSize(); }
+    };
+    MatStep step{this};
+    Mat(const Mat& o) : rows(o.rows), cols(o.cols), data(o.data), type_(o.type_), buf_(o.buf_) {}
+    Mat& operator=(const Mat& o) {
+        rows = o.rows; cols = o.cols; data = o.data; type_ = o.type_; buf_ = o.buf_;
+        return *this;
+    }
     int depth() const { return type_ & 7; }
     int channels() const { return (type_ >> 3) + 1; }
     size_t elemSize1() const { return depth() == CV_8U ? 1 : depth() == CV_32F ? 4 : 8; }

@@ -33,7 +33,7 @@ class S3Params(C.Structure):
                 ("cost_cap", C.c_float), ("cost_offset", C.c_float), ("cost_scale", C.c_float), ("oob_cost", C.c_float),
                 ("num_iter", C.c_int), ("refine_floor", C.c_float), ("exact", C.c_int), ("keep_aggregated", C.c_int),
                 ("agg_threads", C.c_int), ("agg_cache_nodes", C.c_int), ("agg_ring_nodes", C.c_int), ("agg_kernel", C.c_int),
-                ("fh_ctas", C.c_int), ("fh_threads", C.c_int)]
+                ("fh_ctas", C.c_int), ("fh_threads", C.c_int), ("agg_cluster_nodes", C.c_int)]
 
 
 # every symbol include/s3dmst.h declares (tests/test_abi.py checks the library exports all of them)
@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def load_library():
     L.s3dmst_get_disparity.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_lr_check.argtypes = [c_p, C.c_int]
     L.s3dmst_run_dense.argtypes = [c_p, C.c_int, C.c_int, c_p, c_p]
+    L.s3dmst_run.argtypes = [c_p, C.c_int, C.c_uint, C.c_int, c_p, c_p]
     L.s3dmst_reproject_to_3d.argtypes = [c_p, c_p, C.c_float, C.c_int, c_p, c_p]
     L.s3dmst_run_dense_batch.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_batch_front.argtypes = [C.POINTER(c_p), C.c_int, C.c_int]
@@ -338,6 +339,14 @@ class Stereo3DMST:
         dr = np.empty(self.N, np.float32) if fetch else None
         self._ck(self.L.s3dmst_run_dense(self.h, D, int(fill), _ptr(dl), _ptr(dr)))
         self.D = D
+        return dl, dr
+
+    def run(self, Dmax, seed=1, fill=False, fetch=True):
+        """The reference's pipeline (plane init, num_iter rounds of MST_PMS per view, LabelToDisp, LR check): s3dmst_run."""
+        dl = np.empty(self.N, np.float32) if fetch else None
+        dr = np.empty(self.N, np.float32) if fetch else None
+        self._ck(self.L.s3dmst_run(self.h, int(Dmax), int(seed), int(fill), _ptr(dl), _ptr(dr)))
+        self.D = Dmax
         return dl, dr
 
     def sync(self):

@@ -76,7 +76,12 @@ struct Agg3Args {
     double* min_cost;      // [N] pixel order
     float* abc;            // [N][3] pixel order
     int img_w, D;          // image width, labels of the cost rows
-    float oob;             // label cost outside [0, D)       // back-off of a waiting warp between two polls
+    float oob;             // label cost outside [0, D)
+    // proposal generation inside the kernel (s3dmst_pms_iterate): after a tree's listed proposals (its neighbours' labels),
+    // the refinement ladder around a random pixel of the tree itself
+    int gen;
+    uint32_t seed, round;
+    float refine_floor;
 };
 
 __device__ __forceinline__ uint32_t a3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +97,36 @@ __device__ __forceinline__ int a3_ld_relaxed(uint32_t a) {
     int v;
     asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
+}
+// ---- thread-block cluster (one giant tree walked by CL CTAs): progress words and ring rows of the other CTAs are read
+// through distributed shared memory
+__device__ __forceinline__ uint32_t a3_crank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t a3_mapa(uint32_t a, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(cta));
+    return r;
+}
+// Cluster-scope acquire / release compile to MEMBAR.ALL.GPU and an L1 invalidation (CCTL.IVALL) around EVERY access: far
+// too heavy for a poll loop.  The hand-over does not need them: a row and its progress word are written by one warp
+// into its own shared memory in program order (STS row, bar.warp, STS word), remote reads of that memory are serviced
+// in arrival order, and a reader issues its row loads only after the poll loop's branch has consumed the word (no
+// speculation).  What does travel through global memory (far rows) is fenced explicitly by the writer (a3_fence_cl
+// before the word is stored) and read with ld.global.cg (L2), never from L1.
+__device__ __forceinline__ int a3_ld_acquire_cl(uint32_t a) {
+    int v;
+    asm volatile("ld.relaxed.cluster.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void a3_st_release_cl(uint32_t a, int v) {  // a: this CTA's own shared window
+    asm volatile("st.volatile.shared::cta.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");  // an STS behind the row's STSs, same pipe
+}
+__device__ __forceinline__ void a3_fence_cl() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void a3_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ double2 a3_ldcg_d2(const double* p) {
     double2 v;
@@ -136,6 +171,11 @@ template <> struct A3T<double> {
     static __device__ __forceinline__ double ldsw(uint32_t a) { return a3_lds_d(a); }
     static __device__ __forceinline__ T2 lds2(uint32_t a) { return a3_lds_d2(a); }
     static __device__ __forceinline__ void sts2(uint32_t a, T2 v) { a3_sts_d2(a, v); }
+    static __device__ __forceinline__ T2 ldc2(uint32_t a) {  // distributed shared memory (mapa address)
+        double2 v;
+        asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+        return v;
+    }
     static __device__ __forceinline__ T2 ldcg2(const char* p) { return a3_ldcg_d2(reinterpret_cast<const double*>(p)); }
     // warp arg-min with three 32-bit REDUX steps: (cost hi, cost lo, label); ties -> lowest label
     static __device__ __forceinline__ unsigned warp_argmin(double bc, int bd, double& mc) {
@@ -167,6 +207,11 @@ template <> struct A3T<float> {
     static __device__ __forceinline__ void sts2(uint32_t a, T2 v) {
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
     }
+    static __device__ __forceinline__ T2 ldc2(uint32_t a) {
+        float2 v;
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+        return v;
+    }
     static __device__ __forceinline__ T2 ldcg2(const char* p) {
         float2 v;
         asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
@@ -187,8 +232,20 @@ template <> struct A3T<float> {
 // PMS: the "labels" of a pass are up to 64 injected proposals of the tree (two per lane); the cost of (node, proposal)
 // is compute3DLabelCost on the node's cost row; the epilogue is the label update instead of the WTA; a tree with more
 // than 64 proposals runs its passes once per batch of 64, in list order.
-template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS>
+// CL: thread-block cluster size.  CL > 1: ONE tree is walked by the CL x 32 warps of a cluster (a tree's time on one CTA is
+// proportional to its node count: the 204 k-node tree of the FLIR pair bounded the whole launch).  Processing position k
+// (k = top - v on the way up, v - base on the way down) is owned by CTA k % CL, warp (k / CL) % 32; its ring row is row
+// (k / CL) % R of the owner's ring, so the cluster's rings together hold the last R x CL rows and hand over values between
+// nodes closer than NEAR x CL.  Progress words and ring rows of other CTAs are read through distributed shared memory
+// (mapa + ld.acquire.cluster / ld.shared::cluster), published with st.release.cluster; the far path through L2 is the
+// same (the release is cluster scope, so global stores before it are visible to the other SMs of the cluster).
+template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS, int CL>
 __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3Args A) {
+    static_assert(CL == 1 || BIG, "a cluster walks a tree with 32 warps per CTA");
+    static_assert(CL == 1 || CL == 2 || CL == 4 || CL == 8, "portable cluster sizes");
+    constexpr int LOGCL = CL == 1 ? 0 : CL == 2 ? 1 : CL == 4 ? 2 : 3;
+    constexpr int NEAR_E = A3_NEAR * CL;   // hand-over distance and ring rows of the whole cluster
+    constexpr int R_E = A3_R * CL;
     extern __shared__ __align__(16) unsigned char s_raw[];
     using TT = A3T<T>;
     using T2 = typename TT::T2;
@@ -198,43 +255,111 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     T2* s_ring = reinterpret_cast<T2*>(s_raw + ((2 * S3_NUM_W * sizeof(T) + 15) / 16) * 16);  // [A3_R][NH][32]
     int* s_prog = reinterpret_cast<int*>(s_ring + A3_R * NH * 32);  // [32] progress words
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, WM = W - 1;
+    const int WT = W * CL;                                          // warps walking the tree
+    const uint32_t crank = CL > 1 ? a3_crank() : 0u;
+    const int gw = w * CL + (int)crank;                             // this warp's position in the deal
 
-    const int4 unit = A.units[A.unit0 + blockIdx.x];
+    const int4 unit = A.units[A.unit0 + blockIdx.x / CL];
     const Agg3View V = A.views[unit.x];
     const int t = unit.y, slice = unit.w;
     const int base = V.tree_start[t], end = V.tree_start[t + 1], top = end - 1;
     const size_t Dp = (size_t)A.Dp;                 // cost row length
     const size_t DA = PMS ? (size_t)64 : Dp;        // running-sum row length (proposal mode: a [node][64] scratch)
     __shared__ float s_lab[PMS ? 64 * 3 : 1];
+    __shared__ int s_nlad;
     const int p_lo = PMS ? A.prop_off[t] : 0, p_hi = PMS ? A.prop_off[t + 1] : 1;
-    const int lim = PMS ? p_hi : A.d1;              // first label / proposal index that does not exist
+    // passes over the tree: dense mode one; proposal mode one per batch of 64 listed proposals, then (A.gen) one for the
+    // refinement ladder this kernel generates itself from the label the tree holds after those (MST_PMS, :584-625)
+    const int n_listed = PMS ? (p_hi - p_lo + 63) / 64 : 1;
+    const int n_pass = n_listed + ((PMS && A.gen) ? 1 : 0);
 
     for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
         s_w[i] = reinterpret_cast<const T*>(A.lut_w)[i];
         s_w2[i] = reinterpret_cast<const T*>(A.lut_w2)[i];
     }
     if (tid < 32) s_prog[tid] = end;  // up pass: node c is done iff its owner's word is <= c
-    __syncthreads();
+    if constexpr (CL > 1) a3_cluster_sync(); else __syncthreads();
     const uint32_t prog_a = a3_smem(s_prog);
     const unsigned sleep_ns = (unsigned)A.sleep_ns;
     const uint32_t ring_a = a3_smem(s_ring) + (uint32_t)sizeof(T2) * lane;  // this lane's column of the ring
     const uint32_t w_a = a3_smem(s_w);
     constexpr uint32_t ROWB = NH * HB;                      // bytes of one ring row
-    const long long strideC = (long long)W * (long long)Dp * 4, strideA = (long long)W * (long long)(PMS ? 64 : A.Dp) * (long long)sizeof(T);  // bytes between a warp's consecutive rows
+    const long long strideC = (long long)WT * (long long)Dp * 4, strideA = (long long)WT * (long long)(PMS ? 64 : A.Dp) * (long long)sizeof(T);  // bytes between a warp's consecutive rows
     T* const aupT = reinterpret_cast<T*>(V.aup);  // running sums in the state type (the buffer is sized for doubles)
+    // progress word / ring row of processing position k (see the header: owner CTA k % CL, warp (k / CL) % W)
+    auto prog_of = [&](int k) -> uint32_t {
+        if constexpr (CL == 1) return prog_a + 4u * (uint32_t)(k & WM);
+        else return a3_mapa(prog_a + 4u * (uint32_t)((k >> LOGCL) & WM), (uint32_t)(k & (CL - 1)));
+    };
+    auto poll = [&](uint32_t pa) -> int {
+        if constexpr (CL == 1) return a3_ld_acquire(pa);
+        else return a3_ld_acquire_cl(pa);
+    };
+    auto row_of = [&](int k) -> uint32_t {  // this lane's column of the row, in the owner's window
+        const uint32_t ra = ring_a + (uint32_t)((k >> LOGCL) & (A3_R - 1)) * ROWB;
+        if constexpr (CL == 1) return ra;
+        else return a3_mapa(ra, (uint32_t)(k & (CL - 1)));
+    };
+    auto ld_row = [&](uint32_t ra) -> T2 {
+        if constexpr (CL == 1) return TT::lds2(ra);
+        else return TT::ldc2(ra);
+    };
+    auto publish = [&](int v) {
+        if constexpr (CL == 1) a3_st_release(prog_a + 4u * w, v);
+        else a3_st_release_cl(prog_a + 4u * w, v);
+    };
+    // maximum / minimum over the progress words of every warp walking the tree (ring-reuse guard)
+    auto prog_max = [&]() -> int {
+        int m = INT_MIN;
+        if (lane < W) {
+            if constexpr (CL == 1) m = a3_ld_acquire(prog_a + 4u * lane);
+            else {
+#pragma unroll
+                for (int j = 0; j < CL; j++) m = max(m, a3_ld_acquire_cl(a3_mapa(prog_a + 4u * lane, (uint32_t)j)));
+            }
+        }
+        return __reduce_max_sync(0xffffffffu, m);
+    };
+    auto prog_min = [&]() -> int {
+        int m = INT_MAX;
+        if (lane < W) {
+            if constexpr (CL == 1) m = a3_ld_acquire(prog_a + 4u * lane);
+            else {
+#pragma unroll
+                for (int j = 0; j < CL; j++) m = min(m, a3_ld_acquire_cl(a3_mapa(prog_a + 4u * lane, (uint32_t)j)));
+            }
+        }
+        return __reduce_min_sync(0xffffffffu, m);
+    };
 
-    for (int b0 = p_lo; b0 < p_hi; b0 += 64) {  // dense mode: one trip
+    for (int pass = 0; pass < n_pass; pass++) {
+    const bool gen = PMS && pass >= n_listed;
+    const int b0 = PMS ? (gen ? 0 : p_lo + 64 * pass) : 0;   // proposal mode: index of the batch's first proposal (s_lab[0])
+    int b_end = gen ? 0 : p_hi;                              // ... and of the first one that does not exist
+    if (PMS) {
+        if constexpr (CL > 1) a3_cluster_sync(); else __syncthreads();  // the previous batch is done with s_lab, the ring and the progress words
+        if (gen) {
+            // every CTA walking the tree derives the same ladder: the label of a random node of the tree as the listed
+            // proposals left it (written by this cluster before the barrier above; read from L2)
+            if (tid == 0) {
+                const int pix = V.node_pixel[base + (int)(s3_rng(A.seed, A.round, (uint32_t)t, S3_SLOT_REFINE_PIXEL) % (uint32_t)(end - base))];
+                const float* l = A.abc + 3 * (size_t)pix;
+                s_nlad = s3_refine_ladder(__ldcg(l), __ldcg(l + 1), __ldcg(l + 2), (float)(pix % A.img_w), (float)(pix / A.img_w), A.D, A.refine_floor,
+                                          A.seed, A.round, (uint32_t)t, s_lab);
+            }
+        } else
+            for (int i = tid; i < 3 * min(64, p_hi - b0); i += blockDim.x) s_lab[i] = A.labels[3 * (size_t)b0 + i];
+        if (tid < 32) s_prog[tid] = end;
+        if constexpr (CL > 1) a3_cluster_sync(); else __syncthreads();
+        if (gen) b_end = s_nlad;
+        if (b_end <= b0) continue;  // every step of the ladder left [0, Dmax]
+    }
+    const int lim = PMS ? b_end : A.d1; // first label / proposal index that does not exist
     const int l0 = PMS ? b0 : unit.z;   // first label (dense) / proposal (PMS) of this pass
     const int aoff = PMS ? 0 : l0;      // column of l0 in the running-sum rows
     bool act[NH];
 #pragma unroll
     for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < lim;  // the lane's pair holds at least one real label
-    if (PMS) {
-        __syncthreads();  // the previous batch is done with s_lab, the ring and the progress words
-        for (int i = tid; i < 3 * min(64, p_hi - b0); i += blockDim.x) s_lab[i] = A.labels[3 * (size_t)b0 + i];
-        if (tid < 32) s_prog[tid] = end;
-        __syncthreads();
-    }
     // proposal mode: cost of this lane's two proposals at node vv (compute3DLabelCost, :103-118)
     auto pms_cost = [&](int vv) -> float2 {
         const int pix = V.node_pixel[vv];
@@ -242,14 +367,14 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         const float* row = V.cost + (size_t)vv * Dp;
         const int k = 2 * lane;
         float2 c = make_float2(0.f, 0.f);
-        if (b0 + k < p_hi) c.x = s3_label_cost(row, s_lab[3 * k], s_lab[3 * k + 1], s_lab[3 * k + 2], x, y, A.D, A.oob);
-        if (b0 + k + 1 < p_hi) c.y = s3_label_cost(row, s_lab[3 * k + 3], s_lab[3 * k + 4], s_lab[3 * k + 5], x, y, A.D, A.oob);
+        if (b0 + k < b_end) c.x = s3_label_cost(row, s_lab[3 * k], s_lab[3 * k + 1], s_lab[3 * k + 2], x, y, A.D, A.oob);
+        if (b0 + k + 1 < b_end) c.y = s3_label_cost(row, s_lab[3 * k + 3], s_lab[3 * k + 4], s_lab[3 * k + 5], x, y, A.D, A.oob);
         return c;
     };
 
     // ================================================================== leaf -> root
     {
-        int v = top - w;
+        int v = top - gw;
         const char* nup_p = reinterpret_cast<const char*>(V.node_up + v);
         const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + (PMS ? 0 : l0 + 2 * lane));
         char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * DA + aoff + 2 * lane);
@@ -257,11 +382,13 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         // the node's record and cost row live in these registers from the end of the previous iteration (the loads are
         // issued right after the previous publish, so they are in flight during this warp's wait for the children)
         int4 nu = make_int4(0, 0, 0, 0);  // {child_begin, child_count, cw01, cw23}
+        int par = 0;                      // CL > 1: the node's parent (how far the row has to travel)
         float2 cf[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) cf[h] = make_float2(0.f, 0.f);
         if (v >= base) {
             nu = *reinterpret_cast<const int4*>(nup_p);
+            if constexpr (CL > 1) par = V.node_dn[v].x;
             if constexpr (PMS) cf[0] = pms_cost(v);
             else {
 #pragma unroll
@@ -269,17 +396,33 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                     if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
             }
         } else if (lane == 0)
-            a3_st_release(prog_a + 4u * w, base);  // a warp without nodes never holds anybody back
+            publish(base);  // a warp without nodes never holds anybody back
         int guard_ok = top + 1;  // writing ring row v is known to be safe for every v >= guard_ok
 #if A3_INSTR
         long long tq = clock64(), q_pre = 0, q_poll = 0, q_dep = 0, q_guard = 0, q_pub = 0, q_post = 0; const long long t_up0 = tq; int n_nodes = 0, n_guard = 0;
 #endif
+        // ring row of v last held node v + R_E, which only nodes > v + R_E - NEAR_E may still read
+        auto guard_up = [&]() {
+            if (v < guard_ok && v + R_E <= top) {
+#if A3_INSTR
+                n_guard++;
+#endif
+                int m;
+                while (true) {
+                    m = prog_max();
+                    if (m < v + R_E - NEAR_E + 1 + WT) break;
+                    __nanosleep(sleep_ns);
+                }
+                guard_ok = m - (R_E - NEAR_E + WT);
+            }
+        };
         while (v >= base) {
 #if A3_INSTR
             n_nodes++;
 #endif
-            const int vn = v - W;
+            const int vn = v - WT;
             const int cc = nu.y & 7, cb = nu.x;
+            if constexpr (CL > 1) guard_up();  // a round trip through the cluster: taken before the wait for the children, not after it
             T2 acc[NH];
 #pragma unroll
             for (int h = 0; h < NH; h++) acc[h] = TT::zero2();
@@ -288,14 +431,14 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     if (cc > K) {                                                                                                    \
         const int c = cb + K;                                                                                        \
         const T wk = TT::ldsw(w_a + (uint32_t)sizeof(T) * (IW));                                                                 \
-        const uint32_t pa = prog_a + 4u * (uint32_t)((top - c) & WM);                                                \
+        const uint32_t pa = prog_of(top - c);                                                                        \
         A3_CLK(q_pre);                                                                                               \
-        while (a3_ld_acquire(pa) > c) __nanosleep(sleep_ns);                                                         \
+        while (poll(pa) > c) __nanosleep(sleep_ns);                                                                  \
         A3_CLK(q_poll);                                                                                              \
         T2 cv[NH];                                                                                              \
-        if (c - v < A3_NEAR) {                                                                                       \
-            const uint32_t ra = ring_a + (uint32_t)(c & (A3_R - 1)) * ROWB;                                          \
-            _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = TT::lds2(ra + h * HB);                          \
+        if (c - v < NEAR_E) {                                                                                        \
+            const uint32_t ra = row_of(top - c);                                                                     \
+            _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = ld_row(ra + h * HB);                            \
         } else {                                                                                                     \
             const char* gp = aup_lane0 + (size_t)c * DA * sizeof(T);                                                         \
             _Pragma("unroll") for (int h = 0; h < NH; h++)                                                           \
@@ -316,40 +459,31 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 acc[h].x = TT::add(acc[h].x, (T)cf[h].x);
                 acc[h].y = TT::add(acc[h].y, (T)cf[h].y);
             }
-            const bool far_parent = nu.y & S3_NU_FARPARENT;
-            if (far_parent) {  // a parent beyond the ring reads this row from L2: it has to be out before the publish
+            // a parent beyond the rings reads this row from L2: it has to be out before the publish
+            const bool far_parent = CL > 1 ? (v - par >= NEAR_E) : (bool)(nu.y & S3_NU_FARPARENT);
+            if (far_parent) {
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = acc[h];
+                if constexpr (CL > 1) a3_fence_cl();  // every lane's stores, before lane 0 publishes
             }
             A3_CLK(q_dep);
-            // ring row v last held node v + R, which only nodes > v + R - NEAR may still read
-            if (v < guard_ok && v + A3_R <= top) {
-#if A3_INSTR
-                n_guard++;
-#endif
-                int m;
-                while (true) {
-                    m = __reduce_max_sync(0xffffffffu, lane < W ? a3_ld_acquire(prog_a + 4u * lane) : INT_MIN);
-                    if (m < v + A3_R - A3_NEAR + 1 + W) break;
-                    __nanosleep(sleep_ns);
-                }
-                guard_ok = m - (A3_R - A3_NEAR + W);
-            }
+            if constexpr (CL == 1) guard_up();
             A3_CLK(q_guard);
             {
-                const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
+                const uint32_t ra = ring_a + (uint32_t)(((top - v) >> LOGCL) & (A3_R - 1)) * ROWB;
 #pragma unroll
                 for (int h = 0; h < NH; h++) TT::sts2(ra + h * HB, acc[h]);
             }
             __syncwarp();
-            if (lane == 0) a3_st_release(prog_a + 4u * w, v);
+            if (lane == 0) publish(v);
             A3_CLK(q_pub);
             // Global accesses are issued only AFTER the publish: the release fence waits for every memory operation the warp
             // has in flight, and a load still on its way from HBM would put its latency on every level of the tree.
             const bool store_late = !far_parent;
             if (vn >= base) {  // next node of this warp: record and cost row
-                nu = *reinterpret_cast<const int4*>(nup_p - (long long)W * 16);
+                nu = *reinterpret_cast<const int4*>(nup_p - (long long)WT * 16);
+                if constexpr (CL > 1) par = V.node_dn[vn].x;
                 if constexpr (PMS) cf[0] = pms_cost(vn);
                 else {
 #pragma unroll
@@ -358,14 +492,14 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 }
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
-            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * W >= base)
+            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - (PMS ? 0 : 2 * lane * 4) - A3_PF * strideC + lane * 128));
             if (store_late) {  // read back on the way down
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = acc[h];
             }
-            nup_p -= (long long)W * 16;
+            nup_p -= (long long)WT * 16;
             cost_p -= strideC;
             aup_p -= strideA;
             v = vn;
@@ -375,27 +509,30 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         if (blockIdx.x == 0 && lane == 0 && (w == 0 || w == 9)) printf("up W=%d warp %d: %d nodes (%d guards), cycles/node total %lld | pre %lld poll %lld dep %lld guard %lld publish %lld post %lld\n", W, w, n_nodes, n_guard, (clock64() - t_up0) / n_nodes, q_pre / n_nodes, q_poll / n_nodes, q_dep / n_nodes, q_guard / n_nodes, q_pub / n_nodes, q_post / n_nodes);
 #endif
     }
-    __syncthreads();
+    // every row of the way up is in L2 / HBM and every warp of the tree is done with the rings before the way down starts
+    if constexpr (CL > 1) a3_cluster_sync(); else __syncthreads();
     if (tid < 32) s_prog[tid] = base - 1;  // down pass: node p is done iff its owner's word is >= p
-    __syncthreads();
+    if constexpr (CL > 1) a3_cluster_sync(); else __syncthreads();
 
     // ================================================================== root -> leaf, WTA folded in
     {
-        int v = base + w;
+        int v = base + gw;
         const char* ndn_p = reinterpret_cast<const char*>(V.node_dn + v);
         char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * DA + aoff + 2 * lane);
         const char* aup_lane0 = reinterpret_cast<const char*>(aupT + aoff + 2 * lane);
         int4 nd = make_int4(0, 0, 0, 0);  // {parent, parent weight, level | flags, pixel}
+        int2 ch = make_int2(0, 0);        // CL > 1: {child_begin, child_count} (how far the final row has to travel)
         T2 au[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) au[h] = TT::zero2();
         if (v < end) {
             nd = *reinterpret_cast<const int4*>(ndn_p);
+            if constexpr (CL > 1) ch = *reinterpret_cast<const int2*>(V.node_up + v);
 #pragma unroll
-            for (int h = 0; h < NH; h++)
-                if (act[h]) au[h] = *reinterpret_cast<const T2*>(aup_p + h * HB);
+            for (int h = 0; h < NH; h++)  // (cluster: the row was written by another SM — read it from L2, never from this SM's L1)
+                if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + h * HB) : *reinterpret_cast<const T2*>(aup_p + h * HB);
         } else if (lane == 0)
-            a3_st_release(prog_a + 4u * w, end);
+            publish(end);
         int guard_ok = base - 1;  // writing ring row v is known to be safe for every v <= guard_ok
         // WTA over a node's labels held by this warp: strict '<', lowest label wins ties
         auto wta = [&](const T2* f, int vv, int pix) {
@@ -429,9 +566,21 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 }
             }
         };
+        auto guard_dn = [&]() {
+            if (v > guard_ok && v - R_E >= base) {
+                int m;
+                while (true) {
+                    m = prog_min();
+                    if (m > v - R_E + NEAR_E - 1 - WT) break;
+                    __nanosleep(sleep_ns);
+                }
+                guard_ok = m + (R_E - NEAR_E + WT);
+            }
+        };
         while (v < end) {
-            const int vn = v + W;
+            const int vn = v + WT;
             const int p = nd.x;
+            if constexpr (CL > 1) guard_dn();
             T2 fin[NH];
             if (p != v) {
                 // A[c] = w * A[parent] + (1 - w*w) * A_up[c]   (Stereo3DMST.cpp:155)
@@ -441,13 +590,13 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                     au[h].x = TT::mul(wq, au[h].x);
                     au[h].y = TT::mul(wq, au[h].y);
                 }
-                const uint32_t pa = prog_a + 4u * (uint32_t)((p - base) & WM);
-                while (a3_ld_acquire(pa) < p) __nanosleep(sleep_ns);
+                const uint32_t pa = prog_of(p - base);
+                while (poll(pa) < p) __nanosleep(sleep_ns);
                 T2 pv[NH];
-                if (v - p < A3_NEAR) {
-                    const uint32_t ra = ring_a + (uint32_t)(p & (A3_R - 1)) * ROWB;
+                if (v - p < NEAR_E) {
+                    const uint32_t ra = row_of(p - base);
 #pragma unroll
-                    for (int h = 0; h < NH; h++) pv[h] = TT::lds2(ra + h * HB);
+                    for (int h = 0; h < NH; h++) pv[h] = ld_row(ra + h * HB);
                 } else {
                     const char* gp = aup_lane0 + (size_t)p * DA * sizeof(T);
 #pragma unroll
@@ -462,45 +611,43 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #pragma unroll
                 for (int h = 0; h < NH; h++) fin[h] = au[h];  // the root keeps its leaf->root sum
             }
-            if ((nd.z & S3_ND_FAR) || (!PMS && A.keep)) {  // children further than NEAR read the final value from L2
+            // children further than the rings reach read the final value from L2
+            const bool far_child = CL > 1 ? ((ch.y & 7) > 0 && ch.x + (ch.y & 7) - 1 - v >= NEAR_E) : (bool)(nd.z & S3_ND_FAR);
+            if (far_child || (!PMS && A.keep)) {
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = fin[h];
+                if constexpr (CL > 1) a3_fence_cl();
             }
-            if (v > guard_ok && v - A3_R >= base) {
-                int m;
-                while (true) {
-                    m = __reduce_min_sync(0xffffffffu, lane < W ? a3_ld_acquire(prog_a + 4u * lane) : INT_MAX);
-                    if (m > v - A3_R + A3_NEAR - 1 - W) break;
-                    __nanosleep(sleep_ns);
-                }
-                guard_ok = m + (A3_R - A3_NEAR + W);
-            }
+            if constexpr (CL == 1) guard_dn();
             {
-                const uint32_t ra = ring_a + (uint32_t)(v & (A3_R - 1)) * ROWB;
+                const uint32_t ra = ring_a + (uint32_t)(((v - base) >> LOGCL) & (A3_R - 1)) * ROWB;
 #pragma unroll
                 for (int h = 0; h < NH; h++) TT::sts2(ra + h * HB, fin[h]);
             }
             __syncwarp();
-            if (lane == 0) a3_st_release(prog_a + 4u * w, v);
+            if (lane == 0) publish(v);
             // next node's loads: after the publish (see the leaf->root pass), into the registers this node is done with
             const int pix = nd.w;
             if (vn < end) {
-                nd = *reinterpret_cast<const int4*>(ndn_p + (long long)W * 16);
+                nd = *reinterpret_cast<const int4*>(ndn_p + (long long)WT * 16);
+                if constexpr (CL > 1) ch = *reinterpret_cast<const int2*>(V.node_up + vn);
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) au[h] = *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
+                    if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + strideA + h * HB) : *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
             }
-            if (lane < NH * (int)sizeof(T) / 2 && v + A3_PF * W < end)
+            if (lane < NH * (int)sizeof(T) / 2 && v + A3_PF * WT < end)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * (int)sizeof(T) + A3_PF * strideA + lane * 128));
             // the WTA of this node runs while those loads are in flight and the next parent is still being computed
             wta(fin, v, pix);
-            ndn_p += (long long)W * 16;
+            ndn_p += (long long)WT * 16;
             aup_p += strideA;
             v = vn;
         }
     }
-    }  // batches of 64 proposals
+    }  // passes
+    // a CTA's shared memory must stay alive until no other CTA of the cluster can read it any more
+    if constexpr (CL > 1) a3_cluster_sync();
 }
 
 static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
@@ -519,6 +666,44 @@ __global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node
     const int pix = node_dn[v].w;
     disp[pix] = bd;
     best[pix] = bc;
+}
+
+#define A3_CLUSTER 8   // CTAs walking one giant tree
+
+// trees of at least this many nodes are walked by a cluster / get a CTA of 32 warps (development overrides: S3_AGG_CL, S3_AGG_BIG)
+static int s3_agg_cluster_nodes(const s3dmst_ctx* ctx) {
+    static const int env = getenv("S3_AGG_CL") ? atoi(getenv("S3_AGG_CL")) : 0;
+    const int p = ctx->P.agg_cluster_nodes;
+    return p < 0 ? 0 : p > 0 ? p : env ? env : 8192;
+}
+static int s3_agg_big_nodes() {
+    static const int v = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
+    return v;
+}
+
+template <typename K>
+static int agg3_launch(s3dmst_ctx* ctx, K kernel, int grid, int threads, size_t smem, int cluster, cudaStream_t stream, const Agg3Args& A) {
+    S3_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cluster == 1) {
+        kernel<<<grid, threads, smem, stream>>>(A);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        S3_CUDA(cudaLaunchKernelEx(&cfg, kernel, A));
+    }
+    S3_LAUNCH_CHECK();
+    return 0;
 }
 
 // One launch over the trees of every view in `views_mask` (bit 0 = left, bit 1 = right) of every context in `ctxs`
@@ -604,8 +789,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         ctx->units_cap = ubytes + tbytes;
     }
     char* ubase = reinterpret_cast<char*>(ctx->units_dev);
-    S3_CUDA(cudaMemcpyAsync(ubase, table.data(), table.size() * sizeof(Agg3View), cudaMemcpyHostToDevice, ctx->stream));
-    S3_CUDA(cudaMemcpyAsync(ubase + tbytes, units.data(), ubytes, cudaMemcpyHostToDevice, ctx->stream));
+    S3_TRY(s3_h2d_staged(ctx, ubase, table.data(), table.size() * sizeof(Agg3View)));
+    S3_TRY(s3_h2d_staged(ctx, ubase + tbytes, units.data(), ubytes));
     // everything the other contexts have queued (their cost volumes) comes first
     for (int c = 1; c < nctx; c++) {
         S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
@@ -624,43 +809,57 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env ? sleep_env : 20;
 
-    // all but the smallest trees get 32 warps and an SM of their own; the rest 16 warps, two trees per SM
-    static const int big_nodes = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
-    int n_big = 0;
+    // The giant trees get a thread-block cluster (A3_CLUSTER CTAs = 256 warps on one tree), on the context's second
+    // stream so that they run beside the rest; all but the smallest of the others get 32 warps and an SM of their own;
+    // the rest 16 warps, two trees per SM.
+    const int cl_nodes = s3_agg_cluster_nodes(ctx), big_nodes = s3_agg_big_nodes();
+    int n_cl = 0;
+    while (cl_nodes > 0 && n_cl < (int)u.size() && u[n_cl].first >= cl_nodes) n_cl++;
+    int n_big = n_cl;
     while (n_big < (int)u.size() && u[n_big].first >= big_nodes) n_big++;
-    const int n_small = (int)u.size() - n_big;
+    n_big -= n_cl;
+    const int n_small = (int)u.size() - n_cl - n_big;
     const bool full = nl % SW == 0;  // every slice covers SW real labels
     S3_EV_BEGIN(S3DMST_T_AGG, first);
-#define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                           \
+    cudaStream_t launch_stream = ctx->stream;
+#define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                      \
     do {                                                                                                                       \
         const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(T_));                                                              \
-        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false><<<GRID_, THREADS_, smem, ctx->stream>>>(A);                         \
-        S3_LAUNCH_CHECK();                                                                                                     \
+        S3_TRY(agg3_launch(ctx, k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false, CL_>, GRID_, THREADS_, smem, CL_, launch_stream, A)); \
     } while (0)
-#define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_)                                                                 \
+#define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                            \
     do {                                                                                                                       \
-        if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, GRID_, THREADS_);                                          \
-        else A3_LAUNCH_T(float, NH_, FULL_, BIG_, (R_) * 2, NEAR_, GRID_, THREADS_);                                           \
+        if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_);                                     \
+        else A3_LAUNCH_T(float, NH_, FULL_, BIG_, (R_) * 2, NEAR_, CL_, GRID_, THREADS_);                                      \
     } while (0)
     // ring geometry: rows R and hand-over distance NEAR (>= S3_AGG_NEAR, the distance the forest stage flags nodes by).
     // A warp may not run more than (R - NEAR) / W rounds ahead of the slowest one, so R - NEAR >= ~2 W.
-#define A3_DISPATCH(BIG_, RB_, NEARB_, GRID_, THREADS_)                                                 \
+#define A3_DISPATCH(BIG_, RB_, NEARB_, CL_, GRID_, THREADS_)                                            \
     do {                                                                                               \
         if (NH == 2) {                                                                                 \
-            if (full) A3_LAUNCH(2, true, BIG_, RB_ / 2, NEARB_, GRID_, THREADS_); else A3_LAUNCH(2, false, BIG_, RB_ / 2, NEARB_, GRID_, THREADS_); \
+            if (full) A3_LAUNCH(2, true, BIG_, RB_ / 2, NEARB_, CL_, GRID_, THREADS_); else A3_LAUNCH(2, false, BIG_, RB_ / 2, NEARB_, CL_, GRID_, THREADS_); \
         } else {                                                                                       \
-            if (full) A3_LAUNCH(1, true, BIG_, RB_, NEARB_, GRID_, THREADS_); else A3_LAUNCH(1, false, BIG_, RB_, NEARB_, GRID_, THREADS_); \
+            if (full) A3_LAUNCH(1, true, BIG_, RB_, NEARB_, CL_, GRID_, THREADS_); else A3_LAUNCH(1, false, BIG_, RB_, NEARB_, CL_, GRID_, THREADS_); \
         }                                                                                              \
     } while (0)
-    if (n_big) {
+    if (n_cl) {
+        S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        S3_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
+        launch_stream = ctx->stream_aux;
         A.unit0 = 0;
-        A3_DISPATCH(true, 256, 64, n_big, 1024);   // 128 KB ring, one tree per SM
+        A3_DISPATCH(true, 256, 64, A3_CLUSTER, n_cl * A3_CLUSTER, 1024);
+        S3_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
+        launch_stream = ctx->stream;
+    }
+    if (n_big) {
+        A.unit0 = n_cl;
+        A3_DISPATCH(true, 256, 64, 1, n_big, 1024);   // 128 KB ring, one tree per SM
     }
     if (n_small) {
-        A.unit0 = n_big;
-        A3_DISPATCH(false, 128, 32, n_small, 512);  // 64 KB ring: two trees per SM
+        A.unit0 = n_cl + n_big;
+        A3_DISPATCH(false, 128, 32, 1, n_small, 512);  // 64 KB ring: two trees per SM
     }
+    if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
 #undef A3_DISPATCH
 #undef A3_LAUNCH
 #undef A3_LAUNCH_T
@@ -679,8 +878,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         S3_CUDA(cudaEventRecord(ctx->ev_xctx, ctx->stream));
         for (int c = 1; c < nctx; c++) S3_CUDA(cudaStreamWaitEvent(ctxs[c]->stream, ctx->ev_xctx, 0));
     }
-    // No host synchronisation: the staging vectors above are pageable, so the asynchronous copies returned once their
-    // contents were staged; the callers queue the post-processing behind this launch while it runs.
+    // No host synchronisation: the unit list went through the context's pinned staging; the callers queue the
+    // post-processing behind this launch while it runs.
     for (int c = 0; c < nctx; c++)
         for (int view = 0; view < 2; view++)
             if (views_mask & (1 << view)) {
@@ -693,15 +892,18 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
 
 int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) { return s3_aggregate_flow_multi(&ctx, 1, views_mask, d0, d1); }
 
-// Proposal mode of the dataflow kernel: evaluates a tree-grouped proposal list (labels_dev [n][3] grouped by tree, order
-// inside a tree preserved; prop_off_dev [T+1]; h_prop_off = the same offsets on the host) on one view.  scratch_dev:
-// N * 64 doubles.  Returns 1 if it cannot serve the request (the caller then uses the simple kernel).
-int s3_pms_apply_flow(s3dmst_ctx* ctx, int view, const int* h_prop_off, const int* prop_off_dev, const float* labels_dev, double* scratch_dev) {
+// Proposal mode of the dataflow kernel.  Plan: the unit list (trees with work, longest first) and the view table, uploaded
+// once; launch: one evaluation of a tree-grouped proposal list (labels_dev [n][3] grouped by tree, order inside a tree
+// preserved; prop_off_dev [T+1]) on one view, optionally followed by the in-kernel refinement ladder (gen).
+// h_prop_off = the offsets on the host, or nullptr for "every tree" (the generator: every tree refines).
+// scratch_dev: N * 64 doubles.  Returns 1 if this kernel cannot serve the request (the caller then uses the simple one).
+int s3_pms_flow_plan(s3dmst_ctx* ctx, int view, const int* h_prop_off, double* scratch_dev, PmsFlowPlan* plan) {
     View& V = ctx->v[view];
     if (!ctx->P.exact) return 1;  // proposals are always evaluated in the reference's arithmetic
     std::vector<std::pair<int, int4>> u;
     for (int t = 0; t < V.T; t++)
-        if (h_prop_off[t + 1] > h_prop_off[t]) u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(0, t, 0, 0)});
+        if (!h_prop_off || h_prop_off[t + 1] > h_prop_off[t]) u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(0, t, 0, 0)});
+    memset(plan, 0, sizeof *plan);
     if (u.empty()) return 0;
     std::stable_sort(u.begin(), u.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     std::vector<int4> units(u.size());
@@ -718,38 +920,50 @@ int s3_pms_apply_flow(s3dmst_ctx* ctx, int view, const int* h_prop_off, const in
         ctx->units_cap = ubytes + tbytes;
     }
     char* ubase = reinterpret_cast<char*>(ctx->units_dev);
-    S3_CUDA(cudaMemcpyAsync(ubase, &G, sizeof G, cudaMemcpyHostToDevice, ctx->stream));
-    S3_CUDA(cudaMemcpyAsync(ubase + tbytes, units.data(), ubytes, cudaMemcpyHostToDevice, ctx->stream));
+    S3_TRY(s3_h2d_staged(ctx, ubase, &G, sizeof G));
+    S3_TRY(s3_h2d_staged(ctx, ubase + tbytes, units.data(), ubytes));
+    const int cl_nodes = s3_agg_cluster_nodes(ctx), big_nodes = s3_agg_big_nodes();
+    int n_cl = 0;
+    while (cl_nodes > 0 && n_cl < (int)u.size() && u[n_cl].first >= cl_nodes) n_cl++;
+    int n_big = n_cl;
+    while (n_big < (int)u.size() && u[n_big].first >= big_nodes) n_big++;
+    plan->n_cl = n_cl; plan->n_big = n_big - n_cl; plan->n_small = (int)u.size() - n_big;
+    plan->views_dev = ubase; plan->units_dev = ubase + tbytes;
+    return 0;
+}
+
+int s3_pms_flow_launch(s3dmst_ctx* ctx, int view, const PmsFlowPlan* plan, const int* prop_off_dev, const float* labels_dev, int gen, uint32_t seed, uint32_t round) {
+    View& V = ctx->v[view];
+    const int n_cl = plan->n_cl, n_big = plan->n_big, n_small = plan->n_small;
+    if (n_cl + n_big + n_small == 0) return 0;
     Agg3Args A;
     memset(&A, 0, sizeof A);
-    A.views = reinterpret_cast<const Agg3View*>(ubase);
-    A.units = reinterpret_cast<const int4*>(ubase + tbytes);
+    A.views = reinterpret_cast<const Agg3View*>(plan->views_dev);
+    A.units = reinterpret_cast<const int4*>(plan->units_dev);
     A.Dp = V.Dp; A.d1 = 0; A.N = ctx->N; A.n_slices = 1;
     A.lut_w = ctx->lut_w; A.lut_w2 = ctx->lut_w2;
     A.keep = 0;
     A.sleep_ns = 20;
     A.prop_off = prop_off_dev; A.labels = labels_dev; A.min_cost = V.min_cost; A.abc = V.abc;
     A.img_w = ctx->W; A.D = V.D; A.oob = ctx->P.oob_cost;
-    static const int big_nodes = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
-    int n_big = 0;
-    while (n_big < (int)u.size() && u[n_big].first >= big_nodes) n_big++;
-    const int n_small = (int)u.size() - n_big;
+    A.gen = gen; A.seed = seed; A.round = round; A.refine_floor = ctx->P.refine_floor;
     S3_EV_BEGIN(S3DMST_T_PMS, view);
-    if (n_big) {
-        const size_t smem = agg3_smem_bytes(1, 256, sizeof(double));
-        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<double, 1, false, true, 256, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_cl) {
+        S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        S3_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
         A.unit0 = 0;
-        k_agg_flow<double, 1, false, true, 256, 64, true><<<n_big, 1024, smem, ctx->stream>>>(A);
-        S3_LAUNCH_CHECK();
+        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, 64, true, A3_CLUSTER>, n_cl * A3_CLUSTER, 1024, agg3_smem_bytes(1, 256, sizeof(double)), A3_CLUSTER, ctx->stream_aux, A));
+        S3_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
+    }
+    if (n_big) {
+        A.unit0 = n_cl;
+        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, 64, true, 1>, n_big, 1024, agg3_smem_bytes(1, 256, sizeof(double)), 1, ctx->stream, A));
     }
     if (n_small) {
-        const size_t smem = agg3_smem_bytes(1, 128, sizeof(double));
-        S3_CUDA(cudaFuncSetAttribute(k_agg_flow<double, 1, false, false, 128, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        A.unit0 = n_big;
-        k_agg_flow<double, 1, false, false, 128, 32, true><<<n_small, 512, smem, ctx->stream>>>(A);
-        S3_LAUNCH_CHECK();
+        A.unit0 = n_cl + n_big;
+        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, false, 128, 32, true, 1>, n_small, 512, agg3_smem_bytes(1, 128, sizeof(double)), 1, ctx->stream, A));
     }
+    if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     S3_EV_END(S3DMST_T_PMS, view);
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging (units) is read by the async copy above
     return 0;
 }

@@ -25,6 +25,44 @@ int s3_fail(s3dmst_ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 
+
+// Small host -> device metadata copies (unit lists, tree offsets, proposal lists) go through a pinned arena owned by the
+// context: the copy is truly asynchronous and its source may die when this returns.  Two halves, each guarded by an
+// event recorded behind the last copy queued from it; a half is reused only after its event has completed.
+int s3_h2d_staged(s3dmst_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!bytes) return 0;
+    const size_t need = (bytes + 255) / 256 * 256;
+    if (need > ctx->stage_half) {  // (re)allocate: everything queued so far has to finish first
+        S3_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->stage) S3_CUDA(cudaFreeHost(ctx->stage));
+        ctx->stage = nullptr;
+        size_t half = std::max<size_t>(1 << 20, ctx->stage_half);
+        while (half < need) half *= 2;
+        S3_CUDA(cudaHostAlloc(&ctx->stage, 2 * half, cudaHostAllocDefault));
+        ctx->stage_half = half;
+        ctx->stage_used = 0;
+        ctx->stage_cur = 0;
+        ctx->stage_pending[0] = ctx->stage_pending[1] = false;
+        for (int i = 0; i < 2; i++)
+            if (!ctx->stage_ev[i]) S3_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    }
+    if (ctx->stage_used + need > ctx->stage_half) {  // this half is full: mark it, move to the other one once it has drained
+        S3_CUDA(cudaEventRecord(ctx->stage_ev[ctx->stage_cur], ctx->stream));
+        ctx->stage_pending[ctx->stage_cur] = true;
+        ctx->stage_cur ^= 1;
+        if (ctx->stage_pending[ctx->stage_cur]) {
+            S3_CUDA(cudaEventSynchronize(ctx->stage_ev[ctx->stage_cur]));
+            ctx->stage_pending[ctx->stage_cur] = false;
+        }
+        ctx->stage_used = 0;
+    }
+    char* p = ctx->stage + (size_t)ctx->stage_cur * ctx->stage_half + ctx->stage_used;
+    memcpy(p, src_host, bytes);
+    ctx->stage_used += need;
+    S3_CUDA(cudaMemcpyAsync(dst_dev, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
 static thread_local std::string g_create_err;
 
 template <class T>
@@ -48,6 +86,7 @@ static void free_view(View& V) {
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
+    DFREE(V.adj_ptr); DFREE(V.adj); V.adj_ptr_cap = V.adj_cap = 0; V.n_adj = 0; V.adj_ready = false;
     V.forest_ready = V.cost_ready = V.agg_ready = V.labels_ready = false;
     V.T = 0; V.D = V.Dp = 0;
 }
@@ -106,6 +145,7 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->agg_kernel = 0;
     p->fh_ctas = 0;
     p->fh_threads = 0;
+    p->agg_cluster_nodes = 0;
 }
 
 int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream) {
@@ -134,6 +174,9 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
     }
     for (int i = 0; ok && i < S3DMST_T_COUNT * 4; i++) ok = cudaEventCreate(&ctx->ev[i / 4][(i / 2) & 1][i & 1]) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_xctx, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     if (ok) {
         // weights (Stereo3DMST.cpp:444, :513): exp(-w*gamma) in double with gamma promoted from float
@@ -167,12 +210,18 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
     s3_rectify_free(ctx);
-    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev); DFREE(ctx->fh_sync);
+    DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev); DFREE(ctx->fh_sync); DFREE(ctx->abc_init);
     for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
         if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
     if (ctx->ev_xctx) cudaEventDestroy(ctx->ev_xctx);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream_aux) { cudaStreamSynchronize(ctx->stream_aux); cudaStreamDestroy(ctx->stream_aux); }
     if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (int i = 0; i < 2; i++)
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -259,27 +308,15 @@ int s3dmst_build_forest(s3dmst_ctx* ctx, int view) {
 
 int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth, int* adj_size);
 
-// host-side tree adjacency for dumps (Stereo3DMST.cpp:377-384): unique neighbours, ascending
+// tree adjacency for dumps (Stereo3DMST.cpp:377-384): the device CSR (pms.cu) copied to the host
 static int host_adjacency(s3dmst_ctx* ctx, int view, std::vector<int>& adj_ptr, std::vector<int>& adj) {
     View& V = ctx->v[view];
-    const int N = ctx->N, W = ctx->W, H = ctx->H;
-    std::vector<int> tid(N);
-    S3_CUDA(cudaMemcpyAsync(tid.data(), V.tree_id, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_TRY(s3_tree_adjacency(ctx, view));
+    adj_ptr.resize(V.T + 1);
+    adj.resize(V.n_adj);
+    S3_CUDA(cudaMemcpyAsync(adj_ptr.data(), V.adj_ptr, sizeof(int) * (V.T + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (V.n_adj) S3_CUDA(cudaMemcpyAsync(adj.data(), V.adj, sizeof(int) * V.n_adj, cudaMemcpyDeviceToHost, ctx->stream));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<std::vector<int>> nb(V.T);
-    for (int p = 0; p < N; p++) {
-        const int x = p % W, y = p / W;
-        if (x < W - 1 && tid[p] != tid[p + 1]) { nb[tid[p]].push_back(tid[p + 1]); nb[tid[p + 1]].push_back(tid[p]); }
-        if (y < H - 1 && tid[p] != tid[p + W]) { nb[tid[p]].push_back(tid[p + W]); nb[tid[p + W]].push_back(tid[p]); }
-    }
-    adj_ptr.assign(V.T + 1, 0);
-    adj.clear();
-    for (int t = 0; t < V.T; t++) {
-        std::sort(nb[t].begin(), nb[t].end());
-        nb[t].erase(std::unique(nb[t].begin(), nb[t].end()), nb[t].end());
-        adj.insert(adj.end(), nb[t].begin(), nb[t].end());
-        adj_ptr[t + 1] = (int)adj.size();
-    }
     return 0;
 }
 
@@ -293,9 +330,9 @@ int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth
         *max_depth = V.max_depth;
     }
     if (adj_size) {
-        std::vector<int> ap, a;
-        S3_TRY(host_adjacency(ctx, view, ap, a));
-        *adj_size = (int)a.size();
+        S3_CUDA(cudaSetDevice(ctx->device));
+        S3_TRY(s3_tree_adjacency(ctx, view));
+        *adj_size = V.n_adj;
     }
     return 0;
 }
@@ -529,9 +566,11 @@ int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view) {
 
 int s3dmst_set_labels(s3dmst_ctx* ctx, int view, const float* abc) {
     if (view < 0 || view > 1 || !abc || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "set_labels: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
     S3_CUDA(cudaMemcpyAsync(ctx->v[view].abc, abc, sizeof(float) * 3 * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->v[view].labels_ready = true;
+    ctx->pms_round[view] = 0;
     return 0;
 }
 int s3dmst_get_labels(s3dmst_ctx* ctx, int view, float* abc) {
@@ -543,6 +582,7 @@ int s3dmst_get_labels(s3dmst_ctx* ctx, int view, float* abc) {
 int s3dmst_reset_min_cost(s3dmst_ctx* ctx, int view) {
     if (view < 0 || view > 1 || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     std::vector<double> h(ctx->N, DBL_MAX);  // Stereo3DMST.cpp:820-821
+    S3_CUDA(cudaSetDevice(ctx->device));
     S3_CUDA(cudaMemcpyAsync(ctx->v[view].min_cost, h.data(), sizeof(double) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -571,9 +611,7 @@ int s3dmst_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed) {
     S3_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->v[view].forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: no forest");
     if (!ctx->v[view].labels_ready) S3_TRY(s3_init_labels(ctx, view, ctx->v[view].D));  // :390-430
-    std::vector<int> adj_ptr, adj;
-    S3_TRY(host_adjacency(ctx, view, adj_ptr, adj));
-    return s3_pms_iterate(ctx, view, n_iter, seed, adj_ptr, adj);
+    return s3_pms_iterate(ctx, view, n_iter, seed);
 }
 
 int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view) {
@@ -621,6 +659,34 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
         if (rc) return rc;
     }
     for (int view = 0; view < 2; view++) S3_TRY(s3_dense_to_disp(ctx, view));
+    S3_TRY(s3_lr_check(ctx, fill));
+    D2H(left_disp, ctx->v[0].disp_f, sizeof(float) * ctx->N);
+    D2H(right_disp, ctx->v[1].disp_f, sizeof(float) * ctx->N);
+    if (left_disp || right_disp) S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// The reference's own pipeline (stereo3dmst, Stereo3DMST.cpp:805-904) on the current images: forests, random plane
+// initialisation (:390-430), num_iter rounds of MST_PMS per view (:858-889), LabelToDisp (:189-201, :900-902) and the
+// left-right check (:904; the reference passes fill = false).  Cost volumes set with s3dmst_set_cost_volume (the
+// reference's mc-cnn input) are used as they are; without them the a2' volume is built and ingested.  Everything
+// after the forests is queued without host synchronisation.
+int s3dmst_run(s3dmst_ctx* ctx, int Dmax, unsigned seed, int fill, float* left_disp, float* right_disp) {
+    if (ctx->N == 0 || Dmax <= 0) return s3_fail(ctx, S3DMST_E_ARG, "run: images and Dmax > 0 required");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->P.exact) return s3_fail(ctx, S3DMST_E_ARG, "run: the proposal search runs in the exact mode only");
+    memset(ctx->ev_set, 0, sizeof ctx->ev_set);
+    if (!ctx->v[0].forest_ready || !ctx->v[1].forest_ready) {
+        S3_EV_BEGIN(S3DMST_T_FOREST, 0);
+        S3_TRY(s3_forest_stage_mask(ctx, 3));
+        S3_EV_END(S3DMST_T_FOREST, 0);
+    }
+    if (!ctx->v[0].cost_ready || !ctx->v[1].cost_ready || ctx->v[0].D != Dmax || ctx->v[1].D != Dmax) S3_TRY(s3_cost_adgrad(ctx, Dmax, 1));
+    for (int view = 0; view < 2; view++) {
+        S3_TRY(s3_init_labels(ctx, view, Dmax));
+        S3_TRY(s3_pms_iterate(ctx, view, ctx->P.num_iter, seed));
+        S3_TRY(s3_label_to_disp(ctx, view));
+    }
     S3_TRY(s3_lr_check(ctx, fill));
     D2H(left_disp, ctx->v[0].disp_f, sizeof(float) * ctx->N);
     D2H(right_disp, ctx->v[1].disp_f, sizeof(float) * ctx->N);

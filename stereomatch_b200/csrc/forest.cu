@@ -971,6 +971,7 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
         if (mask & (1 << view)) {
             View& V = ctx->v[view];
             V.max_depth = -1;  // tree depths stay on the device until somebody asks (s3_forest_finalize_host)
+            V.adj_ready = false;
             V.forest_ready = true;
             V.cost_ready = false;
             V.agg_ready = false;
@@ -1009,6 +1010,7 @@ int s3_forest_finalize_host(s3dmst_ctx* ctx, int view) {
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     V.max_depth = 0;
     for (int d : V.h_tree_depth) V.max_depth = std::max(V.max_depth, d);
+    V.adj_ready = false;
     V.forest_ready = true;
     V.cost_ready = false;
     V.agg_ready = false;

@@ -93,3 +93,56 @@ S3_HD float s3_label_disp(float a, float b, float c, int x, int y, int max_disp)
     v = 0.0f < v ? v : 0.0f;          // MAX(0.0f, v)
     return S3_FMUL(v, (float)max_disp - 1.0f);
 }
+
+// ---- proposal generator of s3dmst_pms_iterate / s3dmst_run (MST_PMS, Stereo3DMST.cpp:546-629).
+// The reference draws from one sequential minstd_rand0 stream (and std::rand) whose position depends on every earlier
+// tree's data: unusable in parallel, and parity for this stage is by proposal injection.  The library's own
+// generator is counter based: draw (seed, round, tree, slot) is a pure function, so any tree can be generated anywhere.
+S3_HD uint64_t s3_mix64(uint64_t z) {  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+S3_HD uint32_t s3_rng(uint32_t seed, uint32_t round, uint32_t tree, uint32_t slot) {
+    const uint64_t a = s3_mix64(((uint64_t)seed << 32 | round) + 0x9E3779B97F4A7C15ull);
+    return (uint32_t)(s3_mix64(a ^ ((uint64_t)tree << 32 | slot)) >> 32);
+}
+S3_HD float s3_rng_unit(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }           // U[0,1), 24 bits, exact
+S3_HD float s3_rng_sym(uint32_t r) { return S3_FSUB(S3_FMUL(2.0f, s3_rng_unit(r)), 1.0f); }         // U[-1,1), exact
+#define S3_SLOT_REFINE_PIXEL 0x80000000u   // slot of the refinement pixel draw; ladder step k draws slots 0x40000000 + 4k .. + 3
+#define S3_SLOT_LADDER 0x40000000u
+#define S3_MAX_LADDER 64
+
+// index of the sampled pixel inside a tree of `size` pixels: (int)((dice+1)*0.5*size) of :569 with the Q11 clamp
+S3_HD int s3_sample_index(uint32_t r, int size) {
+    const int i = (int)S3_FMUL(s3_rng_unit(r), (float)size);
+    return i < size - 1 ? i : size - 1;
+}
+
+// RANDOM REFINEMENT ladder (:584-625) around label (a, b, c) of pixel (px, py): max_d = Dmax/2, /2, ... > floor with
+// max_n = 1, 1/2, ...; step k is skipped when its disparity leaves [0, Dmax] (:602).  Writes up to S3_MAX_LADDER
+// labels to out[3*i..], returns their number.  fp32 throughout, every operation individually rounded.
+S3_HD int s3_refine_ladder(float a, float b, float c, float px, float py, int max_disp, float floor_d, uint32_t seed, uint32_t round,
+                           uint32_t tree, float* out) {
+    const float nz = 1.0f / sqrtf(S3_FADD(S3_FADD(S3_FMUL(a, a), S3_FMUL(b, b)), 1.0f));
+    const float nx = S3_FMUL(-a, nz), ny = S3_FMUL(-b, nz);
+    const float d = S3_FADD(S3_FADD(S3_FMUL(px, a), S3_FMUL(py, b)), c);
+    float max_n = 1.0f, max_d = S3_FMUL(0.5f, (float)max_disp);
+    int n = 0;
+    for (uint32_t k = 0; max_d > floor_d && k < S3_MAX_LADDER; k++, max_d = S3_FMUL(max_d, 0.5f), max_n = S3_FMUL(max_n, 0.5f)) {
+        const float rd = S3_FADD(d, S3_FMUL(s3_rng_sym(s3_rng(seed, round, tree, S3_SLOT_LADDER + 4 * k)), max_d));
+        if (rd < 0.0f || rd > (float)max_disp) continue;
+        float rx = S3_FADD(nx, S3_FMUL(s3_rng_sym(s3_rng(seed, round, tree, S3_SLOT_LADDER + 4 * k + 1)), max_n));
+        float ry = S3_FADD(ny, S3_FMUL(s3_rng_sym(s3_rng(seed, round, tree, S3_SLOT_LADDER + 4 * k + 2)), max_n));
+        float rz = S3_FADD(nz, S3_FMUL(s3_rng_sym(s3_rng(seed, round, tree, S3_SLOT_LADDER + 4 * k + 3)), max_n));
+        const float inv = 1.0f / sqrtf(S3_FADD(S3_FADD(S3_FMUL(rx, rx), S3_FMUL(ry, ry)), S3_FMUL(rz, rz)));
+        rx = S3_FMUL(rx, inv);
+        ry = S3_FMUL(ry, inv);
+        rz = fabsf(S3_FMUL(rz, inv));
+        out[3 * n] = -rx / rz;
+        out[3 * n + 1] = -ry / rz;
+        out[3 * n + 2] = S3_FADD(S3_FADD(S3_FMUL(rx, px), S3_FMUL(ry, py)), S3_FMUL(rz, rd)) / rz;
+        n++;
+    }
+    return n;
+}

@@ -73,7 +73,12 @@ struct View {
     int4* tile_desc = nullptr;  // [4N] ([0,2N) root->leaf order, [2N,4N) leaf->root order); two int4 per tile: {t0, n, loff, flags}, {level end, parent level start, 0, 0};
                                 //      tree t's tiles start at tile index tree_start[t], level-major, ascending nodes
     int* tree_ntiles = nullptr; // [T]
-    // tree adjacency (host side, built lazily for dumps / proposal generation)
+    // tree adjacency graph (Stereo3DMST.cpp:377-384) as a device CSR, built lazily (proposal generation, parity dumps)
+    int* adj_ptr = nullptr;     // [T+1]
+    int* adj = nullptr;         // [n_adj] neighbours of tree t: adj[adj_ptr[t] .. adj_ptr[t+1]), ascending
+    size_t adj_ptr_cap = 0, adj_cap = 0;
+    int n_adj = 0;
+    bool adj_ready = false;
     std::vector<int> h_tree_start, h_tree_depth, h_unit_tree;
     bool forest_ready = false;
     // ---- volumes
@@ -101,6 +106,8 @@ struct s3dmst_ctx {
     s3dmst_params P;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream_aux = nullptr;   // second stream: the cluster launch of the giant trees runs beside the other trees' launches
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int W = 0, H = 0, N = 0;
     int num_sms = 0;
     View v[2];
@@ -118,11 +125,19 @@ struct s3dmst_ctx {
     cudaEvent_t ev_block = nullptr; // blocking-sync event: batched contexts SLEEP through the forest kernel instead of spinning
     int* h_pin = nullptr;           // pinned staging for the forest stage's host round trip
     size_t h_pin_cap = 0;           // ints
+    char* stage = nullptr;          // pinned staging arena of s3_h2d_staged: two halves, each guarded by an event
+    size_t stage_half = 0, stage_used = 0;
+    int stage_cur = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_pending[2] = {false, false};
     uint32_t* units_dev = nullptr;  // aggregation work units + view table of the current launch
     size_t units_cap = 0;
     int* fh_sync = nullptr;         // grid barrier + per-round live counters of the forest kernel
     void* pms_scratch = nullptr;
     size_t pms_scratch_cap = 0;
+    float* abc_init = nullptr;      // the reference's random plane initialisation for (abc_init_w x abc_init_h, abc_init_d), kept on the device
+    int abc_init_w = 0, abc_init_h = 0, abc_init_d = 0;
+    uint32_t pms_round[2] = {0, 0};  // rounds of the library's generator run since the view's labels were (re)set: the RNG counter
     // rectification front-end (rectify.cu): per-view fixed-point maps, the weight table, staging for the raw pair
     int16_t* map_xy[2] = {nullptr, nullptr};    // [mh][mw][2] integer source corner (x, y)
     uint16_t* map_fxy[2] = {nullptr, nullptr};  // [mh][mw] fy * 32 + fx
@@ -185,11 +200,21 @@ int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
 int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined, level-synchronous tiles)
 int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1);    // aggregate3.cu (dataflow, default)
-int s3_pms_apply_flow(s3dmst_ctx* ctx, int view, const int* h_prop_off, const int* prop_off_dev, const float* labels_dev, double* scratch_dev);
+struct PmsFlowPlan {   // aggregate3.cu: unit list of a proposal-mode launch, uploaded once and reused by every round
+    int n_cl, n_big, n_small;
+    const void* views_dev;
+    const void* units_dev;
+};
+int s3_pms_flow_plan(s3dmst_ctx* ctx, int view, const int* h_prop_off, double* scratch_dev, PmsFlowPlan* plan);
+int s3_pms_flow_launch(s3dmst_ctx* ctx, int view, const PmsFlowPlan* plan, const int* prop_off_dev, const float* labels_dev, int gen, uint32_t seed, uint32_t round);
+// Host -> device copy of small metadata through the context's pinned staging arena (api.cu): truly asynchronous, and the
+// source may die as soon as the call returns.
+int s3_h2d_staged(s3dmst_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int s3_tree_adjacency(s3dmst_ctx* ctx, int view);   // pms.cu: device CSR of the tree adjacency graph (lazy)
 int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1);  // one launch over several frames
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
 int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax);          // pms.cu: the reference's random plane initialisation
-int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed, const std::vector<int>& adj_ptr, const std::vector<int>& adj);
+int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed);
 int s3_label_to_disp(s3dmst_ctx* ctx, int view);                  // post.cu
 int s3_dense_to_disp(s3dmst_ctx* ctx, int view);
 int s3_lr_check(s3dmst_ctx* ctx, int fill);

@@ -19,6 +19,7 @@
 #include "internal.h"
 
 #define PMS_KB 32
+#define CNT_ADJ_ERR (S3_MAX_ROUNDS - 40)   // View::counters slot of the adjacency builder's overflow flag
 
 struct PmsArgs {
     int W, D, Dp;
@@ -128,6 +129,26 @@ __global__ void __launch_bounds__(256) k_pms(PmsArgs A) {
     }
 }
 
+// scratch of the proposal kernels: [N][64] doubles + the label list + the offsets
+static int pms_scratch(s3dmst_ctx* ctx, size_t n_labels, int T, double** scr, float** d_lab, int** d_off) {
+    const size_t scr_bytes = (size_t)ctx->N * 64 * sizeof(double);  // [node][64] (dataflow kernel) / [node][PMS_KB] (simple kernel)
+    const size_t lab_bytes = (3 * n_labels * sizeof(float) + 255) / 256 * 256;
+    const size_t off_bytes = ((size_t)(T + 1) * sizeof(int) + 255) / 256 * 256;
+    if (ctx->pms_scratch_cap < scr_bytes + lab_bytes + off_bytes) {
+        const size_t lab_cap = std::max<size_t>(lab_bytes, 1 << 20) * 2;  // head-room: the proposal count changes from round to round
+        const size_t need = scr_bytes + lab_cap + off_bytes;
+        if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
+        ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
+        S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
+        ctx->pms_scratch_cap = need;
+    }
+    char* basep = (char*)ctx->pms_scratch;
+    *scr = (double*)basep;
+    *d_lab = (float*)(basep + scr_bytes);
+    *d_off = (int*)(basep + ctx->pms_scratch_cap - off_bytes);
+    return 0;
+}
+
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n) {
     View& V = ctx->v[view];
     if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
@@ -150,27 +171,15 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
             lab[3 * (size_t)pos + 2] = h_labels[3 * i + 2];
         }
     }
-    const size_t scr_bytes = (size_t)ctx->N * 64 * sizeof(double);  // [node][64] (dataflow kernel) / [node][PMS_KB] (simple kernel)
-    const size_t lab_bytes = (3 * n * sizeof(float) + 255) / 256 * 256;
-    const size_t off_bytes = ((T + 1) * sizeof(int) + 255) / 256 * 256;
-    const size_t lab_cap = std::max<size_t>(lab_bytes, 1 << 20) * 2;  // head-room: the proposal count changes from round to round
-    const size_t need = scr_bytes + lab_cap + off_bytes;
-    if (ctx->pms_scratch_cap < scr_bytes + lab_bytes + off_bytes) {
-        if (ctx->pms_scratch) S3_CUDA(cudaFree(ctx->pms_scratch));
-        ctx->pms_scratch = nullptr; ctx->pms_scratch_cap = 0;
-        S3_CUDA(cudaMalloc(&ctx->pms_scratch, need));
-        ctx->pms_scratch_cap = need;
-    }
-    char* basep = (char*)ctx->pms_scratch;
-    double* scr = (double*)basep;
-    float* d_lab = (float*)(basep + scr_bytes);
-    int* d_off = (int*)(basep + ctx->pms_scratch_cap - off_bytes);
-    S3_CUDA(cudaMemcpyAsync(d_lab, lab.data(), 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    S3_CUDA(cudaMemcpyAsync(d_off, off.data(), (T + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    double* scr; float* d_lab; int* d_off;
+    S3_TRY(pms_scratch(ctx, n, T, &scr, &d_lab, &d_off));
+    S3_TRY(s3_h2d_staged(ctx, d_lab, lab.data(), 3 * n * sizeof(float)));
+    S3_TRY(s3_h2d_staged(ctx, d_off, off.data(), (T + 1) * sizeof(int)));
 
-    static const bool simple = getenv("S3_PMS_SIMPLE") && atoi(getenv("S3_PMS_SIMPLE")) != 0;
-    if (!simple) {
-        const int r = s3_pms_apply_flow(ctx, view, off.data(), d_off, d_lab, scr);
+    if (ctx->P.agg_kernel != 1) {  // default: the dataflow kernel's proposal mode
+        PmsFlowPlan plan;
+        const int r = s3_pms_flow_plan(ctx, view, off.data(), scr, &plan);
+        if (r == 0) return s3_pms_flow_launch(ctx, view, &plan, d_off, d_lab, 0, 0u, 0u);
         if (r != 1) return r;
     }
     PmsArgs A;
@@ -186,7 +195,138 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
     k_pms<<<T, 256, smem, ctx->stream>>>(A);
     S3_LAUNCH_CHECK();
     S3_EV_END(S3DMST_T_PMS, view);
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tree adjacency graph on the device (tree_g, Stereo3DMST.cpp:377-384: two trees are neighbours iff a grid edge
+// joins them; adjacent_vertices iterates a setS, i.e. ascending tree id).  Built once per forest:
+//   1. every boundary grid edge inserts its two directed pairs into an open-addressing hash set (duplicates collapse)
+//      and a first insertion counts towards the degree of its source tree;
+//   2. exclusive scan of the degrees -> CSR offsets;  3. the set's entries are dealt to their rows;
+//   4. every row is rank-sorted (keys are unique).
+// Scratch: the forest kernel's live-edge lists (idle after the forest is built).
+__device__ __forceinline__ void adj_insert(unsigned long long* table, unsigned mask, int a, int b, int* deg, int* err) {
+    const unsigned long long key = (((unsigned long long)(unsigned)a << 32) | (unsigned)b) + 1ull;  // 0 = empty slot
+    unsigned h = (unsigned)(s3_mix64(key) >> 32) & mask;
+    for (int probe = 0; probe < 4096; probe++) {
+        const unsigned long long old = atomicCAS(table + h, 0ull, key);
+        if (old == 0ull) { atomicAdd(deg + a, 1); return; }
+        if (old == key) return;
+        h = (h + 1) & mask;
+    }
+    *err = 1;
+}
+__global__ void k_adj_insert(int W, int H, const int* __restrict__ tree_id, unsigned long long* table, unsigned mask, int* deg, int* err) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int x = p % W, y = p / W, t = tree_id[p];
+    // a pair repeated along a straight boundary is inserted once per run (the previous pixel of the row / column saw it)
+    if (x < W - 1) {
+        const int u = tree_id[p + 1];
+        if (u != t && !(y > 0 && tree_id[p - W] == t && tree_id[p - W + 1] == u)) { adj_insert(table, mask, t, u, deg, err); adj_insert(table, mask, u, t, deg, err); }
+    }
+    if (y < H - 1) {
+        const int u = tree_id[p + W];
+        if (u != t && !(x > 0 && tree_id[p - 1] == t && tree_id[p + W - 1] == u)) { adj_insert(table, mask, t, u, deg, err); adj_insert(table, mask, u, t, deg, err); }
+    }
+}
+// single-CTA exclusive scan of deg[0..T) into ptr[0..T]; also resets deg (reused as the fill cursor)
+__global__ void __launch_bounds__(1024) k_adj_scan(int T, int* deg, int* ptr) {
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int b = 0; b < T; b += 1024) {
+        const int i = b + tid;
+        const int v = i < T ? deg[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_w[lane], winc = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += u;
+            }
+            s_w[lane] = winc - w;
+        }
+        __syncthreads();
+        const int run = s_run;
+        if (i < T) { ptr[i] = run + s_w[wid] + inc - v; deg[i] = 0; }
+        __syncthreads();
+        if (tid == 1023) s_run = run + s_w[31] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) ptr[T] = s_run;
+}
+__global__ void k_adj_fill(unsigned cap, const unsigned long long* __restrict__ table, const int* __restrict__ ptr, int* cursor, int* out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const unsigned long long key = table[i];
+    if (!key) return;
+    const int a = (int)((key - 1) >> 32), b = (int)(unsigned)(key - 1);
+    out[ptr[a] + atomicAdd(cursor + a, 1)] = b;
+}
+// one CTA per row: rank sort (the keys of a row are distinct)
+__global__ void __launch_bounds__(128) k_adj_sort(const int* __restrict__ ptr, const int* __restrict__ in, int* __restrict__ out) {
+    const int lo = ptr[blockIdx.x], n = ptr[blockIdx.x + 1] - lo;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int x = in[lo + i];
+        int r = 0;
+        for (int j = 0; j < n; j++) r += in[lo + j] < x;
+        out[lo + r] = x;
+    }
+}
+
+int s3_tree_adjacency(s3dmst_ctx* ctx, int view) {
+    View& V = ctx->v[view];
+    if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "tree adjacency: no forest");
+    if (V.adj_ready) return 0;
+    const int N = ctx->N, W = ctx->W, H = ctx->H, T = V.T;
+    unsigned cap = 1;
+    while ((size_t)cap * 2 * sizeof(unsigned long long) <= 32 * (size_t)N && cap < (1u << 30)) cap *= 2;  // largest power of two inside fh_ent[0]
+    cap = std::max(cap, 64u);  // (the buffers carry S3_FH_MAX_CTAS * 16 KB of slack: tiny images still fit)
+    unsigned long long* table = reinterpret_cast<unsigned long long*>(V.fh_ent[0]);
+    int* tmp = reinterpret_cast<int*>(V.fh_ent[1]);          // unsorted rows
+    int* deg = V.e_ra;                                        // [T] degrees, then fill cursors
+    int* err = V.counters + CNT_ADJ_ERR;
+    if (V.adj_ptr_cap < (size_t)T + 1) {
+        if (V.adj_ptr) S3_CUDA(cudaFree(V.adj_ptr));
+        V.adj_ptr = nullptr; V.adj_ptr_cap = 0;
+        S3_CUDA(cudaMalloc(&V.adj_ptr, sizeof(int) * ((size_t)T + 1)));
+        V.adj_ptr_cap = (size_t)T + 1;
+    }
+    S3_CUDA(cudaMemsetAsync(table, 0, (size_t)cap * sizeof(unsigned long long), ctx->stream));
+    S3_CUDA(cudaMemsetAsync(deg, 0, sizeof(int) * (size_t)T, ctx->stream));
+    S3_CUDA(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
+    k_adj_insert<<<(N + 255) / 256, 256, 0, ctx->stream>>>(W, H, V.tree_id, table, cap - 1, deg, err);
+    S3_LAUNCH_CHECK();
+    k_adj_scan<<<1, 1024, 0, ctx->stream>>>(T, deg, V.adj_ptr);
+    S3_LAUNCH_CHECK();
+    int h[2] = {0, 0};
+    S3_CUDA(cudaMemcpyAsync(&h[0], V.adj_ptr + T, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaMemcpyAsync(&h[1], err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));  // once per forest: the size of the CSR
+    if (h[1]) return s3_fail(ctx, S3DMST_E_LIMIT, "tree adjacency: hash set overflow");
+    if ((size_t)h[0] * sizeof(int) > 16 * (size_t)N + 1024) return s3_fail(ctx, S3DMST_E_LIMIT, "tree adjacency: %d entries exceed the scratch", h[0]);
+    V.n_adj = h[0];
+    if (V.adj_cap < (size_t)std::max(1, V.n_adj)) {
+        if (V.adj) S3_CUDA(cudaFree(V.adj));
+        V.adj = nullptr; V.adj_cap = 0;
+        S3_CUDA(cudaMalloc(&V.adj, sizeof(int) * (size_t)std::max(1, V.n_adj)));
+        V.adj_cap = (size_t)std::max(1, V.n_adj);
+    }
+    k_adj_fill<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(cap, table, V.adj_ptr, deg, tmp);
+    S3_LAUNCH_CHECK();
+    k_adj_sort<<<T, 128, 0, ctx->stream>>>(V.adj_ptr, tmp, V.adj);
+    S3_LAUNCH_CHECK();
+    V.adj_ready = true;
     return 0;
 }
 
@@ -200,102 +340,95 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
 #include <functional>
 #include <random>
 
+__global__ void k_fill_f64(int n, double v, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
 int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax) {
     View& V = ctx->v[view];
     const int W = ctx->W, H = ctx->H;
     if (ctx->N == 0 || Dmax <= 0) return s3_fail(ctx, S3DMST_E_ARG, "init_labels: images and Dmax > 0 required");
-    std::vector<float> abc(3 * (size_t)ctx->N);
-    std::default_random_engine engine;  // fresh engine per view (:390): both views draw the same stream
-    std::uniform_real_distribution<float> unit(0.0f, 1.0f);
-    size_t o = 0;
-    for (int y = 0; y < H; y++)
-        for (int x = 0; x < W; x++, o += 3) {
-            const float d = unit(engine) * Dmax;
-            float u, v, s;
-            do {  // (u, v) uniform in the positive quadrant of the unit disc (Q7)
-                u = unit(engine);
-                v = unit(engine);
-                s = u * u + v * v;
-            } while (!(s < 1.0f));
-            const float k = std::sqrt(1.0f - u * u - v * v);
-            const float nx = 2.0f * u * k, ny = 2.0f * v * k;
-            const float nz = std::sqrt(1.0f - nx * nx - ny * ny);
-            abc[o] = -nx / nz;
-            abc[o + 1] = -ny / nz;
-            abc[o + 2] = (nx * x + ny * y + nz * d) / nz;
-        }
-    S3_CUDA(cudaMemcpyAsync(V.abc, abc.data(), abc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<double> big(ctx->N, DBL_MAX);  // :820-821
-    S3_CUDA(cudaMemcpyAsync(V.min_cost, big.data(), big.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    // The stream depends only on (W, H, Dmax) — a fresh default engine per view (:390): both views, and every later
+    // call, draw the same labels.  The serial host loop (rejection sampling: the draw count per pixel is data
+    // dependent) therefore runs once per size and the result is kept on the device.
+    if (!ctx->abc_init || ctx->abc_init_w != W || ctx->abc_init_h != H || ctx->abc_init_d != Dmax) {
+        std::vector<float> abc(3 * (size_t)ctx->N);
+        std::default_random_engine engine;
+        std::uniform_real_distribution<float> unit(0.0f, 1.0f);
+        size_t o = 0;
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++, o += 3) {
+                const float d = unit(engine) * Dmax;
+                float u, v, s;
+                do {  // (u, v) uniform in the positive quadrant of the unit disc (Q7)
+                    u = unit(engine);
+                    v = unit(engine);
+                    s = u * u + v * v;
+                } while (!(s < 1.0f));
+                const float k = std::sqrt(1.0f - u * u - v * v);
+                const float nx = 2.0f * u * k, ny = 2.0f * v * k;
+                const float nz = std::sqrt(1.0f - nx * nx - ny * ny);
+                abc[o] = -nx / nz;
+                abc[o + 1] = -ny / nz;
+                abc[o + 2] = (nx * x + ny * y + nz * d) / nz;
+            }
+        if (ctx->abc_init) S3_CUDA(cudaFree(ctx->abc_init));
+        ctx->abc_init = nullptr;
+        S3_CUDA(cudaMalloc(&ctx->abc_init, abc.size() * sizeof(float)));
+        S3_CUDA(cudaMemcpyAsync(ctx->abc_init, abc.data(), abc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        S3_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->abc_init_w = W; ctx->abc_init_h = H; ctx->abc_init_d = Dmax;
+    }
+    S3_CUDA(cudaMemcpyAsync(V.abc, ctx->abc_init, 3 * (size_t)ctx->N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_fill_f64<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, DBL_MAX, V.min_cost);  // :820-821
+    S3_LAUNCH_CHECK();
     V.labels_ready = true;
+    ctx->pms_round[view] = 0;
     return 0;
 }
 
-// n_iter rounds of MST_PMS (:546-629) with the library's own generator.  Per round and per tree (ascending id):
-// one proposal per neighbouring tree (ascending id) = the label of a random pixel of that tree, then the
-// refinement ladder max_d = Dmax/2, /2, ... > refine_floor around a random pixel of the tree itself.  The "dice"
-// stream is a fresh default engine behind U(-1,1) in every round, as in the reference (std::bind copies, Q8).
-// Defined deviation (parity for this stage is by proposal injection): proposals of a round read the
-// labels as they were when the round started (the serial reference lets tree t see what trees < t changed in
-// the same round; its own OpenMP build already races on exactly that, Q13), and the refinement pixel comes from
-// a seeded mt19937 instead of the unseeded process-global std::rand() (Q6/Q9).
-int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed, const std::vector<int>& adj_ptr, const std::vector<int>& adj) {
+// SPATIAL PROPAGATION proposals of one round (:563-574): for every tree, the label of one random pixel of each neighbouring
+// tree (ascending id), read from the labels as they stand when the round starts.  One thread per CSR entry.
+__global__ void k_pms_gen_prop(int T, const int* __restrict__ adj_ptr, const int* __restrict__ adj, const int* __restrict__ tree_start,
+                               const int* __restrict__ node_pixel, const float* __restrict__ abc, uint32_t seed, uint32_t round, float* __restrict__ labels) {
+    const int t = blockIdx.x;
+    const int lo = adj_ptr[t], n = adj_ptr[t + 1] - lo;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int nb = adj[lo + j];
+        const int b = tree_start[nb], sz = tree_start[nb + 1] - b;
+        const int pix = node_pixel[b + s3_sample_index(s3_rng(seed, round, (uint32_t)t, (uint32_t)j), sz)];
+        labels[3 * (size_t)(lo + j)] = abc[3 * (size_t)pix];
+        labels[3 * (size_t)(lo + j) + 1] = abc[3 * (size_t)pix + 1];
+        labels[3 * (size_t)(lo + j) + 2] = abc[3 * (size_t)pix + 2];
+    }
+}
+
+// n_iter rounds of MST_PMS (:546-629) with the library's own generator, entirely on the device: per round one small
+// kernel gathers the propagation proposals (one per neighbouring tree, ascending id = the label of a random pixel of
+// that tree), then the proposal kernel evaluates them tree by tree and, still inside the kernel, generates and
+// evaluates the refinement ladder max_d = Dmax/2, /2, ... > refine_floor around a random pixel of the tree itself,
+// read AFTER the tree's propagation proposals were applied, as in the reference (:584-595).  No host synchronisation
+// between rounds.  Defined deviations (parity for this stage is by proposal injection): propagation
+// proposals read the labels as they were when the round started (the serial reference lets tree t see what trees < t
+// changed in the same round; its own OpenMP build races on exactly that, Q13); the random numbers come from a
+// counter-based generator (hd_math.h: s3_rng) instead of the sequential minstd_rand0 / unseeded std::rand() streams
+// (Q6/Q8/Q9), and a "random pixel of a tree" indexes the tree's BFS order instead of its raster order.
+int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed) {
     View& V = ctx->v[view];
     if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
         return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: forest, cost volume and labels required");
-    const int N = ctx->N, W = ctx->W, T = V.T, Dmax = V.D;
-    std::vector<int> tid(N);
-    S3_CUDA(cudaMemcpyAsync(tid.data(), V.tree_id, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> tstart(T + 1, 0), tpix(N);  // pixels of every tree in raster order (:352-367)
-    for (int p = 0; p < N; p++) tstart[tid[p] + 1]++;
-    for (int t = 0; t < T; t++) tstart[t + 1] += tstart[t];
-    {
-        std::vector<int> cur(tstart.begin(), tstart.end() - 1);
-        for (int p = 0; p < N; p++) tpix[cur[tid[p]]++] = p;
-    }
-    std::vector<float> abc(3 * (size_t)N), labels;
-    std::vector<int32_t> trees;
-    std::mt19937 pick(seed);
+    if (!ctx->P.exact) return s3_fail(ctx, S3DMST_E_ARG, "pms_iterate: proposals are evaluated in the exact mode only");
+    S3_TRY(s3_tree_adjacency(ctx, view));
+    double* scr; float* d_lab; int* d_off;
+    S3_TRY(pms_scratch(ctx, (size_t)V.n_adj, V.T, &scr, &d_lab, &d_off));
+    PmsFlowPlan plan;
+    S3_TRY(s3_pms_flow_plan(ctx, view, nullptr, scr, &plan));
     for (int it = 0; it < n_iter; it++) {
-        S3_CUDA(cudaMemcpyAsync(abc.data(), V.abc, abc.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        S3_CUDA(cudaStreamSynchronize(ctx->stream));
-        std::default_random_engine engine;
-        std::uniform_real_distribution<float> sym(-1.0f, 1.0f);
-        trees.clear();
-        labels.clear();
-        auto push = [&](int t, float a, float b, float c) {
-            trees.push_back(t);
-            labels.push_back(a); labels.push_back(b); labels.push_back(c);
-        };
-        for (int t = 0; t < T; t++) {
-            for (int k = adj_ptr[t]; k < adj_ptr[t + 1]; k++) {
-                const int nb = adj[k], sz = tstart[nb + 1] - tstart[nb];
-                const int idx = std::min(sz - 1, (int)((sym(engine) + 1.0f) * 0.5f * sz));  // Q11 clamp
-                const float* l = &abc[3 * (size_t)tpix[tstart[nb] + idx]];
-                push(t, l[0], l[1], l[2]);
-            }
-            const int sz = tstart[t + 1] - tstart[t];
-            const int p = tpix[tstart[t] + (int)(pick() % (unsigned)sz)];
-            const float px = (float)(p % W), py = (float)(p / W);
-            const float* l = &abc[3 * (size_t)p];
-            const float nz = 1.0f / std::sqrt(l[0] * l[0] + l[1] * l[1] + 1.0f);
-            const float nx = -l[0] * nz, ny = -l[1] * nz;
-            const float d = px * l[0] + py * l[1] + l[2];
-            float span_n = 1.0f;
-            for (float span_d = 0.5f * Dmax; span_d > ctx->P.refine_floor; span_d *= 0.5f, span_n *= 0.5f) {
-                const float rd = d + sym(engine) * span_d;
-                if (rd < 0.0f || rd > (float)Dmax) continue;  // draws 1 number, then 3 more only when in range (A11)
-                float rx = nx + sym(engine) * span_n;
-                float ry = ny + sym(engine) * span_n;
-                float rz = nz + sym(engine) * span_n;
-                const float inv = 1.0f / std::sqrt(rx * rx + ry * ry + rz * rz);
-                rx *= inv; ry *= inv; rz = std::fabs(rz * inv);
-                push(t, -rx / rz, -ry / rz, (rx * px + ry * py + rz * rd) / rz);
-            }
-        }
-        S3_TRY(s3_pms_apply(ctx, view, trees.data(), labels.data(), trees.size()));
+        const uint32_t round = ctx->pms_round[view]++;
+        k_pms_gen_prop<<<V.T, 64, 0, ctx->stream>>>(V.T, V.adj_ptr, V.adj, V.tree_start, V.node_pixel, V.abc, seed, round, d_lab);
+        S3_LAUNCH_CHECK();
+        S3_TRY(s3_pms_flow_launch(ctx, view, &plan, V.adj_ptr, d_lab, 1, seed, round));
     }
     return 0;
 }

@@ -19,8 +19,12 @@
 //                               allocated but unfilled, exactly as the reference does on a failed step (:727-759).
 //   "ADGRAD"                    extension: truncated colour + gradient volume built on the GPU.
 //   anything else               prints "wrong data cost" and returns (:756-759).
-// Search: S3DMST_MODE=dense (default) evaluates every integer label; S3DMST_MODE=pms runs
-// num_iter rounds of on-device proposal search (s3dmst_pms_iterate).  No GUI windows, no chdir.
+// Search: by default what the reference does — random plane initialisation, num_iter (100) rounds of MST_PMS per view,
+// LabelToDisp, left-right check (s3dmst_run): sub-pixel slanted-plane disparities.  The proposal stream is the library's
+// own (include/s3dmst.h: s3dmst_pms_iterate), so the maps agree with the reference's in quality, not bit for bit.
+// S3DMST_MODE=dense opts into the dense integer-label WTA instead.  No GUI windows, no chdir.
+// Inputs are validated before anything is allocated on their account (the reference trusts them): both images non-empty
+// CV_8UC3 of one size, Dmax > 0; rows are read with each Mat's own step.
 #include <sys/time.h>
 
 #include <cstdio>
@@ -58,9 +62,31 @@ extern "C" void stereo3dmst(std::string left_name, std::string right_name, cv::M
                             cv::Mat& leftDisp, cv::Mat& rightDisp, std::string data_cost, int Dmax) {
     (void)left_name;  // only forwarded to mc-cnn's command line by the reference (:733-748)
     (void)right_name;
+    if (leftImg.empty() || rightImg.empty() || leftImg.type() != CV_8UC3 || rightImg.type() != CV_8UC3 || leftImg.rows != rightImg.rows ||
+        leftImg.cols != rightImg.cols || Dmax <= 0) {
+        std::cout << "stereo3dmst: need two non-empty CV_8UC3 images of one size and Dmax > 0" << std::endl;
+        return;
+    }
     const int rows = leftImg.rows, cols = leftImg.cols;
     leftDisp.create(rows, cols, CV_32F);  // :722-723
     rightDisp.create(rows, cols, CV_32F);
+    // rows are addressed through each Mat's own step (a ROI or a padded Mat is not cols*3 wide); the C ABI takes one
+    // stride for both images, so a pair with different steps is packed first
+    const size_t lstep = (size_t)leftImg.step, rstep = (size_t)rightImg.step;
+    std::vector<unsigned char> packed;
+    const unsigned char* lptr = leftImg.data;
+    const unsigned char* rptr = rightImg.data;
+    size_t stride = lstep;
+    if (lstep != rstep) {
+        packed.resize((size_t)2 * rows * cols * 3);
+        for (int y = 0; y < rows; y++) {
+            memcpy(&packed[(size_t)y * cols * 3], leftImg.data + (size_t)y * lstep, (size_t)cols * 3);
+            memcpy(&packed[((size_t)rows + y) * cols * 3], rightImg.data + (size_t)y * rstep, (size_t)cols * 3);
+        }
+        lptr = packed.data();
+        rptr = packed.data() + (size_t)rows * cols * 3;
+        stride = (size_t)cols * 3;
+    }
 
     const bool mccnn = data_cost == "MCCNN_acrt" || data_cost == "MCCNN_fst";
     if (!mccnn && data_cost != "ADGRAD") {
@@ -82,15 +108,16 @@ extern "C" void stereo3dmst(std::string left_name, std::string right_name, cv::M
         P.cost_offset = 1.0f;
         P.cost_scale = 0.5f;
     }
+    const char* mode = getenv("S3DMST_MODE");
+    const bool pms = !(mode && !strcmp(mode, "dense"));
+    if (!mccnn && pms) P.cost_scale = 1.0f / 6.0f;  // the a2' volume spans [0, 3]: scaled into the [0, 0.5] range the ingest caps at (:789-801)
     const char* dev_env = getenv("S3DMST_DEVICE");
     s3dmst_ctx* ctx = NULL;
     if (s3dmst_create(&ctx, dev_env ? atoi(dev_env) : 0, &P, NULL) != S3DMST_OK) {
         std::cout << "stereo3dmst: " << s3dmst_last_error(NULL) << std::endl;
         return;
     }
-    const char* mode = getenv("S3DMST_MODE");
-    const bool pms = mode && !strcmp(mode, "pms");
-    int rc = s3dmst_set_images(ctx, leftImg.data, rightImg.data, cols, rows, cols * 3);
+    int rc = s3dmst_set_images(ctx, lptr, rptr, cols, rows, (int)stride);
     if (!rc) rc = s3dmst_build_forest(ctx, 0);
     if (!rc) rc = s3dmst_build_forest(ctx, 1);
     if (!rc) {
@@ -100,18 +127,18 @@ extern "C" void stereo3dmst(std::string left_name, std::string right_name, cv::M
         } else
             rc = s3dmst_build_cost_volume(ctx, Dmax, pms ? 1 : 0);
     }
-    for (int view = 0; view < 2 && !rc; view++) {
-        if (pms) {
-            rc = s3dmst_pms_iterate(ctx, view, P.num_iter, 1u);  // :858-889
-            if (!rc) rc = s3dmst_label_to_disp(ctx, view);      // :189-201, :900-902
-        } else {
+    if (pms) {
+        // :805-904: plane init, num_iter rounds of MST_PMS per view, LabelToDisp, LR check with fill = false
+        if (!rc) rc = s3dmst_run(ctx, Dmax, 1u, 0, reinterpret_cast<float*>(leftDisp.data), reinterpret_cast<float*>(rightDisp.data));
+    } else {
+        for (int view = 0; view < 2 && !rc; view++) {
             rc = s3dmst_aggregate_dense(ctx, view, 0, Dmax, NULL, NULL);
             if (!rc) rc = s3dmst_dense_to_disparity(ctx, view);
         }
+        if (!rc) rc = s3dmst_lr_check(ctx, 0);  // :904, fill = false
+        if (!rc) rc = s3dmst_get_disparity(ctx, 0, reinterpret_cast<float*>(leftDisp.data));
+        if (!rc) rc = s3dmst_get_disparity(ctx, 1, reinterpret_cast<float*>(rightDisp.data));
     }
-    if (!rc) rc = s3dmst_lr_check(ctx, 0);  // :904, fill = false
-    if (!rc) rc = s3dmst_get_disparity(ctx, 0, reinterpret_cast<float*>(leftDisp.data));
-    if (!rc) rc = s3dmst_get_disparity(ctx, 1, reinterpret_cast<float*>(rightDisp.data));
     if (rc) std::cout << "stereo3dmst: " << s3dmst_last_error(ctx) << std::endl;
     s3dmst_destroy(ctx);
 }

@@ -71,6 +71,27 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "ref_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+    make_medium(O, R)
+
+
+def make_medium(O, R):
+    """ref_medium.npz: the reference's full pipeline on an input that segments into SEVERAL trees under its own
+    literals (c = 5000, min size 200), so the 100 x 2 rounds exercise neighbour-tree propagation (ref_small is one tree).
+    Only what cannot be regenerated is stored: the images and the reference's two disparity maps; the cost volume is
+    the oracle's a2' volume x 1/6 (an input, rebuilt by the tests from the stored images)."""
+    W, H, D = 200, 150, 16
+    L, Rt, _ = synth.make_natural_pair(W, H, D, seed=23)
+    lv_raw, rv_raw = O.cost_adgrad(L, Rt, D)
+    lv_raw = (lv_raw * np.float32(1 / 6.0)).astype(np.float32)
+    rv_raw = (rv_raw * np.float32(1 / 6.0)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        R.srand(1)
+        dl, dr = R.stereo3dmst(td, L, Rt, lv_raw, rv_raw, D)
+    T = (O.forest(L).T, O.forest(Rt).T)
+    assert min(T) >= 4, T
+    path = os.path.join(ROOT, "tests", "golden", "ref_medium.npz")
+    np.savez_compressed(path, W=W, H=H, D=D, left=L, right=Rt, trees=np.int32(T), full_left_disp=dl, full_right_disp=dr)
+    print("wrote", path, os.path.getsize(path), "bytes, trees", T)
 
 
 if __name__ == "__main__":

@@ -48,3 +48,37 @@ float hd_label_cost(const float* row, float a, float b, float c, int x, int y, i
 float hd_label_disp(float a, float b, float c, int x, int y, int D) { return s3_label_disp(a, b, c, x, y, D); }
 float hd_ingest(float v, float cap, float off, float sc) { return s3_ingest(v, cap, off, sc); }
 }
+
+// ---- host mirror of the on-device proposal generator (s3dmst_pms_iterate): the same hd_math.h functions, called in
+// the order the kernels call them
+extern "C" {
+// propagation proposals of one round: for tree t and its j-th neighbour (CSR, ascending), the label of a sampled pixel
+void hd_gen_propagation(int T, const int* adj_ptr, const int* adj, const int* tree_start, const int* node_pixel, const float* abc,
+                        unsigned seed, unsigned round, int* out_tree, float* out_labels) {
+    for (int t = 0; t < T; t++)
+        for (int j = 0; j < adj_ptr[t + 1] - adj_ptr[t]; j++) {
+            const int e = adj_ptr[t] + j, nb = adj[e];
+            const int b = tree_start[nb], sz = tree_start[nb + 1] - b;
+            const int pix = node_pixel[b + s3_sample_index(s3_rng(seed, round, (uint32_t)t, (uint32_t)j), sz)];
+            out_tree[e] = t;
+            for (int k = 0; k < 3; k++) out_labels[3 * (size_t)e + k] = abc[3 * (size_t)pix + k];
+        }
+}
+// refinement ladders of one round from the labels as the propagation proposals left them; returns the proposal count
+int hd_gen_refinement(int T, int W, const int* tree_start, const int* node_pixel, const float* abc, int Dmax, float floor_d,
+                      unsigned seed, unsigned round, int* out_tree, float* out_labels) {
+    int n = 0;
+    for (int t = 0; t < T; t++) {
+        const int b = tree_start[t], sz = tree_start[t + 1] - b;
+        const int pix = node_pixel[b + (int)(s3_rng(seed, round, (uint32_t)t, S3_SLOT_REFINE_PIXEL) % (uint32_t)sz)];
+        float lab[3 * S3_MAX_LADDER];
+        const int k = s3_refine_ladder(abc[3 * (size_t)pix], abc[3 * (size_t)pix + 1], abc[3 * (size_t)pix + 2], (float)(pix % W), (float)(pix / W), Dmax,
+                                       floor_d, seed, round, (uint32_t)t, lab);
+        for (int i = 0; i < k; i++, n++) {
+            out_tree[n] = t;
+            for (int c = 0; c < 3; c++) out_labels[3 * (size_t)n + c] = lab[3 * i + c];
+        }
+    }
+    return n;
+}
+}

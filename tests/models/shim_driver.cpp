@@ -25,3 +25,11 @@ extern "C" int shim_call(const unsigned char* l, const unsigned char* r, int W, 
     memcpy(out_r, DR.data, (size_t)W * H * 4);
     return 0;
 }
+
+// a right image of another size and type: the shim must return before reading either image
+extern "C" int shim_call_mismatched(int W, int H) {
+    cv::Mat L(H, W, CV_8UC3), R(H / 2, W, CV_32F), DL, DR;
+    memset(L.data, 0, (size_t)W * H * 3);
+    stereo3dmst("img1r.png", "img2r.png", L, R, DL, DR, "ADGRAD", 16);
+    return DL.rows;
+}

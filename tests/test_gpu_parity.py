@@ -109,13 +109,14 @@ def test_cost_volume_matches_oracle(api, oracle, W, H, D, seed):
 
 
 @pytest.mark.parametrize("W,H,D,seed,c,ms,nat", CASES[:7])
-@pytest.mark.parametrize("own_forest", [False, True])
-def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat, own_forest):
+@pytest.mark.parametrize("own_forest,cluster", [(False, -1), (True, -1), (True, 48)])
+def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat, own_forest, cluster):
+    """cluster = 48: every tree of >= 48 nodes is walked by a thread-block cluster of 8 CTAs (the giant-tree kernel)."""
     L, R, _ = make(W, H, D, seed, nat)
     F = oracle.forest(L, c=c, min_size=ms)
     lv, _ = oracle.cost_adgrad(L, R, D)
     disp_o, best_o, agg_o = oracle.aggregate_dense(F, lv, want_agg=True)
-    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, keep_aggregated=1)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, keep_aggregated=1, agg_cluster_nodes=cluster)
     eng.set_images(L, R)
     if own_forest:
         eng.build_forest(0)
@@ -147,12 +148,13 @@ def test_dense_aggregation_config_independent(api, oracle, threads, cap):
     eng.close()
 
 
-def test_dense_label_slices_and_ranges(api, oracle):
+@pytest.mark.parametrize("cluster", [-1, 100])
+def test_dense_label_slices_and_ranges(api, oracle, cluster):
     W, H, D = 120, 80, 200   # > 128 labels: several (tree, slice) units + the combine kernel
     L, R, _ = make(W, H, 24, 13, 0)
     F = oracle.forest(L, c=900.0, min_size=40)
     lv, _ = oracle.cost_adgrad(L, R, D)
-    eng = api.Stereo3DMST(fh_c=900.0, min_cc_size=40)
+    eng = api.Stereo3DMST(fh_c=900.0, min_cc_size=40, agg_cluster_nodes=cluster)
     eng.set_images(L, R)
     eng.build_forest(0)
     eng.set_cost_volume(0, lv, ingest=False)
@@ -205,9 +207,11 @@ def test_pms_apply_matches_oracle(api, oracle):
     eng.close()
 
 
-def test_pms_replays_recorded_reference_sequence(api, oracle):
+@pytest.mark.parametrize("cluster,kernel", [(-1, 0), (64, 0), (-1, 1)])
+def test_pms_replays_recorded_reference_sequence(api, oracle, cluster, kernel):
     """Injected-proposal parity (north star): record the proposal sequence of oracle MST_PMS iterations and
-    replay it on the GPU; labels and min costs must be identical."""
+    replay it on the GPU; labels and min costs must be identical.  (cluster: trees walked by a CTA cluster;
+    kernel = 1: the simple level-synchronous proposal kernel.)"""
     W, H, D = 120, 72, 14
     L, R, _ = make(W, H, D, 31, 0)
     N = W * H
@@ -216,7 +220,7 @@ def test_pms_replays_recorded_reference_sequence(api, oracle):
     lv = oracle.ingest(oracle.cost_adgrad(L, R, D)[0], 0.5, 0.0, 1 / 6.0)
     abc_o = oracle.plane_init(W, H, D)
     mn_o = np.full(N, np.finfo(np.float64).max)
-    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, cost_scale=1 / 6.0)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, cost_scale=1 / 6.0, agg_cluster_nodes=cluster, agg_kernel=kernel)
     eng.set_images(L, R)
     eng.build_forest(0)
     eng.build_forest(1)
@@ -258,6 +262,198 @@ def test_init_labels_and_generator(api, oracle):
     d = eng.get_disparity(0)
     assert d.min() >= 0.0 and d.max() <= D - 1.0
     eng.close()
+
+
+@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_medium.npz"])
+def test_reference_pipeline_end_to_end_golden(api, oracle, fixture):
+    """a1, north star "the 3DMST pipeline reproduces the reference disparity maps": tests/golden/ref_small.npz holds
+    full_left_disp / full_right_disp written by the reference's own stereo3dmst() (its translation unit compiled
+    unmodified, tests/golden/make_golden.py).  The oracle re-runs that pipeline (forests, plane init, 100 rounds of MST_PMS
+    per view on the reference's RNG streams) and records every round's proposals; the GPU replays each round through the
+    C ABI and must hold the oracle's labels and minimum costs after EVERY round, and the reference's maps at the end.
+    ref_small is a single tree; ref_medium has 23 / 33 trees (labels propagate between neighbouring trees)."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", fixture))
+    W, H, D = int(gold["W"]), int(gold["H"]), int(gold["D"])
+    N = W * H
+    L, R = gold["left"], gold["right"]
+    if "lv_raw" in gold.files:
+        raws = (gold["lv_raw"], gold["rv_raw"])
+    else:  # the fixture's volume is the a2' volume x 1/6 (tests/golden/make_golden.py: make_medium)
+        raws = tuple(v * np.float32(1 / 6.0) for v in oracle.cost_adgrad(L, R, D))
+    eng = api.Stereo3DMST()                       # the reference's literals: c = 5000, min size 200, gamma = 1/12
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    g = oracle.rand_new(1)                        # std::rand(), shared by both views (Stereo3DMST.cpp:584)
+    vols = (oracle.ingest(raws[0]), oracle.ingest(raws[1]))
+    for view, raw in enumerate(raws):
+        eng.set_cost_volume(view, raw, ingest=True)
+        assert np.array_equal(bits(eng.get_cost_volume(view)), bits(vols[view]))
+    forests, states = [], []
+    for view, img in enumerate((L, R)):          # :841-847: per view forest, debug colouring (3N random() draws, Q6), plane init
+        F = oracle.forest(img)
+        oracle.lib.orc_rand_burn(g, 3 * N)
+        eng.init_labels(view, D)
+        abc = oracle.plane_init(W, H, D)
+        assert np.array_equal(bits(eng.get_labels(view)), bits(abc))
+        forests.append(F); states.append((np.full(N, np.finfo(np.float64).max), abc))
+    n_props = 0
+    for view in (0, 1):                           # :858-889: 100 rounds on the left view, then 100 on the right
+        F, (mn, abc) = forests[view], states[view]
+        for it in range(100):
+            n, rt, rl = oracle.mst_pms(F, vols[view], D, mn, abc, g, record_cap=80 * F.T + 64)
+            eng.pms_apply(view, rt, rl)
+            n_props += n
+            if it % 10 == 9 or it < 3:
+                assert np.array_equal(bits(eng.get_min_cost(view)), bits(mn)), (view, it)
+                assert np.array_equal(bits(eng.get_labels(view)), bits(abc)), (view, it)
+        eng.label_to_disp(view)
+    eng.lr_check(fill=False)                      # :904
+    assert n_props > 1000
+    assert np.array_equal(bits(eng.get_disparity(0)), bits(gold["full_left_disp"]))
+    assert np.array_equal(bits(eng.get_disparity(1)), bits(gold["full_right_disp"]))
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def hdgen(tmp_path_factory):
+    """Host build of stereomatch_b200/csrc/hd_math.h (the generator's arithmetic, shared with the kernels)."""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path_factory.mktemp("hdgen") / "libhdgen.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, os.path.join(here, "models", "hd_math_host.cpp")])
+    lib = C.CDLL(out)
+    p = C.c_void_p
+    lib.hd_gen_propagation.argtypes = [C.c_int, p, p, p, p, p, C.c_uint, C.c_uint, p, p]
+    lib.hd_gen_refinement.argtypes = [C.c_int, C.c_int, p, p, p, C.c_int, C.c_float, C.c_uint, C.c_uint, p, p]
+    lib.hd_gen_refinement.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("cluster", [-1, 64])
+def test_device_generator_equals_its_injected_stream(api, oracle, hdgen, cluster):
+    """a12 with the library's own generator (s3dmst_pms_iterate: propagation gather kernel + refinement ladder generated
+    inside the proposal kernel, no host round trip).  Its proposal stream is a pure function of (seed, round, tree, slot)
+    and of the labels; a host build of the same header regenerates it and injects it through s3dmst_pms_apply into a
+    second context: both contexts must hold identical labels and costs after every round — which also pins the
+    reference's sequencing: a tree's ladder starts from the label its own propagation proposals left (:584-595)."""
+    import ctypes as C
+    W, H, D = 160, 96, 20
+    L, R, _ = make(W, H, D, 51, 0)
+    N = W * H
+    def mk():
+        e = api.Stereo3DMST(fh_c=600.0, min_cc_size=40, cost_scale=1 / 6.0, agg_cluster_nodes=cluster)
+        e.set_images(L, R)
+        e.build_forest(0); e.build_forest(1)
+        e.build_cost_volume(D, ingest=True)
+        e.init_labels(0, D)
+        return e
+    dev, inj = mk(), mk()
+    G = dev.get_forest(0)
+    F = oracle.forest(L, c=600.0, min_size=40)
+    assert np.array_equal(G["adj_ptr"], F.adj_ptr) and np.array_equal(G["adj"], F.adj)   # device CSR == tree_g (:377-384)
+    T, nadj = G["T"], len(G["adj"])
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    seed = 7
+    for rnd in range(4):
+        dev.pms_iterate(0, 1, seed=seed)
+        abc = inj.get_labels(0)                                 # labels at the start of the round
+        pt = np.empty(nadj, np.int32); pl = np.empty((nadj, 3), np.float32)
+        hdgen.hd_gen_propagation(T, ptr(G["adj_ptr"]), ptr(G["adj"]), ptr(G["tree_start"]), ptr(G["node_pixel"]), ptr(abc), seed, rnd, ptr(pt), ptr(pl))
+        inj.pms_apply(0, pt, pl)
+        abc = inj.get_labels(0)                                 # ... and after the propagation proposals
+        rt = np.empty(64 * T, np.int32); rl = np.empty((64 * T, 3), np.float32)
+        n = hdgen.hd_gen_refinement(T, W, ptr(G["tree_start"]), ptr(G["node_pixel"]), ptr(abc), D, 0.1, seed, rnd, ptr(rt), ptr(rl))
+        assert n > T                                            # several ladder steps per tree stay inside [0, Dmax]
+        inj.pms_apply(0, rt[:n], rl[:n])
+        assert np.array_equal(bits(dev.get_min_cost(0)), bits(inj.get_min_cost(0))), rnd
+        assert np.array_equal(bits(dev.get_labels(0)), bits(inj.get_labels(0))), rnd
+    # the oracle agrees with the injected context on the last round's stream (one more round, checked on the CPU)
+    mn_o = inj.get_min_cost(0).copy(); abc_o = inj.get_labels(0).copy()
+    vol = inj.get_cost_volume(0)
+    dev.pms_iterate(0, 1, seed=seed)
+    pt = np.empty(nadj, np.int32); pl = np.empty((nadj, 3), np.float32)
+    hdgen.hd_gen_propagation(T, ptr(G["adj_ptr"]), ptr(G["adj"]), ptr(G["tree_start"]), ptr(G["node_pixel"]), ptr(abc_o), seed, 4, ptr(pt), ptr(pl))
+    oracle.pms_apply(F, vol, D, pt, pl, mn_o, abc_o)
+    rt = np.empty(64 * T, np.int32); rl = np.empty((64 * T, 3), np.float32)
+    n = hdgen.hd_gen_refinement(T, W, ptr(G["tree_start"]), ptr(G["node_pixel"]), ptr(abc_o), D, 0.1, seed, 4, ptr(rt), ptr(rl))
+    oracle.pms_apply(F, vol, D, rt[:n], rl[:n], mn_o, abc_o)
+    assert np.array_equal(bits(dev.get_min_cost(0)), bits(mn_o)) and np.array_equal(bits(dev.get_labels(0)), bits(abc_o))
+    dev.close(); inj.close()
+
+
+def test_run_reference_mode_pipeline(api, oracle):
+    """s3dmst_run = the reference's orchestration (:805-904) with the library's generator: equals the stage calls it is
+    made of, is reproducible, returns sub-pixel disparities in [0, Dmax-1] with invalid left pixels zeroed, and lands near
+    the ground truth of the synthetic pair."""
+    W, H, D = 256, 160, 32
+    L, R, gt = make(W, H, D, 77, 0)
+    eng = api.Stereo3DMST(cost_scale=1 / 6.0, num_iter=12)
+    eng.set_images(L, R)
+    dl, dr = eng.run(D, seed=5)
+    e2 = api.Stereo3DMST(cost_scale=1 / 6.0, num_iter=12)
+    e2.set_images(L, R)
+    e2.build_forest(0); e2.build_forest(1)
+    e2.build_cost_volume(D, ingest=True)
+    for v in (0, 1):
+        e2.init_labels(v, D)
+        e2.pms_iterate(v, 12, seed=5)
+        e2.label_to_disp(v)
+    e2.lr_check(fill=False)
+    assert np.array_equal(bits(dl), bits(e2.get_disparity(0))) and np.array_equal(bits(dr), bits(e2.get_disparity(1)))
+    dl2, dr2 = eng.run(D, seed=5)
+    assert np.array_equal(bits(dl), bits(dl2)) and np.array_equal(bits(dr), bits(dr2))
+    assert dl.min() >= 0.0 and dl.max() <= D - 1.0 and dr.min() >= 0.0 and dr.max() <= D - 1.0
+    assert np.any(dl != np.round(dl))                                     # slanted planes: sub-pixel values
+    want, _ = oracle.lr_check(oracle.label_to_disp(eng.get_labels(0), W, H, D) * np.float32(D - 1.0), dr, W, H, D, False)
+    assert np.array_equal(bits(dl), bits(want))
+    valid = dl.reshape(H, W) > 0
+    err = np.abs(dl.reshape(H, W) - gt)
+    assert valid.mean() > 0.3 and (err[valid] <= 1.0).mean() > 0.5
+    eng.close(); e2.close()
+
+
+def test_batch_mixed_c4_shapes(api, oracle):
+    """BASELINE config C4 is a batch of 1920x1080 (D=256) frames plus the FLIR pairs (2048x1536, D=100): contexts of
+    different sizes cannot share one aggregation launch, so a caller groups them by shape.  One batch of two full-size
+    synthetic C4 frames and one batch of two FLIR-sized frames (the bundled pair and its mirror image): every frame's
+    maps equal the single-frame pipeline's, and the forests / winners equal the oracle's on one view of each shape."""
+    import cv2
+    from oracle.pyoracle import Oracle
+    O = Oracle(fast=True)
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    FLl = cv2.imread(os.path.join(g, "flir_000020_left.jpg")); FLr = cv2.imread(os.path.join(g, "flir_000020_right.jpg"))
+    groups = [
+        (256, [synth.make_pair(1920, 1080, 256, seed=synth.BASE_SEED + 10 + i)[:2] for i in range(2)]),
+        (100, [(FLl, FLr), (np.ascontiguousarray(FLr[:, ::-1]), np.ascontiguousarray(FLl[:, ::-1]))]),
+    ]
+    for D, frames in groups:
+        engs = []
+        for Li, Ri in frames:
+            e = api.Stereo3DMST(fh_ctas=36)
+            e.set_images(Li, Ri)
+            engs.append(e)
+        outs = api.run_dense_batch(engs, D, fill=True)
+        Hh, Ww = frames[0][0].shape[:2]
+        for (Li, Ri), (dl, dr), e in zip(frames, outs, engs):
+            single = api.Stereo3DMST()
+            single.set_images(Li, Ri)
+            sl, sr = single.run_dense(D, fill=True)
+            single.close()
+            assert np.array_equal(bits(dl), bits(sl)) and np.array_equal(bits(dr), bits(sr))
+        # oracle on the right view of the first frame of the group (forest + aggregated winners)
+        Li, Ri = frames[0]
+        F = O.forest(Ri)
+        G = engs[0].get_forest(1)
+        assert np.array_equal(G["mask"], F.mask) and np.array_equal(G["node_pixel"], F.node_pixel) and np.array_equal(G["parent"], F.parent)
+        vol = engs[0].get_cost_volume(1)
+        do, bo, _ = O.aggregate_dense(F, vol)
+        del vol
+        assert np.array_equal(bits(outs[0][1]), bits(do.astype(np.float32)))
+        disp, best = engs[0].aggregate_dense(1, 0, D)
+        assert np.array_equal(disp, do) and np.array_equal(bits(best), bits(bo))
+        for e in engs:
+            e.close()
 
 
 def test_golden_reference_proposals(api, oracle):

@@ -82,6 +82,19 @@ def test_full_pipeline_matches_reference(oracle, gold):
     assert np.array_equal(bits(out["right_disp"]), bits(gold["full_right_disp"]))
 
 
+def test_full_pipeline_matches_reference_many_trees(oracle):
+    """tests/golden/ref_medium.npz: the reference's stereo3dmst() on a 200x150 pair that its own literals segment into
+    23 / 33 trees, so the 100 x 2 rounds propagate labels between neighbouring trees (ref_small is a single tree)."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_medium.npz"))
+    D = int(gold["D"])
+    L, R = gold["left"], gold["right"]
+    assert (oracle.forest(L).T, oracle.forest(R).T) == tuple(gold["trees"])
+    lv, rv = oracle.cost_adgrad(L, R, D)
+    out = oracle.stereo3dmst(L, R, lv * np.float32(1 / 6.0), rv * np.float32(1 / 6.0), D, num_iter=100)
+    assert np.array_equal(bits(out["left_disp"]), bits(gold["full_left_disp"]))
+    assert np.array_equal(bits(out["right_disp"]), bits(gold["full_right_disp"]))
+
+
 def test_tree_filter_bruteforce_identity(oracle, gold):
     """agg(v) = sum_u prod(weights on path u->v) * cost(u)  (SURVEY §4), small tree, 1e-12 rel."""
     D = int(gold["D"])
