@@ -61,7 +61,7 @@ typedef struct s3dmst_params {
                            frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
                            frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
     int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel */
-    int agg_cluster_nodes; /* 0 = auto (8192): trees of at least this many nodes are walked by a thread-block cluster of
+    int agg_cluster_nodes; /* 0 = auto (32768): trees of at least this many nodes are walked by a thread-block cluster of
                            8 CTAs (256 warps) instead of one CTA; < 0: never */
 } s3dmst_params;
 

@@ -433,16 +433,29 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         const T wk = TT::ldsw(w_a + (uint32_t)sizeof(T) * (IW));                                                                 \
         const uint32_t pa = prog_of(top - c);                                                                        \
         A3_CLK(q_pre);                                                                                               \
-        while (poll(pa) > c) __nanosleep(sleep_ns);                                                                  \
-        A3_CLK(q_poll);                                                                                              \
         T2 cv[NH];                                                                                              \
-        if (c - v < NEAR_E) {                                                                                        \
+        if (CL > 1 && c - v < NEAR_E) {                                                                              \
+            /* another SM: the progress word and, right behind it, the row — ONE round trip through the cluster when */ \
+            /* the child is done (requests of a warp to one CTA are serviced in order; a row fetched too early is    */ \
+            /* simply fetched again) */                                                                              \
             const uint32_t ra = row_of(top - c);                                                                     \
-            _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = ld_row(ra + h * HB);                            \
+            while (true) {                                                                                           \
+                const int f = poll(pa);                                                                              \
+                _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = ld_row(ra + h * HB);                        \
+                if (f <= c) break;                                                                                   \
+            }                                                                                                        \
+            A3_CLK(q_poll);                                                                                          \
         } else {                                                                                                     \
-            const char* gp = aup_lane0 + (size_t)c * DA * sizeof(T);                                                         \
-            _Pragma("unroll") for (int h = 0; h < NH; h++)                                                           \
-                cv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2(); \
+            while (poll(pa) > c) __nanosleep(sleep_ns);                                                              \
+            A3_CLK(q_poll);                                                                                          \
+            if (c - v < NEAR_E) {                                                                                    \
+                const uint32_t ra = row_of(top - c);                                                                 \
+                _Pragma("unroll") for (int h = 0; h < NH; h++) cv[h] = ld_row(ra + h * HB);                        \
+            } else {                                                                                                 \
+                const char* gp = aup_lane0 + (size_t)c * DA * sizeof(T);                                             \
+                _Pragma("unroll") for (int h = 0; h < NH; h++)                                                       \
+                    cv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2();                                           \
+            }                                                                                                        \
         }                                                                                                            \
         _Pragma("unroll") for (int h = 0; h < NH; h++) {                                                             \
             acc[h].x = TT::add(acc[h].x, TT::mul(wk, cv[h].x));                                                      \
@@ -468,7 +481,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 if constexpr (CL > 1) a3_fence_cl();  // every lane's stores, before lane 0 publishes
             }
             A3_CLK(q_dep);
-            if constexpr (CL == 1) guard_up();
+            if constexpr (CL == 1) guard_up();  // (measured: at the top it makes no difference for one CTA)
             A3_CLK(q_guard);
             {
                 const uint32_t ra = ring_a + (uint32_t)(((top - v) >> LOGCL) & (A3_R - 1)) * ROWB;
@@ -591,16 +604,26 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                     au[h].y = TT::mul(wq, au[h].y);
                 }
                 const uint32_t pa = prog_of(p - base);
-                while (poll(pa) < p) __nanosleep(sleep_ns);
                 T2 pv[NH];
-                if (v - p < NEAR_E) {
+                if (CL > 1 && v - p < NEAR_E) {  // word and row in one round trip through the cluster (see the way up)
                     const uint32_t ra = row_of(p - base);
+                    while (true) {
+                        const int f = poll(pa);
 #pragma unroll
-                    for (int h = 0; h < NH; h++) pv[h] = ld_row(ra + h * HB);
+                        for (int h = 0; h < NH; h++) pv[h] = ld_row(ra + h * HB);
+                        if (f >= p) break;
+                    }
                 } else {
-                    const char* gp = aup_lane0 + (size_t)p * DA * sizeof(T);
+                    while (poll(pa) < p) __nanosleep(sleep_ns);
+                    if (v - p < NEAR_E) {
+                        const uint32_t ra = row_of(p - base);
 #pragma unroll
-                    for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2();
+                        for (int h = 0; h < NH; h++) pv[h] = ld_row(ra + h * HB);
+                    } else {
+                        const char* gp = aup_lane0 + (size_t)p * DA * sizeof(T);
+#pragma unroll
+                        for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2();
+                    }
                 }
 #pragma unroll
                 for (int h = 0; h < NH; h++) {
@@ -669,12 +692,15 @@ __global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node
 }
 
 #define A3_CLUSTER 8   // CTAs walking one giant tree
+#ifndef A3_CL_NEAR
+#define A3_CL_NEAR 32   // hand-over distance per CTA of a cluster (x A3_CLUSTER nodes for the cluster)
+#endif
 
 // trees of at least this many nodes are walked by a cluster / get a CTA of 32 warps (development overrides: S3_AGG_CL, S3_AGG_BIG)
 static int s3_agg_cluster_nodes(const s3dmst_ctx* ctx) {
     static const int env = getenv("S3_AGG_CL") ? atoi(getenv("S3_AGG_CL")) : 0;
     const int p = ctx->P.agg_cluster_nodes;
-    return p < 0 ? 0 : p > 0 ? p : env ? env : 8192;
+    return p < 0 ? 0 : p > 0 ? p : env ? env : 32768;
 }
 static int s3_agg_big_nodes() {
     static const int v = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
@@ -807,7 +833,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
-    A.sleep_ns = sleep_env ? sleep_env : 20;
+    A.sleep_ns = sleep_env < 0 ? 0 : sleep_env ? sleep_env : 20;
 
     // The giant trees get a thread-block cluster (A3_CLUSTER CTAs = 256 warps on one tree), on the context's second
     // stream so that they run beside the rest; all but the smallest of the others get 32 warps and an SM of their own;
@@ -847,7 +873,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         S3_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
         launch_stream = ctx->stream_aux;
         A.unit0 = 0;
-        A3_DISPATCH(true, 256, 64, A3_CLUSTER, n_cl * A3_CLUSTER, 1024);
+        A3_DISPATCH(true, 256, A3_CL_NEAR, A3_CLUSTER, n_cl * A3_CLUSTER, 1024);
         S3_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
         launch_stream = ctx->stream;
     }
@@ -952,7 +978,7 @@ int s3_pms_flow_launch(s3dmst_ctx* ctx, int view, const PmsFlowPlan* plan, const
         S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         S3_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
         A.unit0 = 0;
-        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, 64, true, A3_CLUSTER>, n_cl * A3_CLUSTER, 1024, agg3_smem_bytes(1, 256, sizeof(double)), A3_CLUSTER, ctx->stream_aux, A));
+        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, A3_CL_NEAR, true, A3_CLUSTER>, n_cl * A3_CLUSTER, 1024, agg3_smem_bytes(1, 256, sizeof(double)), A3_CLUSTER, ctx->stream_aux, A));
         S3_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
     }
     if (n_big) {
