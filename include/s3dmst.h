@@ -34,7 +34,8 @@ enum {
     S3DMST_E_ARG = -1,   /* bad argument / call order */
     S3DMST_E_CUDA = -2,  /* CUDA runtime error (message has the detail) */
     S3DMST_E_STATE = -3, /* required stage has not run */
-    S3DMST_E_LIMIT = -4  /* internal iteration cap hit (forest kernels) */
+    S3DMST_E_LIMIT = -4, /* internal iteration cap hit (forest kernels) */
+    S3DMST_E_COMM = -5   /* NCCL missing or failed (label-range sharding) */
 };
 
 /* The literals of src/Stereo3DMST.cpp lifted into one struct (reference values are the defaults). */
@@ -135,6 +136,27 @@ int s3dmst_dense_result_dev(s3dmst_ctx* ctx, int view, double** best_cost_dev, i
 /* After an all-reduce(MIN) of best cost into global_min_dev: disp := INT32_MAX where the local cost is not
  * the global minimum, so that a second all-reduce(MIN) on disp yields the lowest d attaining the minimum. */
 int s3dmst_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
+/* Label-range sharding of ONE large pair over the GPUs of a box (BASELINE config C5): one process and one
+ * context per GPU; every rank builds the (deterministic) forests and its own label range of the cost volume, and the
+ * only exchange is the per-pixel MIN-LOC that replaces the reference's serial `agg < min_cost` over ascending labels
+ * (Stereo3DMST.cpp:173-185).  NCCL is bound at run time (dlopen libnccl.so.2); nothing else needs it.
+ *   s3dmst_comm_unique_id  rank 0 fills 128 bytes (ncclUniqueId) and hands them to the other ranks by its own means
+ *   s3dmst_comm_init       collective: every rank, with the same id
+ *   s3dmst_comm_label_range  the labels [d0, d1) this rank aggregates (boundaries are multiples of 4)
+ *   s3dmst_reduce_minloc   MIN-LOC all-reduce of a view's dense result (best cost f64, disparity i32; lowest d wins
+ *                          ties), queued on the context's stream — no host synchronisation
+ *   s3dmst_aggregate_dense_sharded  both views: this rank's labels, then the reduction; the left view's reduction runs
+ *                          on the context's communication stream while the right view is aggregated.  Afterwards every
+ *                          rank holds the global result (s3dmst_dense_to_disparity / s3dmst_lr_check as usual).
+ *   s3dmst_comm_minloc_ms  device time of the two views' reductions of the last sharded call (CUDA events), ms */
+int s3dmst_comm_unique_id(void* id128);
+int s3dmst_comm_init(s3dmst_ctx* ctx, const void* id128, int rank, int nranks);
+int s3dmst_comm_destroy(s3dmst_ctx* ctx);
+int s3dmst_comm_label_range(const s3dmst_ctx* ctx, int D, int* d0, int* d1);
+int s3dmst_reduce_minloc(s3dmst_ctx* ctx, int view);
+int s3dmst_aggregate_dense_sharded(s3dmst_ctx* ctx, int D);
+double s3dmst_comm_minloc_ms(s3dmst_ctx* ctx);
+
 /* Dense disparity (int) -> float disparity map used by the LR check. */
 int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view);
 

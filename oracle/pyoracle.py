@@ -94,6 +94,7 @@ class Oracle:
         L.orc_plane_init.argtypes = [C.c_int, C.c_int, C.c_int, c_p]
         L.orc_ingest.argtypes = [c_p, C.c_size_t, C.c_float, C.c_float, C.c_float]
         L.orc_cost_adgrad.argtypes = [c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p]
+        L.orc_cost_adgrad_range.argtypes = [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]
         L.orc_eval_proposal.argtypes = [c_p, c_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, c_p, c_p, c_p]
         L.orc_eval_proposal.restype = C.c_int
         L.orc_pms_apply.argtypes = [c_p, c_p, C.c_int, c_p, c_p, C.c_int, c_p, c_p]
@@ -143,6 +144,16 @@ class Oracle:
         lv = np.empty((D, H * W), np.float32)
         rv = np.empty((D, H * W), np.float32)
         self.lib.orc_cost_adgrad(_ptr(left_bgr), _ptr(right_bgr), W, H, D, _ptr(lv), _ptr(rv))
+        return lv, rv
+
+    def cost_adgrad_range(self, left_bgr, right_bgr, d0, d1, views=(0, 1)):
+        """Rows d0..d1-1 of the two volumes cost_adgrad returns (None for a view not in `views`): bench.py's sharded CPU arm."""
+        left_bgr = np.ascontiguousarray(left_bgr, np.uint8)
+        right_bgr = np.ascontiguousarray(right_bgr, np.uint8)
+        H, W, _ = left_bgr.shape
+        lv = np.empty((d1 - d0, H * W), np.float32) if 0 in views else None
+        rv = np.empty((d1 - d0, H * W), np.float32) if 1 in views else None
+        self.lib.orc_cost_adgrad_range(_ptr(left_bgr), _ptr(right_bgr), W, H, d0, d1, _ptr(lv), _ptr(rv))
         return lv, rv
 
     def aggregate_dense(self, F: Forest, vol, d0=0, d1=None, want_agg=False):

@@ -466,6 +466,34 @@ void orc_cost_adgrad(const uint8_t* left_bgr, const uint8_t* right_bgr, int W, i
             }
 }
 
+// the labels [d0, d1) of the same two volumes (rows 0 .. d1-d0-1 of the outputs; either output may be null): what one
+// shard of the CPU arm of bench.py builds; every element is computed exactly as above
+void orc_cost_adgrad_range(const uint8_t* left_bgr, const uint8_t* right_bgr, int W, int H, int d0, int d1, float* left_vol,
+                           float* right_vol) {
+    const size_t N = (size_t)W * H;
+    for (int d = d0; d < d1; d++)
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                const size_t p = (size_t)y * W + x, idx = (size_t)(d - d0) * N + p;
+                if (right_vol) {
+                    if (d + x + 1 < W) {  // right reference at x, left match at x + d
+                        const uint8_t* ref0 = right_bgr + 3 * p;
+                        const uint8_t* mat0 = left_bgr + 3 * (p + d);
+                        right_vol[idx] = adgrad_pair(ref0, ref0 + 3, mat0, mat0 + 3);
+                    } else
+                        right_vol[idx] = 3.0f;
+                }
+                if (left_vol) {
+                    if (x - d >= 0 && x + 1 < W) {  // the left entry at x was mirrored from the right reference at x - d
+                        const uint8_t* ref0 = right_bgr + 3 * (p - d);
+                        const uint8_t* mat0 = left_bgr + 3 * p;
+                        left_vol[idx] = adgrad_pair(ref0, ref0 + 3, mat0, mat0 + 3);
+                    } else
+                        left_vol[idx] = 3.0f;
+                }
+            }
+}
+
 // -------------------------------------------------------------------------------------------
 // a8: compute3DLabelCost (Stereo3DMST.cpp:103-118)
 // -------------------------------------------------------------------------------------------

@@ -45,6 +45,8 @@ ABI_SYMBOLS = [
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
     "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_comm_unique_id", "s3dmst_comm_init", "s3dmst_comm_destroy", "s3dmst_comm_label_range", "s3dmst_reduce_minloc", "s3dmst_aggregate_dense_sharded",
+    "s3dmst_comm_minloc_ms",
 ]
 
 _lib = None
@@ -112,8 +114,47 @@ def load_library():
     L.s3dmst_stage_ms.restype = C.c_double
     L.s3dmst_launch_count.argtypes = [c_p]
     L.s3dmst_launch_count.restype = C.c_longlong
+    L.s3dmst_comm_unique_id.argtypes = [c_p]
+    L.s3dmst_comm_init.argtypes = [c_p, c_p, C.c_int, C.c_int]
+    L.s3dmst_comm_destroy.argtypes = [c_p]
+    L.s3dmst_comm_label_range.argtypes = [c_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.s3dmst_reduce_minloc.argtypes = [c_p, C.c_int]
+    L.s3dmst_aggregate_dense_sharded.argtypes = [c_p, C.c_int]
+    L.s3dmst_comm_minloc_ms.argtypes = [c_p]
+    L.s3dmst_comm_minloc_ms.restype = C.c_double
     _lib = L
     return L
+
+
+def _prefer_torch_nccl():
+    """The library binds NCCL at run time by SONAME (libnccl.so.2).  In a Python process that also uses torch, torch's
+    bundled copy has to be the one the process holds: had the system copy been loaded first, a later `import torch` would
+    be resolved against it and fail on newer symbols.  Importing torch first makes the order right; without torch the
+    system copy is used."""
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
+
+
+_cudart_lib = None
+
+
+def _cudart():
+    """The CUDA runtime the library itself links (for plain D2H copies of device pointers the ABI hands out)."""
+    global _cudart_lib
+    if _cudart_lib is None:
+        load_library()
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _cudart_lib = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _cudart_lib is None:
+            raise S3Error("libcudart not found")
+        _cudart_lib.cudaMemcpy.argtypes = [c_p, c_p, C.c_size_t, C.c_int]
+    return _cudart_lib
 
 
 def default_params() -> S3Params:
@@ -276,6 +317,52 @@ class Stereo3DMST:
 
     def minloc_mask(self, view, global_min_dev_ptr):
         self._ck(self.L.s3dmst_minloc_mask(self.h, view, c_p(global_min_dev_ptr)))
+
+    # -- label-range sharding over NCCL (one context per GPU / process) ------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes (ncclUniqueId) made by rank 0; hand them to the other ranks (e.g. torch.distributed broadcast)."""
+        _prefer_torch_nccl()
+        buf = C.create_string_buffer(128)
+        rc = load_library().s3dmst_comm_unique_id(buf)
+        if rc != 0:
+            raise S3Error(f"s3dmst_comm_unique_id failed ({rc}): NCCL could not be loaded")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        _prefer_torch_nccl()
+        self._ck(self.L.s3dmst_comm_init(self.h, C.c_char_p(unique_id), int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        self._ck(self.L.s3dmst_comm_destroy(self.h))
+
+    def comm_label_range(self, D):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.s3dmst_comm_label_range(self.h, int(D), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def reduce_minloc(self, view):
+        self._ck(self.L.s3dmst_reduce_minloc(self.h, view))
+
+    def aggregate_dense_sharded(self, D):
+        """This rank's label range of both views + the MIN-LOC reduction (s3dmst_aggregate_dense_sharded): asynchronous."""
+        self._ck(self.L.s3dmst_aggregate_dense_sharded(self.h, int(D)))
+
+    def comm_minloc_ms(self):
+        return self.L.s3dmst_comm_minloc_ms(self.h)
+
+    def get_dense_result(self, view):
+        """(disparity int32 [N], best cost float64 [N]) of the last dense / sharded call, copied to the host."""
+        import ctypes
+        pb, pd = self.dense_result_dev(view)
+        disp = np.empty(self.N, np.int32); best = np.empty(self.N, np.float64)
+        self.sync()
+        cudart = _cudart()
+        for dst, src in ((disp, pd), (best, pb)):
+            rc = cudart.cudaMemcpy(dst.ctypes.data_as(c_p), c_p(src), ctypes.c_size_t(dst.nbytes), 2)
+            if rc != 0:
+                raise S3Error(f"cudaMemcpy D2H failed ({rc})")
+        return disp, best
 
     def dense_to_disparity(self, view):
         self._ck(self.L.s3dmst_dense_to_disparity(self.h, view))

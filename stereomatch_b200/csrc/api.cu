@@ -207,6 +207,11 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
 void s3dmst_destroy(s3dmst_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    s3dmst_comm_destroy(ctx);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    for (int i = 0; i < 2; i++) if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
+    for (int i = 0; i < 4; i++) if (ctx->ev_comm_t[i]) cudaEventDestroy(ctx->ev_comm_t[i]);
+    DFREE(ctx->gmin);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
     s3_rectify_free(ctx);

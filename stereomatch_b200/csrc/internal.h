@@ -135,6 +135,14 @@ struct s3dmst_ctx {
     int* fh_sync = nullptr;         // grid barrier + per-round live counters of the forest kernel
     void* pms_scratch = nullptr;
     size_t pms_scratch_cap = 0;
+    // label-range sharding (comm.cu): NCCL communicator bound at run time, its stream, the global-minimum buffer
+    void* comm = nullptr;
+    int comm_rank = 0, comm_nranks = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_comm[2] = {nullptr, nullptr}, ev_comm_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool comm_timed = false;
+    double* gmin = nullptr;
+    size_t gmin_cap = 0;
     float* abc_init = nullptr;      // the reference's random plane initialisation for (abc_init_w x abc_init_h, abc_init_d), kept on the device
     int abc_init_w = 0, abc_init_h = 0, abc_init_d = 0;
     uint32_t pms_round[2] = {0, 0};  // rounds of the library's generator run since the view's labels were (re)set: the RNG counter

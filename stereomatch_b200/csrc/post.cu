@@ -117,11 +117,6 @@ __global__ void __launch_bounds__(256) k_lr_fill(int W, float* __restrict__ left
     for (int x = x0; x < x1 && cnt < 32; x++, cnt++) row[x] = outv[cnt];
 }
 
-__global__ void k_minloc_mask(int N, const double* __restrict__ best, const double* __restrict__ gmin, int32_t* disp) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < N && best[p] != gmin[p]) disp[p] = 0x7fffffff;
-}
-
 int s3_label_to_disp(s3dmst_ctx* ctx, int view) {
     View& V = ctx->v[view];
     if (!V.labels_ready || V.D <= 0) return s3_fail(ctx, S3DMST_E_STATE, "label_to_disp: labels and a cost volume (Dmax) required");
@@ -152,13 +147,6 @@ int s3_lr_check(s3dmst_ctx* ctx, int fill) {
         S3_LAUNCH_CHECK();
     }
     S3_EV_END(S3DMST_T_POST, 0);
-    return 0;
-}
-
-int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev) {
-    View& V = ctx->v[view];
-    k_minloc_mask<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, V.best, global_min_dev, V.disp_i);
-    S3_LAUNCH_CHECK();
     return 0;
 }
 

@@ -12,8 +12,10 @@ Two ways the path shards:
                  all_reduce(MIN) of the disparity                       -> lowest d attaining the minimum
             which is exactly the reference tie rule (strict '<' over ascending d, Stereo3DMST.cpp:177).
 
-`minloc_reduce` is written on torch tensors so the same code runs over NCCL on GPUs and over gloo on CPU
-(tests/test_parallel_gloo.py).
+On the GPU the reduction lives in the C library (s3dmst_comm_init / s3dmst_aggregate_dense_sharded, csrc/comm.cu:
+NCCL bound at run time, no host synchronisation, the left view's reduction overlapping the right view's aggregation);
+`comm_init_from_torch` only carries the 128-byte ncclUniqueId from rank 0 to the other ranks.  `minloc_reduce` is the
+same reduction written on torch tensors so that it also runs over gloo on CPU (tests/test_parallel_gloo.py).
 """
 from __future__ import annotations
 
@@ -41,7 +43,7 @@ def minloc_reduce(best, disp, group=None, mask_fn=None):
     """In-place MIN-LOC all-reduce of (best cost [N] float64, disparity [N] int32) tensors over `group`.
 
     mask_fn(global_min) must set disp to INT32_MAX wherever the local cost differs from the global minimum;
-    the default does it with torch ops (CPU / any device), the GPU path passes Stereo3DMST.minloc_mask.
+    the default does it with torch ops (the GPU path does not come through here: csrc/comm.cu).
     Returns (global_min, disp)."""
     import torch
     import torch.distributed as dist
@@ -56,42 +58,18 @@ def minloc_reduce(best, disp, group=None, mask_fn=None):
     return gmin, disp
 
 
-class _DevArray:
-    """Zero-copy view of device memory owned by the C library, for torch.as_tensor()."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
-
-
-def dense_result_tensors(eng, view):
-    """torch views (no copy) of the context's dense result: (best cost f64 [N], disparity i32 [N])."""
-    import torch
-
-    pb, pd = eng.dense_result_dev(view)
-    best = torch.as_tensor(_DevArray(pb, eng.N, "<f8"), device="cuda")
-    disp = torch.as_tensor(_DevArray(pd, eng.N, "<i4"), device="cuda")
-    return best, disp
-
-
-def aggregate_dense_label_sharded(eng, view, D, group=None):
-    """Label-sharded dense aggregation of one view: this rank's labels on its GPU, then the MIN-LOC reduction.
-    On return every rank's context holds the global disparity / best cost (device side)."""
+def comm_init_from_torch(eng, group=None):
+    """Give `eng` (one context per rank) its own NCCL communicator spanning `group`: rank 0 makes the ncclUniqueId with the
+    C library, torch.distributed only broadcasts those 128 bytes."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    d0, d1 = label_range(D, world, rank)
-    best, disp = dense_result_tensors(eng, view)
-    if d1 > d0:
-        eng.aggregate_dense(view, d0, d1, fetch=False)
-    else:  # more ranks than label blocks: contribute the identity of MIN-LOC
-        best.fill_(float(np.finfo(np.float64).max))
-        disp.fill_(INT32_MAX)
-    eng.sync()
-    torch.cuda.synchronize()
-    gmin, _ = minloc_reduce(best, disp, group,
-                            mask_fn=lambda gmin: (torch.cuda.synchronize(), eng.minloc_mask(view, gmin.data_ptr()), eng.sync()))
-    best.copy_(gmin)  # the context now holds the global minimum next to the global disparity
-    torch.cuda.synchronize()
-    return best, disp
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    eng.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+    return rank, world

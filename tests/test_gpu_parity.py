@@ -628,8 +628,10 @@ def test_full_size_c2_properties(api, oracle):
 
 
 def test_label_sharded_two_gpus_nccl(api, oracle):
-    """BASELINE config C5 in small: one pair, label range split over 2 GPUs (torchrun, NCCL), MIN-LOC reduction;
-    every rank's result must equal the oracle's full-range result bit for bit (tools/label_sharded.py --check)."""
+    """BASELINE config C5 in small: one pair, label range split over 2 GPUs (torchrun), MIN-LOC over the library's own NCCL
+    communicator; every rank's result must equal the oracle's full-range result bit for bit (tools/label_sharded.py).
+    Needs 2 GPUs: on the single-GPU test box tests/test_comm_c.py covers the same entry points with one rank, and
+    bench.py --gpus N runs this check on the driver's multi-GPU boxes."""
     import subprocess
     import sys
     import torch
@@ -637,9 +639,31 @@ def test_label_sharded_two_gpus_nccl(api, oracle):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", os.path.join(root, "tools", "label_sharded.py"), "--check"], capture_output=True, text=True, timeout=600)
+                        "--master-port", "29533", os.path.join(root, "tools", "label_sharded.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"check": true' in r.stdout
+
+
+def test_label_sharded_reduce_partial_ranges(api, oracle):
+    """s3dmst_reduce_minloc on a one-rank communicator is the identity on (best, disparity); s3dmst_comm_label_range
+    partitions like stereomatch_b200.parallel.label_range (the gloo tests' reference)."""
+    from stereomatch_b200 import parallel
+    W, H, D = 160, 96, 40
+    L, R, _ = make(W, H, D, 19, 0)
+    eng = api.Stereo3DMST()
+    eng.comm_init(eng.comm_unique_id(), 0, 1)
+    assert eng.comm_label_range(D) == parallel.label_range(D, 1, 0)
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    eng.build_cost_volume(D)
+    disp, best = eng.aggregate_dense(0, 8, 24)
+    eng.reduce_minloc(0)
+    d2, b2 = eng.get_dense_result(0)
+    assert np.array_equal(disp, d2) and np.array_equal(bits(best), bits(b2))
+    lv, _ = oracle.cost_adgrad(L, R, D)
+    do, bo, _ = oracle.aggregate_dense(oracle.forest(L), lv, 8, 24)
+    assert np.array_equal(d2, do) and np.array_equal(bits(b2), bits(bo))
+    eng.close()
 
 
 def test_full_size_c3_pms_properties(api, oracle):
