@@ -187,6 +187,22 @@ int s3dmst_get_disparity(s3dmst_ctx* ctx, int view, float* disp);
 /* a14 leftRightConsistencyCheck (:632-710): invalid left pixels -> 0; fill != 0 runs the scan-line fill. */
 int s3dmst_lr_check(s3dmst_ctx* ctx, int fill);
 
+/* Post-filters the reference's author ran around the same outputs.
+ * s3dmst_get_lr_mask: the left view's invalid-pixel mask of the last s3dmst_lr_check (1 = invalid), uint8 [H*W].
+ * s3dmst_weighted_median: weightedMedianFilter (src/PatchMatchStereoGPU.cu:2436-2599) on a view's disparity map, applied
+ *   to the pixels of `mask` (host uint8 [H*W]; NULL = the left-right check's mask, left view only): window (2*radius+1)^2
+ *   (the reference: radius 10), weight exp(-sqrt(|dR|+|dG|+|dB|) * gamma) against the centre pixel of the view's image
+ *   (gamma 0.1 for 0..255 intensities), stable sort by disparity, first disparity whose running weight reaches half.
+ *   Every pixel reads the map as it was before the call (the reference filters in place and races).
+ * s3dmst_wmf_table: the 766 weights exp(-sqrt(i) * gamma) the filter uses (host-side, no device needed): parity dumps.
+ * s3dmst_norm_factor: 1 / (tree filter of the all-ones volume) per pixel, double [H*W] (ComputeMSTCostNormFactor /
+ *   cost_norm_factor, PatchMatchStereoGPU.cu:5333-5429, :5898-5919): multiplying a view's aggregated costs by it is the
+ *   reference's "normalised aggregation" (a per-pixel positive factor: it rescales `best`, never changes a winner). */
+int s3dmst_get_lr_mask(s3dmst_ctx* ctx, uint8_t* mask);
+int s3dmst_weighted_median(s3dmst_ctx* ctx, int view, int radius, float gamma, const uint8_t* mask);
+void s3dmst_wmf_table(float gamma, float* tab766);
+int s3dmst_norm_factor(s3dmst_ctx* ctx, int view, double* norm_factor);
+
 /* The step after the path in its caller (src/stereo_Yin.cpp:218-243): left disparities below disp_floor are raised to it
  * (in the context's left map), then cv::reprojectImageTo3D(disp, xyz, Q, handle_missing) with the 4x4 row-major Q of
  * stereoRectify — bit-identical to OpenCV's CV_32F path — and the packed colour of the point cloud

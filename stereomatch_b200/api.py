@@ -46,10 +46,17 @@ ABI_SYMBOLS = [
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
     "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
     "s3dmst_comm_unique_id", "s3dmst_comm_init", "s3dmst_comm_destroy", "s3dmst_comm_label_range", "s3dmst_reduce_minloc", "s3dmst_aggregate_dense_sharded",
-    "s3dmst_comm_minloc_ms",
+    "s3dmst_comm_minloc_ms", "s3dmst_get_lr_mask", "s3dmst_weighted_median", "s3dmst_wmf_table", "s3dmst_norm_factor",
 ]
 
 _lib = None
+
+
+def wmf_table(gamma=0.1):
+    """float32 [766]: the weights exp(-sqrt(i) * gamma) of the weighted median filter (host-side call, no GPU needed)."""
+    tab = np.empty(766, np.float32)
+    load_library().s3dmst_wmf_table(C.c_float(gamma), tab.ctypes.data_as(c_p))
+    return tab
 
 
 def remap_table():
@@ -114,6 +121,11 @@ def load_library():
     L.s3dmst_stage_ms.restype = C.c_double
     L.s3dmst_launch_count.argtypes = [c_p]
     L.s3dmst_launch_count.restype = C.c_longlong
+    L.s3dmst_get_lr_mask.argtypes = [c_p, c_p]
+    L.s3dmst_weighted_median.argtypes = [c_p, C.c_int, C.c_int, C.c_float, c_p]
+    L.s3dmst_wmf_table.argtypes = [C.c_float, c_p]
+    L.s3dmst_wmf_table.restype = None
+    L.s3dmst_norm_factor.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_comm_unique_id.argtypes = [c_p]
     L.s3dmst_comm_init.argtypes = [c_p, c_p, C.c_int, C.c_int]
     L.s3dmst_comm_destroy.argtypes = [c_p]
@@ -412,6 +424,22 @@ class Stereo3DMST:
 
     def lr_check(self, fill=False):
         self._ck(self.L.s3dmst_lr_check(self.h, int(fill)))
+
+    def get_lr_mask(self):
+        m = np.empty(self.N, np.uint8)
+        self._ck(self.L.s3dmst_get_lr_mask(self.h, _ptr(m)))
+        return m
+
+    def weighted_median(self, view=0, radius=10, gamma=0.1, mask=None):
+        """weightedMedianFilter (PatchMatchStereoGPU.cu:2436-2599) on the pixels of `mask` (None: the LR check's, left view)."""
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        self._ck(self.L.s3dmst_weighted_median(self.h, view, int(radius), float(gamma), _ptr(mask)))
+
+    def norm_factor(self, view):
+        nf = np.empty(self.N, np.float64)
+        self._ck(self.L.s3dmst_norm_factor(self.h, view, _ptr(nf)))
+        return nf
 
     def reproject_to_3d(self, Q, disp_floor=10.0, handle_missing=True, want_rgb=True):
         """stereo_Yin.cpp:218-243: floor the left disparity map, cv::reprojectImageTo3D with Q, point-cloud colours."""

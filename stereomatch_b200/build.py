@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libs3dmst.so")
-SOURCES = ["api.cu", "image.cu", "rectify.cu", "forest.cu", "cost.cu", "aggregate.cu", "aggregate2.cu", "aggregate3.cu", "pms.cu", "post.cu", "comm.cu"]
+SOURCES = ["api.cu", "image.cu", "rectify.cu", "forest.cu", "cost.cu", "aggregate.cu", "aggregate3.cu", "pms.cu", "post.cu", "postfilter.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
          "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "shared", "-ldl"]

@@ -197,6 +197,7 @@ __global__ void k_wta_finish(int N, int n_slices, const int* __restrict__ node_p
 
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1) {
     View& V = ctx->v[view];
+    S3_TRY(s3_forest_finish_host(ctx));
     if (!V.forest_ready || !V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense: forest and cost volume required");
     if (d0 < 0 || d1 > V.D || d0 >= d1 || (d0 & 1)) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: need 0 <= d0 < d1 <= D and d0 even");
     const int nl = d1 - d0;

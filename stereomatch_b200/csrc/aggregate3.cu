@@ -744,6 +744,10 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         if (views_mask & (1 << view)) first = view;
     if (first < 0) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: empty view mask");
     const int Dv = ctx->v[first].D, Dp = ctx->v[first].Dp;
+    for (int c = 0; c < nctx; c++) {  // tree counts and sizes of every frame: the only thing the host waits for
+        const int r = s3_forest_finish_host(ctxs[c]);
+        if (r) return c == 0 ? r : s3_fail(ctx, r, "aggregate_dense: frame %d: %s", c, ctxs[c]->err.c_str());
+    }
     for (int c = 0; c < nctx; c++) {
         if (ctxs[c]->device != ctx->device || ctxs[c]->N != ctx->N)
             return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: batched contexts must share the device and the image size");
@@ -926,6 +930,7 @@ int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) { return 
 int s3_pms_flow_plan(s3dmst_ctx* ctx, int view, const int* h_prop_off, double* scratch_dev, PmsFlowPlan* plan) {
     View& V = ctx->v[view];
     if (!ctx->P.exact) return 1;  // proposals are always evaluated in the reference's arithmetic
+    S3_TRY(s3_forest_finish_host(ctx));
     std::vector<std::pair<int, int4>> u;
     for (int t = 0; t < V.T; t++)
         if (!h_prop_off || h_prop_off[t + 1] > h_prop_off[t]) u.push_back({V.h_tree_start[t + 1] - V.h_tree_start[t], make_int4(0, t, 0, 0)});

@@ -8,9 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
-#include <chrono>
 #include <numeric>
-#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -82,7 +80,7 @@ static void free_view(View& V) {
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
     DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
-    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits); DFREE(V.tile_desc); DFREE(V.tree_ntiles);
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits);
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
@@ -108,7 +106,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     S3_CUDA(dalloc(&V.tree_size, n)); S3_CUDA(dalloc(&V.tree_rootpix, n));
     S3_CUDA(dalloc(&V.tree_start, n + 1)); S3_CUDA(dalloc(&V.tree_depth, n)); S3_CUDA(dalloc(&V.unit_tree, n));
     S3_CUDA(dalloc(&V.node_pixel, n)); S3_CUDA(dalloc(&V.pixel_node, n)); S3_CUDA(dalloc(&V.parent, n));
-    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.leaf_bits, n / 32 + 2)); S3_CUDA(dalloc(&V.tile_desc, 4 * n)); S3_CUDA(dalloc(&V.tree_ntiles, n));
+    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.leaf_bits, n / 32 + 2));
     S3_CUDA(dalloc(&V.lvl_start, 2 * n + 2));
     S3_CUDA(dalloc(&V.disp_i, n)); S3_CUDA(dalloc(&V.best, n)); S3_CUDA(dalloc(&V.abc, 3 * n)); S3_CUDA(dalloc(&V.min_cost, n));
     S3_CUDA(dalloc(&V.disp_f, n)); S3_CUDA(dalloc(&V.lr_mask, n));
@@ -119,8 +117,16 @@ static int set_size(s3dmst_ctx* ctx, int W, int H) {
     if (W < 1 || H < 1 || (long long)W * H > (1ll << 27)) return s3_fail(ctx, S3DMST_E_ARG, "image size %dx%d unsupported", W, H);
     if (ctx->W == W && ctx->H == H) return 0;
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
+    ctx->W = ctx->H = ctx->N = 0;
+    ctx->forest_pending = 0;
+    for (int i = 0; i < 2; i++) {
+        const int r = alloc_view(ctx, ctx->v[i], W * H);
+        if (r) {  // a failed allocation leaves a context without images, not one that claims buffers it does not have
+            for (int k = 0; k < 2; k++) free_view(ctx->v[k]);
+            return r;
+        }
+    }
     ctx->W = W; ctx->H = H; ctx->N = W * H;
-    for (int i = 0; i < 2; i++) S3_TRY(alloc_view(ctx, ctx->v[i], ctx->N));
     return 0;
 }
 
@@ -234,6 +240,7 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
 const char* s3dmst_last_error(const s3dmst_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int s3dmst_sync(s3dmst_ctx* ctx) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -270,6 +277,7 @@ static int set_images_impl(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8
                                   ctx->stream));
         ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
     }
+    ctx->forest_pending = 0;
     if (sync) S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
     return 0;
 }
@@ -329,6 +337,8 @@ int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     View& V = ctx->v[view];
     if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "forest_info: no forest");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(s3_forest_finish_host(ctx));
     if (num_trees) *num_trees = V.T;
     if (max_depth) {
         S3_TRY(s3_forest_depths(ctx, view));
@@ -353,6 +363,8 @@ int s3dmst_get_forest(s3dmst_ctx* ctx, int view, uint16_t* edge_weight, uint8_t*
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     View& V = ctx->v[view];
     if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "get_forest: no forest");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(s3_forest_finish_host(ctx));
     const size_t N = ctx->N;
     D2H(edge_weight, V.ew, 2 * N * sizeof(uint16_t));
     D2H(edge_mask, V.mask, 2 * N);
@@ -393,8 +405,7 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     if (tree_start[T] != N) return s3_fail(ctx, S3DMST_E_ARG, "set_forest: tree_start[T] != W*H");
     // derive the per-node records the kernels read (children contiguous in BFS order)
     std::vector<NodeUp> nu(N);
-    std::vector<int> level(N, 0), pixel_node(N, -1), tree_id(N, 0), lvl(2 * (size_t)N + 2, 0), depth(T, 0), ntiles(T, 0);
-    std::vector<int4> tdesc(4 * (size_t)N);
+    std::vector<int> level(N, 0), pixel_node(N, -1), tree_id(N, 0), lvl(2 * (size_t)N + 2, 0), depth(T, 0);
     for (int i = 0; i < N; i++) { nu[i].child_begin = 0; nu[i].child_count = 0; nu[i].cw01 = nu[i].cw23 = 0; }
     for (int t = 0; t < T; t++) {
         const int a = tree_start[t], b = tree_start[t + 1];
@@ -424,28 +435,6 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
             if (level[g] != level[g - 1]) L[++d] = g;
         L[++d] = b;
         depth[t] = d;
-        int nt = 0;  // aggregation tiles: <= S3_TILE_NODES consecutive nodes of one level
-        for (int l = 0; l < d; l++)
-            for (int s0 = L[l]; s0 < L[l + 1]; s0 += S3_TILE_NODES) {
-                const int n = std::min(S3_TILE_NODES, L[l + 1] - s0);
-                const int fl = (s0 == L[l] ? S3_TF_FIRST : 0) | (s0 + n >= L[l + 1] ? S3_TF_LAST : 0);
-                tdesc[2 * (size_t)(a + nt)] = make_int4(s0, n, s0 - L[l], fl);
-                tdesc[2 * (size_t)(a + nt) + 1] = make_int4(L[l + 1], l > 0 ? L[l - 1] : 0, 0, 0);
-                nt++;
-            }
-        ntiles[t] = nt;
-        {   // leaf->root order: levels descending, tiles of a level in ascending node order
-            int k = 0;
-            for (int l = d - 1; l >= 0; l--)
-                for (int x = 0; x < nt; x++) {
-                    const int4 A = tdesc[2 * (size_t)(a + x)];
-                    if (A.x >= L[l] && A.x < L[l + 1]) {
-                        tdesc[2 * (size_t)N + 2 * (size_t)(a + k)] = A;
-                        tdesc[2 * (size_t)N + 2 * (size_t)(a + k) + 1] = tdesc[2 * (size_t)(a + x) + 1];
-                        k++;
-                    }
-                }
-        }
     }
     std::vector<int> order(T);
     std::iota(order.begin(), order.end(), 0);
@@ -474,14 +463,12 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.tree_id, tree_id.data(), sizeof(int) * N);
     H2D(V.lvl_start, lvl.data(), sizeof(int) * (N + T + 1));
     H2D(V.tree_depth, depth.data(), sizeof(int) * T);
-    H2D(V.tile_desc, tdesc.data(), sizeof(int4) * 4 * N);
-    H2D(V.tree_ntiles, ntiles.data(), sizeof(int) * T);
     H2D(V.unit_tree, order.data(), sizeof(int) * T);
+    H2D(V.counters + (S3_MAX_ROUNDS - 64), &T, sizeof(int));  // forest.cu CNT_T: the device-side tree count
     H2D(V.tree_rootpix, rootpix.data(), sizeof(int) * T);
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     V.T = T;
     V.h_tree_start.assign(tree_start, tree_start + T + 1);
-    V.h_unit_tree = order;
     return s3_forest_finalize_host(ctx, view);
 }
 
@@ -504,6 +491,7 @@ int s3dmst_set_cost_volume(s3dmst_ctx* ctx, int view, const float* vol, int D, i
 }
 
 int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !vol) return s3_fail(ctx, S3DMST_E_ARG, "get_cost_volume: bad arguments");
     View& V = ctx->v[view];
     if (!V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "get_cost_volume: no volume");
@@ -524,7 +512,7 @@ int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* d
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     S3_CUDA(cudaSetDevice(ctx->device));
     {
-        int rc = ctx->P.agg_kernel == 1 ? 1 : ctx->P.agg_kernel == 2 ? s3_aggregate_dense2(ctx, 1 << view, d0, d1) : s3_aggregate_flow(ctx, 1 << view, d0, d1);
+        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 1 << view, d0, d1);
         if (rc == 1) rc = s3_aggregate_dense(ctx, view, d0, d1);  // simple kernel: any even d0, any depth
         if (rc) return rc;
     }
@@ -536,6 +524,7 @@ int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* d
 }
 
 int s3dmst_get_aggregated(s3dmst_ctx* ctx, int view, double* agg) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !agg) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     View& V = ctx->v[view];
     if (!V.agg_ready || !ctx->P.keep_aggregated) return s3_fail(ctx, S3DMST_E_STATE, "get_aggregated: needs keep_aggregated and a dense run");
@@ -560,11 +549,13 @@ int s3dmst_dense_result_dev(s3dmst_ctx* ctx, int view, double** best_cost_dev, i
 }
 
 int s3dmst_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !global_min_dev) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     return s3_minloc_mask(ctx, view, global_min_dev);
 }
 
 int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     return s3_dense_to_disp(ctx, view);
 }
@@ -579,6 +570,7 @@ int s3dmst_set_labels(s3dmst_ctx* ctx, int view, const float* abc) {
     return 0;
 }
 int s3dmst_get_labels(s3dmst_ctx* ctx, int view, float* abc) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !abc) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     D2H(abc, ctx->v[view].abc, sizeof(float) * 3 * ctx->N);
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -593,6 +585,7 @@ int s3dmst_reset_min_cost(s3dmst_ctx* ctx, int view) {
     return 0;
 }
 int s3dmst_get_min_cost(s3dmst_ctx* ctx, int view, double* mc) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !mc) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     D2H(mc, ctx->v[view].min_cost, sizeof(double) * ctx->N);
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -620,17 +613,20 @@ int s3dmst_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed) {
 }
 
 int s3dmst_label_to_disp(s3dmst_ctx* ctx, int view) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     return s3_label_to_disp(ctx, view);
 }
 
 int s3dmst_set_disparity(s3dmst_ctx* ctx, int view, const float* disp) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !disp || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     S3_CUDA(cudaMemcpyAsync(ctx->v[view].disp_f, disp, sizeof(float) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 int s3dmst_get_disparity(s3dmst_ctx* ctx, int view, float* disp) {
+    S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !disp) return s3_fail(ctx, S3DMST_E_ARG, "bad arguments");
     D2H(disp, ctx->v[view].disp_f, sizeof(float) * ctx->N);
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -640,6 +636,28 @@ int s3dmst_get_disparity(s3dmst_ctx* ctx, int view, float* disp) {
 int s3dmst_lr_check(s3dmst_ctx* ctx, int fill) {
     S3_CUDA(cudaSetDevice(ctx->device));
     return s3_lr_check(ctx, fill);
+}
+
+int s3dmst_get_lr_mask(s3dmst_ctx* ctx, uint8_t* mask) {
+    if (!mask || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "get_lr_mask: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_CUDA(cudaMemcpyAsync(mask, ctx->v[0].lr_mask, (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int s3dmst_weighted_median(s3dmst_ctx* ctx, int view, int radius, float gamma, const uint8_t* mask) {
+    if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(s3_weighted_median(ctx, view, radius, gamma, mask));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int s3dmst_norm_factor(s3dmst_ctx* ctx, int view, double* norm_factor) {
+    if (view < 0 || view > 1 || !norm_factor) return s3_fail(ctx, S3DMST_E_ARG, "norm_factor: bad arguments");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_norm_factor(ctx, view, norm_factor);
 }
 
 int s3dmst_reproject_to_3d(s3dmst_ctx* ctx, const double* Q, float disp_floor, int handle_missing, float* xyz, uint32_t* rgb) {
@@ -656,7 +674,7 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     S3_EV_END(S3DMST_T_FOREST, 0);
     S3_TRY(s3_cost_adgrad(ctx, D, 0));
     {
-        int rc = ctx->P.agg_kernel == 1 ? 1 : ctx->P.agg_kernel == 2 ? s3_aggregate_dense2(ctx, 3, 0, D) : s3_aggregate_flow(ctx, 3, 0, D);  // both views' trees in one launch
+        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 3, 0, D);  // both views' trees in one launch
         if (rc == 1) {
             rc = 0;
             for (int view = 0; view < 2 && !rc; view++) rc = s3_aggregate_dense(ctx, view, 0, D);
@@ -706,66 +724,22 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
     for (int c = 0; c < n; c++)
         if (!ctxs[c] || ctxs[c]->device != ctx->device || ctxs[c]->N != ctx->N || ctxs[c]->N == 0)
             return s3_fail(ctx, S3DMST_E_ARG, "run_dense_batch: contexts must share the device and hold images of one size");
-    // forest + cost volume per frame: independent streams, one host thread each (the forest stage reads tree counts back)
-    const bool dbg = getenv("S3_DEBUG_BATCH") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    if (dbg)
-        for (int c = 0; c < n; c++)
-            for (int i = 0; i < 8; i++)
-                if (!ctxs[c]->dbg_ev[i]) cudaEventCreate(&ctxs[c]->dbg_ev[i]);
-    const double t_begin = now();
-    std::vector<double> t_forest(n, 0.0);
-    static const bool joint_fh = getenv("S3_FH_JOINT") && atoi(getenv("S3_FH_JOINT")) != 0;
-    std::vector<int> rc(n, 0);
-    auto front = [&](int c) {
+    S3_CUDA(cudaSetDevice(ctx->device));
+    // Front: forest + cost volume of every frame, queued on the frames' own streams by this one host thread.  Nothing
+    // here waits for the device: the tree counts and sizes travel to the host behind the forest kernels, and the joint
+    // aggregation below is the first thing that needs them.
+    for (int c = 0; (phases & 1) && c < n; c++) {
         s3dmst_ctx* cx = ctxs[c];
-        rc[c] = [&]() -> int {
+        const int r = [&]() -> int {
             s3dmst_ctx* ctx = cx;  // the error macros report into this frame's context
-            S3_CUDA(cudaSetDevice(ctx->device));
-            if (joint_fh)
-                S3_TRY(s3_forest_post(ctx, 3));
-            else {
-                memset(ctx->ev_set, 0, sizeof ctx->ev_set);
-                S3_EV_BEGIN(S3DMST_T_FOREST, 0);
-                S3_TRY(s3_forest_stage_mask(ctx, 3));
-            }
-            S3_EV_END(S3DMST_T_FOREST, 0);
-            if (dbg) { cudaStreamSynchronize(ctx->stream); t_forest[c] = now(); }
-            S3_TRY(s3_cost_adgrad(ctx, D, 0));
-            if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[5], ctx->stream);
-            if (dbg) cudaStreamSynchronize(ctx->stream);
-            return 0;
-        }();
-    };
-    // Optional (S3_FH_JOINT=1): image stages on the frames' own streams, then ONE forest-kernel launch per
-    // S3_FH_MAX_VIEWS / 2 frames.  Measured at C2, 8 frames: the joint launch is bound by L2 sector throughput
-    // (22.5 ms until all forests are done) and loses to per-frame launches overlapping on the streams (18 ms).
-    for (int c = 0; (phases & 1) && joint_fh && c < n; c++) {
-        s3dmst_ctx* cx = ctxs[c];
-        memset(cx->ev_set, 0, sizeof cx->ev_set);
-        int r = [&]() -> int {
-            s3dmst_ctx* ctx = cx;
+            memset(ctx->ev_set, 0, sizeof ctx->ev_set);
             S3_EV_BEGIN(S3DMST_T_FOREST, 0);
-            return s3_forest_pre(ctx, 3);
+            S3_TRY(s3_forest_stage_mask(ctx, 3));
+            S3_EV_END(S3DMST_T_FOREST, 0);
+            return s3_cost_adgrad(ctx, D, 0);
         }();
         if (r) return c == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frame %d: %s", c, cx->err.c_str());
     }
-    for (int c0 = 0; (phases & 1) && joint_fh && c0 < n; c0 += S3_FH_MAX_VIEWS / 2) {
-        const int r = s3_fh_launch_multi(ctxs + c0, std::min(S3_FH_MAX_VIEWS / 2, n - c0), 3);
-        if (r) return c0 == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frames %d..: %s", c0, ctxs[c0]->err.c_str());
-    }
-    if (!(phases & 1)) {
-    } else if (n == 1)
-        front(0);
-    else {
-        std::vector<std::thread> th;
-        for (int c = 0; c < n; c++) th.emplace_back(front, c);
-        for (auto& t : th) t.join();
-    }
-    for (int c = 0; c < n; c++)
-        if (rc[c]) return c == 0 ? rc[c] : s3_fail(ctx, rc[c], "run_dense_batch: frame %d: %s", c, ctxs[c]->err.c_str());
-    S3_CUDA(cudaSetDevice(ctx->device));
-    const double t_front = now();
     if (!(phases & 2)) return 0;
     {
         int r = ctx->P.agg_kernel == 0 ? s3_aggregate_flow_multi(ctxs, n, 3, 0, D) : 1;
@@ -788,20 +762,8 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
         if (left_disp && left_disp[c]) S3_CUDA(cudaMemcpyAsync(left_disp[c], cx->v[0].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
         if (right_disp && right_disp[c]) S3_CUDA(cudaMemcpyAsync(right_disp[c], cx->v[1].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
     }
-    if (left_disp || right_disp || dbg)
+    if (left_disp || right_disp)
         for (int c = 0; c < n; c++) S3_CUDA(cudaStreamSynchronize(ctxs[c]->stream));
-    if (dbg) {
-        double tf = 0.0;
-        for (int c = 0; c < n; c++) tf = std::max(tf, t_forest[c]);
-        for (int c = 0; c < n && (phases & 1); c++) {
-            float t[6] = {0, 0, 0, 0, 0, 0};
-            for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], ctxs[0]->dbg_ev[0], ctxs[c]->dbg_ev[i]);
-            float t0 = 0;
-            cudaEventElapsedTime(&t0, ctxs[0]->dbg_ev[0], ctxs[c]->dbg_ev[0]);
-            fprintf(stderr, "  frame %d: start %.2f | image %.2f | FH %.2f | labels %.2f | BFS %.2f | cost %.2f (ms since frame 0 started)\n", c, t0, t[1], t[2], t[3], t[4], t[5]);
-        }
-        fprintf(stderr, "[batch %d] forests done +%.2f ms, cost volumes done +%.2f ms, total %.2f ms\n", n, tf - t_begin, t_front - t_begin, now() - t_begin);
-    }
     return 0;
 }
 

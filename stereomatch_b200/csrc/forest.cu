@@ -30,10 +30,11 @@
 
 #include "internal.h"
 
+#define CNT_T (S3_MAX_ROUNDS - 64)          // number of trees (device side)
+#define CNT_UNIT_HIST (S3_MAX_ROUNDS - 256) // [64] size-class histogram + cursors of the work order
 #define CNT_ERR (S3_MAX_ROUNDS - 1)
 #define CNT_LIST (S3_MAX_ROUNDS - 2)
 #define CNT_ROUNDS (S3_MAX_ROUNDS - 3)
-#define CNT_FIRSTS (S3_MAX_ROUNDS - 4)
 #define CNT_ACT (S3_MAX_ROUNDS - 20)  // [2] live-list lengths of the FH rounds
 #define ROUND_CAP (S3_FH_ROUNDS - 32)
 
@@ -187,10 +188,7 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
     const int lane = threadIdx.x & 31;
     unsigned bar_target = 0;
     int round = 0;
-    long long tA = 0, tB = 0, tS = 0, t0 = clock64(), t1;
-    long long visits = 0;
     __shared__ int s_cnt;
-#define FH_T(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
 #define FH_BAR() fh_grid_bar(AA.bar + 32 * vi, bar_target, (unsigned)nblk)  // the views never wait for each other
 
     // ------------------------------------------------------------------ FH
@@ -259,14 +257,11 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
                     off = __shfl_sync(0xffffffffu, off, 0);
                     if (live) dst[off + __popc(bal & ((1u << lane) - 1))] = en;
                 }
-                visits++;
             }
             __syncthreads();
             const int my_cnt = s_cnt;
             if (threadIdx.x == 0 && my_cnt) atomicAdd(AA.gcnt + S3_FH_MAX_VIEWS * round + vi, my_cnt);
-            FH_T(tA);
             FH_BAR();
-            FH_T(tS);
             n_live = __ldcg(AA.gcnt + S3_FH_MAX_VIEWS * round + vi);
             // ---- phase 2: decide every edge that is the minimum of one of its components
             for (int pos = threadIdx.x; pos < my_cnt; pos += blockDim.x) {
@@ -295,20 +290,11 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
                     dst[pos] = en;
                 }
             }
-            FH_T(tB);
             FH_BAR();
-            FH_T(tS);
             my_src = my_cnt;
             par ^= 1;
         }
     }
-    if (gtid == 0) {
-        A.counters[S3_MAX_ROUNDS - 8] = (int)(tA >> 10); A.counters[S3_MAX_ROUNDS - 7] = (int)(tB >> 10);
-        A.counters[S3_MAX_ROUNDS - 6] = (int)(visits); A.counters[S3_MAX_ROUNDS - 5] = (int)(tS >> 10);
-        A.counters[S3_MAX_ROUNDS - 9] = 0; A.counters[S3_MAX_ROUNDS - 10] = round;
-        tA = 0;
-    }
-    t0 = clock64();
 
     // ------------------------------------------------------------------ min-size merge
     const int E2 = 2 * A.N;
@@ -391,8 +377,7 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
         }
         FH_BAR();
     }
-    FH_T(tA);
-    if (gtid == 0) { A.counters[CNT_ROUNDS] = round; A.counters[S3_MAX_ROUNDS - 11] = (int)(tA >> 10); }
+    if (gtid == 0) A.counters[CNT_ROUNDS] = round;
 }
 
 __global__ void k_uf_init(int N, FHComp* comp, int* parent, unsigned long long* resv, int* minpix) {
@@ -410,7 +395,11 @@ __global__ void k_uf_init(int N, FHComp* comp, int* parent, unsigned long long* 
     minpix[i] = 0x7fffffff;
 }
 
-// ---- labelling: trees numbered by their minimum pixel (first-seen raster order, :352-367)
+// ---- labelling: trees numbered by their minimum pixel (first-seen raster order, :352-367).  Entirely on the device:
+// a tree's number is the rank of its minimum pixel among all minimum pixels = an exclusive scan of the "I am my
+// tree's minimum pixel" flags over the image; tree_start is a scan of the tree sizes (exact: every union added the
+// hooked size).  The host learns T and the sizes from ONE asynchronous copy it only waits for when it builds the
+// aggregation work list — by then the BFS and the cost kernels are already queued behind these.
 __global__ void k_label_roots(int N, int* parent, int* root_of, int* minpix) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
@@ -418,30 +407,114 @@ __global__ void k_label_roots(int N, int* parent, int* root_of, int* minpix) {
     root_of[p] = r;
     atomicMin(minpix + r, p);
 }
-__global__ void k_label_firsts(int N, const int* __restrict__ root_of, const int* __restrict__ minpix, const int* __restrict__ uf_size,
-                               int* firsts, int* sizes, int* counter) {
+__global__ void k_label_flags(int N, const int* __restrict__ root_of, const int* __restrict__ minpix, int* __restrict__ flag) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const int r = root_of[p];
-    if (minpix[r] == p) {  // the minimum pixel of its tree: one record (pixel, tree size) per tree, in arrival order
-        const int i = atomicAdd(counter, 1);
-        firsts[i] = p;
-        sizes[i] = uf_size[FHC_I * r];
+    if (p < N) flag[p] = minpix[root_of[p]] == p;
+}
+// exclusive scan of n ints (n on the host, or *n_dev when n_dev != nullptr): 1024 elements per CTA, block totals scanned
+// by one CTA, then added back.  out[n] = total.
+__global__ void __launch_bounds__(1024) k_scan_local(int n_host, const int* n_dev, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ bsum) {
+    const int n = n_dev ? *n_dev : n_host;
+    __shared__ int s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i = blockIdx.x * 1024 + tid;
+    if (blockIdx.x * 1024 >= n) { if (tid == 0) bsum[blockIdx.x] = 0; return; }
+    const int v = i < n ? in[i] : 0;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const int w = s_w[lane];
+        int winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += u;
+        }
+        s_w[lane] = winc - w;
+        if (lane == 31) bsum[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    if (i < n) out[i] = s_w[wid] + inc - v;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int nb, int* bsum) {  // in-place exclusive scan of nb block totals, total -> bsum[nb]
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int b = 0; b < nb; b += 1024) {
+        const int i = b + tid;
+        const int v = i < nb ? bsum[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = s_w[lane];
+            int winc = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += u;
+            }
+            s_w[lane] = winc - w;
+        }
+        __syncthreads();
+        const int run = s_run;
+        if (i < nb) bsum[i] = run + s_w[wid] + inc - v;
+        __syncthreads();
+        if (tid == 1023) s_run = run + s_w[31] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) bsum[nb] = s_run;
+}
+__global__ void k_scan_apply(int n_host, const int* n_dev, int* __restrict__ out, const int* __restrict__ bsum, int nb, int* total_out) {
+    const int n = n_dev ? *n_dev : n_host;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += bsum[i >> 10];
+    if (i == 0) {
+        out[n] = bsum[nb];
+        if (total_out) *total_out = bsum[nb];
     }
 }
-__global__ void k_label_mark(int T, const int* __restrict__ rootpix, int* tid_at, int* tree_size) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    tid_at[rootpix[t]] = t;
-    tree_size[t] = 0;
-}
-__global__ void k_label_ids(int N, const int* __restrict__ root_of, const int* __restrict__ minpix,
-                            const int* __restrict__ tid_at, int* tree_id, int* tree_size) {
+// the minimum pixel of tree t: its rank, its pixel, its size
+__global__ void k_label_assign(int N, const int* __restrict__ flag, const int* __restrict__ rank, const int* __restrict__ root_of,
+                               const int* __restrict__ uf_size, int* __restrict__ rootpix, int* __restrict__ tree_size, int* __restrict__ tid_at) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const int t = tid_at[minpix[root_of[p]]];
-    tree_id[p] = t;
-    atomicAdd(tree_size + t, 1);
+    if (p >= N || !flag[p]) return;
+    const int t = rank[p];
+    rootpix[t] = p;
+    tree_size[t] = uf_size[FHC_I * root_of[p]];
+    tid_at[p] = t;
+}
+__global__ void k_label_ids2(int N, const int* __restrict__ root_of, const int* __restrict__ minpix,
+                             const int* __restrict__ tid_at, int* tree_id) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) tree_id[p] = tid_at[minpix[root_of[p]]];
+}
+// work order of the per-tree kernels (BFS): trees by decreasing size class (log2 of the node count); the order inside
+// a class is arbitrary (it only balances the load)
+__global__ void k_unit_hist(const int* T_dev, const int* __restrict__ tree_size, int* hist) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < *T_dev) atomicAdd(hist + (31 - __clz(max(1, tree_size[t]))), 1);
+}
+__global__ void k_unit_scatter(const int* T_dev, const int* __restrict__ tree_size, int* hist, int* __restrict__ unit_tree) {
+    __shared__ int s_off[32];
+    if (threadIdx.x == 0) {  // offsets of the classes, largest first (hist[32..63] = cursors)
+        int run = 0;
+        for (int b = 31; b >= 0; b--) { s_off[b] = run; run += hist[b]; }
+    }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *T_dev) return;
+    const int b = 31 - __clz(max(1, tree_size[t]));
+    unit_tree[s_off[b] + atomicAdd(hist + 32 + b, 1)] = t;
 }
 
 // ---- per-pixel forest adjacency, pre-sorted: four 16-bit entries (w << 3) | direction (0 up, 1 left, 2 right, 3 down) in
@@ -476,12 +549,11 @@ __global__ void k_pix_adj(int W, int H, const uint16_t* __restrict__ ew, const u
 #endif
 #define BFS_FRONT 512   // frontier entries kept in shared memory per level (wider levels go through global memory)
 struct BfsArgs {
-    int T;
+    const int* T;     // device: number of trees
     const int* unit_tree;
     const int* tree_start;
     const int* tree_rootpix;
     const unsigned long long* adjw;
-    int* dbg_out;     // development counters (4 ints)
     uint32_t* front;  // [N] frontier words by node (pixel | direction of the parent << 28), the wide-level fallback
     int* node_pixel;
     int* pixel_node;
@@ -492,14 +564,11 @@ struct BfsArgs {
     int4* node_dn;
     int* lvl_start;
     int* tree_depth;
-    int4* tile_desc;
-    int* tree_ntiles;
 };
 struct BfsArgs2 {
     BfsArgs v[2];
     int W, H, NN;
     int grid0;  // CTAs [0, grid0) serve v[0], the rest v[1]: both views' trees re-indexed by one launch
-    int dbg;    // development knobs: 1 = no warm-up loads, 2 = no tile descriptors
 };
 
 #if BFS_INSTR
@@ -535,7 +604,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     const int vi = (int)blockIdx.x >= AA.grid0;
     const BfsArgs& B = AA.v[vi];
     const int bid = vi ? blockIdx.x - AA.grid0 : blockIdx.x, nb = vi ? gridDim.x - AA.grid0 : AA.grid0;
-    const int T = B.T, W = AA.W, NN = AA.NN;
+    const int T = *B.T, W = AA.W, NN = AA.NN;
     const int* __restrict__ unit_tree = B.unit_tree;
     const int* __restrict__ tree_start = B.tree_start;
     const int* __restrict__ tree_rootpix = B.tree_rootpix;
@@ -543,14 +612,13 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     uint32_t* front = B.front;
     int* pixel_node = B.pixel_node;
     NodeUp* node_up = B.node_up; int4* node_dn = B.node_dn; int* lvl_start = B.lvl_start;
-    int* tree_depth = B.tree_depth; int4* tile_desc = B.tile_desc; int* tree_ntiles = B.tree_ntiles;
+    int* tree_depth = B.tree_depth;
     __shared__ int s_warp[BFS_THREADS / 32];
     __shared__ int s_total;
     __shared__ int s_state[4];
     __shared__ uint32_t s_front[2][BFS_FRONT];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const bool warm = !(AA.dbg & 1);
     for (int u = bid; u < T; u += nb) {
         const int t = unit_tree[u];
         const int base = tree_start[t];
@@ -564,9 +632,9 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
         }
         __syncthreads();
         int a = base, b = base + 1, L = 0, cur = 0;
-        const long long tb0 = clock64();
-        long long tq = tb0, q_load = 0, q_scan = 0, q_store = 0, q_sync = 0;
-        (void)tq; (void)q_load; (void)q_scan; (void)q_store; (void)q_sync;
+#if BFS_INSTR
+        long long tq = clock64(), q_load = 0, q_scan = 0, q_store = 0, q_sync = 0;
+#endif
         // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record
         // one child of node g: frontier word, pixel -> node, root->leaf record, warm-up of its own children's lines
         auto emit_child = [&](int g, int pix, uint32_t en, int h, int bnext, int Lc, int curc) {
@@ -577,7 +645,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             else front[h] = fw;
             pixel_node[q] = h;
             node_dn[h] = make_int4(g, (int)(en >> 3), Lc + 1, q);
-            if (warm) {  // q's possible children: rows above and below (q +- 1 share q's line)
+            {  // q's possible children: rows above and below (q +- 1 share q's line)
                 if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
                 if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
             }
@@ -670,59 +738,11 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             __syncthreads();
         }
         __syncthreads();
-        const long long tb1 = clock64();
         if (tid == 0) tree_depth[t] = L;
-        // aggregation tiles (<= S3_TILE_NODES consecutive nodes of one level): one thread per level, block scan of the
-        // per-level tile counts; written twice: root->leaf order (levels ascending) at [0,2N) and leaf->root order
-        // (levels descending) at [2N,4N)
-        for (int dir = 0; dir < ((AA.dbg & 2) ? 0 : 2); dir++) {
-            int run_t = 0;
-            for (int l0 = 0; l0 < L; l0 += BFS_THREADS) {
-                const int li = l0 + tid;                       // position in processing order
-                const int l = dir == 0 ? li : L - 1 - li;      // level
-                int ls = 0, le = 0, cnt = 0;
-                if (li < L) {
-                    ls = lvl[l];
-                    le = lvl[l + 1];
-                    cnt = (le - ls + S3_TILE_NODES - 1) / S3_TILE_NODES;
-                }
-                int incl = cnt;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int vv = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += vv;
-                }
-                if (lane == 31) s_warp[wid] = incl;
-                __syncthreads();
-                if (wid == 0) {
-                    int vv = lane < BFS_THREADS / 32 ? s_warp[lane] : 0;
-                    int iv = vv;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int u2 = __shfl_up_sync(0xffffffffu, iv, o);
-                        if (lane >= o) iv += u2;
-                    }
-                    if (lane < BFS_THREADS / 32) s_warp[lane] = iv - vv;
-                    if (lane == 31) s_total = iv;
-                }
-                __syncthreads();
-                size_t ti = (size_t)(dir ? NN : 0) + (size_t)base + run_t + incl - cnt + s_warp[wid];  // tile index (2 int4 each)
-                if (li < L) {
-                    const int ps = l > 0 ? lvl[l - 1] : 0;
-                    for (int s0 = ls; s0 < le; s0 += S3_TILE_NODES, ti++) {
-                        const int n = min(S3_TILE_NODES, le - s0);
-                        tile_desc[2 * ti] = make_int4(s0, n, s0 - ls, (s0 == ls ? S3_TF_FIRST : 0) | (s0 + n >= le ? S3_TF_LAST : 0));
-                        tile_desc[2 * ti + 1] = make_int4(le, ps, 0, 0);
-                    }
-                }
-                run_t += s_total;
-                __syncthreads();
-            }
-            if (tid == 0) tree_ntiles[t] = run_t;
-        }
         __syncthreads();
 #if BFS_INSTR
         if (u == 0 && tid == 0) printf("bfs cycles/level: load %lld scan %lld store %lld sync %lld\n", q_load / L, q_scan / L, q_store / L, q_sync / L);
 #endif
-        if (u == 0 && tid == 0) { B.dbg_out[0] = (int)((tb1 - tb0) >> 4); B.dbg_out[1] = (int)((clock64() - tb1) >> 4); B.dbg_out[2] = L; B.dbg_out[3] = b - base; }
     }
 }
 
@@ -751,11 +771,9 @@ static void fill_fh_args(s3dmst_ctx* ctx, View& V, FHArgs& A) {
     // Live-list band.  A wide band means fewer rounds (latency: one pair alone on the GPU, 16384/65536), a narrow one
     // fewer futile re-visits of edges whose turn has not come (throughput: contexts set up for batching share the GPU and
     // are bound by random DRAM accesses, 8192/24576).  Measured at C2: batch of 8 20.65 -> 19.77 ms, single 5.00 -> 5.20.
-    static const int env_low = getenv("S3_FH_LOW") ? atoi(getenv("S3_FH_LOW")) : 0;
-    static const int env_high = getenv("S3_FH_HIGH") ? atoi(getenv("S3_FH_HIGH")) : 0;
     const bool batching = ctx->P.fh_ctas > 0;
-    A.band_low = env_low ? env_low : (batching ? 8192 : 16384);
-    A.band_high = env_high ? env_high : (batching ? 24576 : 65536);
+    A.band_low = batching ? 8192 : 16384;
+    A.band_high = batching ? 24576 : 65536;
     A.mask = V.mask; A.e_ra = V.e_ra; A.e_rb = V.e_rb; A.e_flag = V.e_flag; A.counters = V.counters;
 }
 
@@ -805,20 +823,6 @@ int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask) {
 
 int s3_fh_launch(s3dmst_ctx* ctx, int mask) { return s3_fh_launch_multi(&ctx, 1, mask); }
 
-// tree sizes straight from the union-find (exact: every union added the hooked size)
-__global__ void k_label_sizes(int T, const int* __restrict__ rootpix, const int* __restrict__ root_of,
-                              const int* __restrict__ uf_size, int* tid_at, int* tree_size) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    tid_at[rootpix[t]] = t;
-    tree_size[t] = uf_size[FHC_I * root_of[rootpix[t]]];
-}
-__global__ void k_label_ids2(int N, const int* __restrict__ root_of, const int* __restrict__ minpix,
-                             const int* __restrict__ tid_at, int* tree_id) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < N) tree_id[p] = tid_at[minpix[root_of[p]]];
-}
-
 // Forest construction for the views in `mask` (bit 0 left, bit 1 right).  The views are independent, so each
 // device stage is ONE launch covering both (FH+merge: one cluster per view; BFS: one CTA per tree of either
 // view) and the two host round trips (tree count, tree sizes -> offsets and work order) are shared.
@@ -839,106 +843,84 @@ int s3_forest_pre(s3dmst_ctx* ctx, int mask) {
     return 0;
 }
 
-// everything after the forest kernel: tree ids, sizes, BFS re-indexing (reads tree counts back: host-synchronous)
+static int scan_exclusive(s3dmst_ctx* ctx, int n_host, const int* n_dev, int n_max, const int* in, int* out, int* bsum, int* total_out) {
+    const int nb = (n_max + 1023) / 1024;
+    k_scan_local<<<nb, 1024, 0, ctx->stream>>>(n_host, n_dev, in, out, bsum);
+    S3_LAUNCH_CHECK();
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(nb, bsum);
+    S3_LAUNCH_CHECK();
+    k_scan_apply<<<(n_max + 255) / 256, 256, 0, ctx->stream>>>(n_host, n_dev, out, bsum, nb, total_out);
+    S3_LAUNCH_CHECK();
+    return 0;
+}
+
+static int forest_tmax(const s3dmst_ctx* ctx) {  // a tree has at least max(2, min_cc_size) pixels unless the whole image is one small component
+    return std::min(ctx->N, ctx->N / std::max(2, ctx->P.min_cc_size) + 2);
+}
+
+// Everything after the forest kernel, queued without any host synchronisation: tree numbering, tree_start, work order,
+// adjacency records, BFS re-indexing, flat copies — and one copy of (error flag, T, tree sizes) into pinned memory,
+// marked by an event.  s3_forest_finish_host() waits for that event when the host needs the sizes.
 int s3_forest_post(s3dmst_ctx* ctx, int mask) {
     const int N = ctx->N, W = ctx->W, H = ctx->H;
     const int TB = 256;
-    // ONE host round trip: per tree its minimum pixel and size (unordered), plus the kernel's counters.  A tree has at
-    // least max(2, min_cc_size) pixels unless the whole image is one small component.
-    const int Tmax = std::min(N, N / std::max(2, ctx->P.min_cc_size) + 2);
-    int hc[2][16];
-    std::vector<int> rootpix[2], tsize[2];
-    // A context that runs beside others (a batch: one host thread per frame, several ranks per host) must not spin through
-    // the forest kernel's ~8 ms: the copies go to pinned memory and the thread sleeps on a blocking-sync event.  One pair
-    // alone keeps the spinning wait (lowest wake-up latency).
-    const bool sleep_wait = ctx->P.fh_ctas > 0;
-    const size_t pin_view = 16 + 2 * (size_t)Tmax;
-    if (sleep_wait && ctx->h_pin_cap < 2 * pin_view) {
-        if (ctx->h_pin) S3_CUDA(cudaFreeHost(ctx->h_pin));
+    const int Tmax = forest_tmax(ctx);
+    const size_t pin_view = 16 + (size_t)Tmax;
+    if (ctx->h_pin_cap < 2 * pin_view) {
+        if (ctx->h_pin) {
+            S3_CUDA(cudaStreamSynchronize(ctx->stream));
+            S3_CUDA(cudaFreeHost(ctx->h_pin));
+        }
         ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
         S3_CUDA(cudaHostAlloc(&ctx->h_pin, 2 * pin_view * sizeof(int), cudaHostAllocDefault));
         ctx->h_pin_cap = 2 * pin_view;
     }
-    for (int view = 0; view < 2; view++) {
-        if (!(mask & (1 << view))) continue;
-        View& V = ctx->v[view];
-        k_label_roots<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.uf_parent, V.scan_tmp, V.minpix);
-        S3_LAUNCH_CHECK();
-        k_label_firsts<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.scan_tmp, V.minpix, &reinterpret_cast<FHComp*>(V.uf_comp)->size, V.tree_rootpix,
-                                                                  V.tree_size, V.counters + CNT_FIRSTS);
-        S3_LAUNCH_CHECK();
-        rootpix[view].resize(Tmax);
-        tsize[view].resize(Tmax);
-        int* pin = sleep_wait ? ctx->h_pin + view * pin_view : nullptr;
-        S3_CUDA(cudaMemcpyAsync(sleep_wait ? pin : hc[view], V.counters + S3_MAX_ROUNDS - 16, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        S3_CUDA(cudaMemcpyAsync(sleep_wait ? pin + 16 : rootpix[view].data(), V.tree_rootpix, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
-        S3_CUDA(cudaMemcpyAsync(sleep_wait ? pin + 16 + Tmax : tsize[view].data(), V.tree_size, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    if (sleep_wait) {
-        S3_CUDA(cudaEventRecord(ctx->ev_block, ctx->stream));
-        S3_CUDA(cudaEventSynchronize(ctx->ev_block));
-        for (int view = 0; view < 2; view++) {
-            if (!(mask & (1 << view))) continue;
-            const int* pin = ctx->h_pin + view * pin_view;
-            memcpy(hc[view], pin, sizeof(int) * 16);
-            memcpy(rootpix[view].data(), pin + 16, sizeof(int) * Tmax);
-            memcpy(tsize[view].data(), pin + 16 + Tmax, sizeof(int) * Tmax);
-        }
-    } else
-        S3_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int view = 0; view < 2; view++) {
-        if (!(mask & (1 << view))) continue;
-        View& V = ctx->v[view];
-        if (hc[view][15]) return s3_fail(ctx, S3DMST_E_LIMIT, "forest kernel hit the round cap");
-        if (getenv("S3_DEBUG_FH"))
-            fprintf(stderr, "[fh view %d] fh-rounds %d total-rounds %d visits/thread %d | kcycles phase1 %d phase2 %d sync %d merge %d\n", view, hc[view][6],
-                    hc[view][13], hc[view][10], hc[view][8], hc[view][9], hc[view][11], hc[view][5]);
-        const int T = hc[view][16 - (S3_MAX_ROUNDS - CNT_FIRSTS)];
-        if (T <= 0 || T > Tmax) return s3_fail(ctx, S3DMST_E_CUDA, "labelling produced T=%d (bound %d)", T, Tmax);
-        V.T = T;
-        // tree ids = first-seen raster order = by minimum pixel (Stereo3DMST.cpp:352-367)
-        std::vector<int> ord(T);
-        std::iota(ord.begin(), ord.end(), 0);
-        std::sort(ord.begin(), ord.end(), [&](int a, int b) { return rootpix[view][a] < rootpix[view][b]; });
-        std::vector<int> rp(T), ts(T);
-        for (int t = 0; t < T; t++) { rp[t] = rootpix[view][ord[t]]; ts[t] = tsize[view][ord[t]]; }
-        rootpix[view].swap(rp);
-        tsize[view].swap(ts);
-        S3_CUDA(cudaMemcpyAsync(V.tree_rootpix, rootpix[view].data(), sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
-        int* tid_at = V.pixel_node;  // scratch until BFS fills it: [N]
-        k_label_sizes<<<(T + TB - 1) / TB, TB, 0, ctx->stream>>>(T, V.tree_rootpix, V.scan_tmp, &reinterpret_cast<FHComp*>(V.uf_comp)->size, tid_at, V.tree_size);
-        S3_LAUNCH_CHECK();
-        k_label_ids2<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.scan_tmp, V.minpix, tid_at, V.tree_id);
-        S3_LAUNCH_CHECK();
-    }
-    if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[3], ctx->stream);
     BfsArgs2 BA;
     memset(&BA, 0, sizeof BA);
     BA.W = W; BA.H = H; BA.NN = N;
-    BA.dbg = getenv("S3_BFS_DBG") ? atoi(getenv("S3_BFS_DBG")) : 0;
     int nv = 0, grid = 0;
     for (int view = 0; view < 2; view++) {
         if (!(mask & (1 << view))) continue;
         View& V = ctx->v[view];
-        const int T = V.T;
-        V.h_tree_start.assign(T + 1, 0);
-        for (int t = 0; t < T; t++) V.h_tree_start[t + 1] = V.h_tree_start[t] + tsize[view][t];
-        if (V.h_tree_start[T] != N) return s3_fail(ctx, S3DMST_E_CUDA, "tree sizes sum to %d, expected %d", V.h_tree_start[T], N);
-        V.h_unit_tree.resize(T);
-        std::iota(V.h_unit_tree.begin(), V.h_unit_tree.end(), 0);
-        std::stable_sort(V.h_unit_tree.begin(), V.h_unit_tree.end(), [&](int x, int y) { return tsize[view][x] > tsize[view][y]; });
-        S3_CUDA(cudaMemcpyAsync(V.tree_start, V.h_tree_start.data(), sizeof(int) * (T + 1), cudaMemcpyHostToDevice, ctx->stream));
-        S3_CUDA(cudaMemcpyAsync(V.unit_tree, V.h_unit_tree.data(), sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
+        int* root_of = V.scan_tmp;            // [N]
+        int* flag = V.e_rb;                   // [N] (forest-kernel scratch, idle now)
+        int* rank = V.e_ra;                   // [N + 1], block totals behind it
+        int* bsum = V.e_ra + N + 8;
+        int* tid_at = V.pixel_node;           // scratch until the BFS fills it
+        int* T_dev = V.counters + CNT_T;
+        int* hist = V.counters + CNT_UNIT_HIST;
+        k_label_roots<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.uf_parent, root_of, V.minpix);
+        S3_LAUNCH_CHECK();
+        k_label_flags<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, root_of, V.minpix, flag);
+        S3_LAUNCH_CHECK();
+        S3_TRY(scan_exclusive(ctx, N, nullptr, N, flag, rank, bsum, T_dev));
+        k_label_assign<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, flag, rank, root_of, &reinterpret_cast<FHComp*>(V.uf_comp)->size, V.tree_rootpix,
+                                                                  V.tree_size, tid_at);
+        S3_LAUNCH_CHECK();
+        k_label_ids2<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, root_of, V.minpix, tid_at, V.tree_id);
+        S3_LAUNCH_CHECK();
+        S3_TRY(scan_exclusive(ctx, 0, T_dev, Tmax, V.tree_size, V.tree_start, bsum, nullptr));
+        S3_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * 64, ctx->stream));
+        k_unit_hist<<<(Tmax + TB - 1) / TB, TB, 0, ctx->stream>>>(T_dev, V.tree_size, hist);
+        S3_LAUNCH_CHECK();
+        k_unit_scatter<<<(Tmax + TB - 1) / TB, TB, 0, ctx->stream>>>(T_dev, V.tree_size, hist, V.unit_tree);
+        S3_LAUNCH_CHECK();
+        // the host's copy: [0] round-cap flag of the forest kernel, [1] T, [16 ..] tree sizes
+        int* pin = ctx->h_pin + view * pin_view;
+        S3_CUDA(cudaMemcpyAsync(pin, V.counters + CNT_ERR, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaMemcpyAsync(pin + 1, T_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        S3_CUDA(cudaMemcpyAsync(pin + 16, V.tree_size, sizeof(int) * Tmax, cudaMemcpyDeviceToHost, ctx->stream));
         BfsArgs& B = BA.v[nv];
-        B.T = T; B.unit_tree = V.unit_tree; B.tree_start = V.tree_start; B.tree_rootpix = V.tree_rootpix; B.adjw = reinterpret_cast<const unsigned long long*>(V.adjw); B.front = V.bfs_front; B.dbg_out = V.counters + S3_MAX_ROUNDS - 30;
+        B.T = T_dev; B.unit_tree = V.unit_tree; B.tree_start = V.tree_start; B.tree_rootpix = V.tree_rootpix; B.adjw = reinterpret_cast<const unsigned long long*>(V.adjw); B.front = V.bfs_front;
         B.node_pixel = V.node_pixel; B.pixel_node = V.pixel_node; B.parent = V.parent; B.level = V.level; B.pw = V.pw;
         B.node_up = V.node_up; B.node_dn = V.node_dn; B.lvl_start = V.lvl_start; B.tree_depth = V.tree_depth;
-        B.tile_desc = V.tile_desc; B.tree_ntiles = V.tree_ntiles;
-        const int g = std::min(T, ctx->num_sms * 16);
+        const int g = std::min(Tmax, ctx->num_sms * 16);
         if (nv == 0) BA.grid0 = g;
         grid += g;
         nv++;
     }
+    S3_CUDA(cudaEventRecord(ctx->ev_block, ctx->stream));
+    ctx->forest_pending |= mask;
     if (nv == 1) BA.v[1] = BA.v[0];
     for (int view = 0; view < 2; view++)
         if (mask & (1 << view)) {
@@ -953,39 +935,46 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
             View& V = ctx->v[view];
             k_bfs_unpack<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_dn, V.node_pixel, V.parent, V.level, V.pw, V.leaf_bits);
             S3_LAUNCH_CHECK();
-        }
-    if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[4], ctx->stream);
-    if (getenv("S3_DEBUG_FH")) {
-        for (int view = 0; view < 2; view++)
-            if (mask & (1 << view)) {
-                View& V = ctx->v[view];
-                int d[4];
-                S3_CUDA(cudaMemcpy(d, V.counters + S3_MAX_ROUNDS - 30, sizeof d, cudaMemcpyDeviceToHost));
-                fprintf(stderr, "[bfs view %d] largest tree: %d nodes, %d levels, bfs %d kcycles (%.0f cycles/level), tiles %d kcycles\n", view, d[3], d[2], d[0] >> 6,
-                        16.0 * d[0] / std::max(1, d[2]), d[1] >> 6);
-            }
-    }
-    // (the host-side staging vectors above are pageable: an asynchronous H2D copy from pageable memory returns once the
-    // data is staged, so nothing here has to outlive this function)
-    for (int view = 0; view < 2; view++)
-        if (mask & (1 << view)) {
-            View& V = ctx->v[view];
-            V.max_depth = -1;  // tree depths stay on the device until somebody asks (s3_forest_finalize_host)
+            V.max_depth = -1;  // tree depths stay on the device until somebody asks (s3_forest_depths)
             V.adj_ready = false;
-            V.forest_ready = true;
+            V.forest_ready = true;   // the device side is complete in stream order; T and the sizes reach the host lazily
             V.cost_ready = false;
             V.agg_ready = false;
+            V.T = -1;
         }
     return 0;
 }
 
-#define S3_DBG_MARK(i) do { if (ctx->dbg_ev[0]) cudaEventRecord(ctx->dbg_ev[i], ctx->stream); } while (0)
+// The host's view of the forests queued by s3_forest_post: tree count and tree_start.  Waits (sleeping, not spinning:
+// a batch has many frames and a box many ranks) for the copy s3_forest_post queued; no-op when nothing is pending.
+int s3_forest_finish_host(s3dmst_ctx* ctx) {
+    if (!ctx->forest_pending) return 0;
+    const int N = ctx->N;
+    const int Tmax = forest_tmax(ctx);
+    const size_t pin_view = 16 + (size_t)Tmax;
+    S3_CUDA(cudaEventSynchronize(ctx->ev_block));
+    const int mask = ctx->forest_pending;
+    ctx->forest_pending = 0;
+    for (int view = 0; view < 2; view++) {
+        if (!(mask & (1 << view))) continue;
+        View& V = ctx->v[view];
+        const int* pin = ctx->h_pin + view * pin_view;
+        V.forest_ready = false;
+        if (pin[0]) return s3_fail(ctx, S3DMST_E_LIMIT, "forest kernel hit the round cap");
+        const int T = pin[1];
+        if (T <= 0 || T > Tmax) return s3_fail(ctx, S3DMST_E_CUDA, "labelling produced T=%d (bound %d)", T, Tmax);
+        V.T = T;
+        V.h_tree_start.assign(T + 1, 0);
+        for (int t = 0; t < T; t++) V.h_tree_start[t + 1] = V.h_tree_start[t] + pin[16 + t];
+        if (V.h_tree_start[T] != N) return s3_fail(ctx, S3DMST_E_CUDA, "tree sizes sum to %d, expected %d", V.h_tree_start[T], N);
+        V.forest_ready = true;
+    }
+    return 0;
+}
+
 int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
-    S3_DBG_MARK(0);
     S3_TRY(s3_forest_pre(ctx, mask));
-    S3_DBG_MARK(1);
     S3_TRY(s3_fh_launch(ctx, mask));
-    S3_DBG_MARK(2);
     return s3_forest_post(ctx, mask);
 }
 
@@ -994,6 +983,7 @@ int s3_forest_stage(s3dmst_ctx* ctx, int view) { return s3_forest_stage_mask(ctx
 // tree depths -> host (forest_info / parity dumps); the pipeline itself never needs them on the host
 int s3_forest_depths(s3dmst_ctx* ctx, int view) {
     View& V = ctx->v[view];
+    S3_TRY(s3_forest_finish_host(ctx));
     if (V.max_depth >= 0) return 0;
     V.h_tree_depth.resize(V.T);
     S3_CUDA(cudaMemcpyAsync(V.h_tree_depth.data(), V.tree_depth, sizeof(int) * V.T, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1003,16 +993,14 @@ int s3_forest_depths(s3dmst_ctx* ctx, int view) {
     return 0;
 }
 
+// an uploaded forest (s3dmst_set_forest): the host already knows T and tree_start
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view) {
     View& V = ctx->v[view];
-    V.h_tree_depth.resize(V.T);
-    S3_CUDA(cudaMemcpyAsync(V.h_tree_depth.data(), V.tree_depth, sizeof(int) * V.T, cudaMemcpyDeviceToHost, ctx->stream));
-    S3_CUDA(cudaStreamSynchronize(ctx->stream));
-    V.max_depth = 0;
-    for (int d : V.h_tree_depth) V.max_depth = std::max(V.max_depth, d);
+    ctx->forest_pending &= ~(1 << view);
+    V.max_depth = -1;
     V.adj_ready = false;
     V.forest_ready = true;
     V.cost_ready = false;
     V.agg_ready = false;
-    return 0;
+    return s3_forest_depths(ctx, view);
 }

@@ -11,9 +11,6 @@
 #define S3_NUM_W 766            // integer edge weights 0..765 (|dR|+|dG|+|dB|)
 #define S3_NO_EDGE 0xFFFFu
 #define S3_DEAD 0xFFFFFFFFu
-#define S3_TILE_NODES 16         // nodes per aggregation tile (== math warps of the pipelined kernel)
-#define S3_TF_FIRST 1            // tile flags: first / last tile of its tree level
-#define S3_TF_LAST 2
 #define S3_AGG_NEAR 32          // dataflow aggregation: a parent/child closer than this (in BFS index) is handed over in shared memory
 #define S3_NU_FARPARENT 0x100    // NodeUp.child_count flag: the node's parent is S3_AGG_NEAR or more nodes away
 #define S3_ND_FAR (1 << 30)      // node_dn.z flag: the node has a child S3_AGG_NEAR or more nodes away
@@ -70,9 +67,6 @@ struct View {
     int4* node_dn = nullptr;    // [N] {parent, parent weight, level | flags, pixel}: the root->leaf pass record
     uint32_t* leaf_bits = nullptr;  // [N/32 + 1] bit v = node v is a leaf (prefetch target selection on the way down)
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
-    int4* tile_desc = nullptr;  // [4N] ([0,2N) root->leaf order, [2N,4N) leaf->root order); two int4 per tile: {t0, n, loff, flags}, {level end, parent level start, 0, 0};
-                                //      tree t's tiles start at tile index tree_start[t], level-major, ascending nodes
-    int* tree_ntiles = nullptr; // [T]
     // tree adjacency graph (Stereo3DMST.cpp:377-384) as a device CSR, built lazily (proposal generation, parity dumps)
     int* adj_ptr = nullptr;     // [T+1]
     int* adj = nullptr;         // [n_adj] neighbours of tree t: adj[adj_ptr[t] .. adj_ptr[t+1]), ascending
@@ -120,10 +114,10 @@ struct s3dmst_ctx {
     long long launches = 0;
     std::string err;
     // scratch for PMS
-    cudaEvent_t dbg_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // S3_DEBUG_BATCH timeline marks
     cudaEvent_t ev_xctx = nullptr;  // orders this context's stream against another context's in batched launches
     cudaEvent_t ev_block = nullptr; // blocking-sync event: batched contexts SLEEP through the forest kernel instead of spinning
-    int* h_pin = nullptr;           // pinned staging for the forest stage's host round trip
+    int forest_pending = 0;         // views whose tree count / sizes are still on their way to the host (s3_forest_finish_host)
+    int* h_pin = nullptr;           // pinned landing zone of the forest stage's (T, tree sizes) copy
     size_t h_pin_cap = 0;           // ints
     char* stage = nullptr;          // pinned staging arena of s3_h2d_staged: two halves, each guarded by an event
     size_t stage_half = 0, stage_used = 0;
@@ -195,7 +189,8 @@ int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask);              // both views 
 int s3_fh_launch(s3dmst_ctx* ctx, int mask);
 int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask);   // one launch over several frames
 int s3_forest_pre(s3dmst_ctx* ctx, int mask);                     // image stage + union-find init (async)
-int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (host-synchronous)
+int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (asynchronous)
+int s3_forest_finish_host(s3dmst_ctx* ctx);                       // tree count / sizes -> host (waits for the copy s3_forest_post queued)
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);
 int s3_forest_depths(s3dmst_ctx* ctx, int view);                  // forest.cu: lazy D2H of the tree depths           // forest.cu: unit order, depths
 int s3_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const uint16_t* map_fxy, int W, int H);  // rectify.cu
@@ -206,7 +201,6 @@ int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
-int s3_aggregate_dense2(s3dmst_ctx* ctx, int views_mask, int d0, int d1);  // aggregate2.cu (TMA-pipelined, level-synchronous tiles)
 int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1);    // aggregate3.cu (dataflow, default)
 struct PmsFlowPlan {   // aggregate3.cu: unit list of a proposal-mode launch, uploaded once and reused by every round
     int n_cl, n_big, n_small;
@@ -229,3 +223,5 @@ int s3_lr_check(s3dmst_ctx* ctx, int fill);
 int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
 int s3_reproject(s3dmst_ctx* ctx, const double* Q16, float disp_floor, int handle_missing, float* h_xyz, uint32_t* h_rgb);
 int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D);
+int s3_weighted_median(s3dmst_ctx* ctx, int view, int radius, float gamma, const uint8_t* h_mask);  // postfilter.cu
+int s3_norm_factor(s3dmst_ctx* ctx, int view, double* h_out);

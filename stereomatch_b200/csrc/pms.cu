@@ -154,6 +154,7 @@ int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const flo
     if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
         return s3_fail(ctx, S3DMST_E_STATE, "pms_apply: forest, cost volume and labels required");
     if (n == 0) return 0;
+    S3_TRY(s3_forest_finish_host(ctx));
     const int T = V.T;
     std::vector<int> off(T + 1, 0);
     for (size_t i = 0; i < n; i++) {
@@ -288,6 +289,7 @@ int s3_tree_adjacency(s3dmst_ctx* ctx, int view) {
     View& V = ctx->v[view];
     if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "tree adjacency: no forest");
     if (V.adj_ready) return 0;
+    S3_TRY(s3_forest_finish_host(ctx));
     const int N = ctx->N, W = ctx->W, H = ctx->H, T = V.T;
     unsigned cap = 1;
     while ((size_t)cap * 2 * sizeof(unsigned long long) <= 32 * (size_t)N && cap < (1u << 30)) cap *= 2;  // largest power of two inside fh_ent[0]
@@ -419,6 +421,7 @@ int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed) {
     if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
         return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: forest, cost volume and labels required");
     if (!ctx->P.exact) return s3_fail(ctx, S3DMST_E_ARG, "pms_iterate: proposals are evaluated in the exact mode only");
+    S3_TRY(s3_forest_finish_host(ctx));
     S3_TRY(s3_tree_adjacency(ctx, view));
     double* scr; float* d_lab; int* d_off;
     S3_TRY(pms_scratch(ctx, (size_t)V.n_adj, V.T, &scr, &d_lab, &d_off));

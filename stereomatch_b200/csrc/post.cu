@@ -143,7 +143,9 @@ int s3_lr_check(s3dmst_ctx* ctx, int fill) {
     k_lr_pass1<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->W, ctx->N, D, L.disp_f, R.disp_f, L.lr_mask);
     S3_LAUNCH_CHECK();
     if (fill) {
-        k_lr_fill<<<ctx->H, 256, 2 * ctx->W * sizeof(int), ctx->stream>>>(ctx->W, L.disp_f, L.lr_mask);
+        const size_t smem = 2 * (size_t)ctx->W * sizeof(int);  // up to 64 KB at W = 8192: above the 48 KB default limit
+        S3_CUDA(cudaFuncSetAttribute(k_lr_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lr_fill<<<ctx->H, 256, smem, ctx->stream>>>(ctx->W, L.disp_f, L.lr_mask);
         S3_LAUNCH_CHECK();
     }
     S3_EV_END(S3DMST_T_POST, 0);

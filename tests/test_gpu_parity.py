@@ -134,17 +134,22 @@ def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat
 
 @pytest.mark.parametrize("threads,cap", [(32, 1), (64, 2), (256, 4), (512, 64)])
 def test_dense_aggregation_config_independent(api, oracle, threads, cap):
+    """agg_kernel = 1: the simple level-synchronous kernel (aggregate.cu: any even d0, the fall-back of the dataflow kernel
+    for label ranges that do not start on a 16-byte boundary), for several CTA shapes."""
     W, H, D = 200, 120, 70   # two label chunks per lane, a partly filled second chunk
     L, R, _ = make(W, H, 24, 9, 1)
     F = oracle.forest(L)
     lv, _ = oracle.cost_adgrad(L, R, D)
     disp_o, best_o, _ = oracle.aggregate_dense(F, lv)
-    eng = api.Stereo3DMST(agg_threads=threads, agg_cache_nodes=cap)
+    eng = api.Stereo3DMST(agg_threads=threads, agg_cache_nodes=cap, agg_kernel=1)
     eng.set_images(L, R)
     eng.build_forest(0)
     eng.set_cost_volume(0, lv, ingest=False)
     disp, best = eng.aggregate_dense(0)
     assert np.array_equal(disp, disp_o) and np.array_equal(bits(best), bits(best_o))
+    d2, b2 = eng.aggregate_dense(0, 6, 50)
+    do2, bo2, _ = oracle.aggregate_dense(F, lv, 6, 50)
+    assert np.array_equal(d2, do2) and np.array_equal(bits(b2), bits(bo2))
     eng.close()
 
 
@@ -495,7 +500,7 @@ def test_golden_reference_proposals(api, oracle):
 @pytest.mark.parametrize("fill", [False, True])
 def test_lr_check_matches_oracle(api, oracle, fill):
     rng = np.random.default_rng(8)
-    for (W, H, D) in ((97, 13, 16), (1300, 3, 60), (5, 4, 4)):
+    for (W, H, D) in ((97, 13, 16), (1300, 3, 60), (5, 4, 4), (7001, 2, 24)):   # the last: 2*W ints of shared memory > 48 KB
         L, R, _ = make(W, H, 12, 1, 0)
         eng = api.Stereo3DMST(min_cc_size=2, fh_c=10.0)
         eng.set_images(L, R)
@@ -865,3 +870,56 @@ def test_remap_matches_opencv(api, oracle):
     dl2, dr2 = e2.run_dense(16, fill=True)
     assert np.array_equal(dl, dl2) and np.array_equal(dr, dr2)
     e.close(); e2.close()
+
+
+def test_weighted_median_matches_oracle(api, oracle):
+    """weightedMedianFilter (PatchMatchStereoGPU.cu:2436-2599) on LR-invalid pixels, bit for bit against
+    the CPU restatement (oracle/postfilter_oracle.py), incl. windows hanging over every image border."""
+    from oracle import postfilter_oracle as po
+    W, H, D = 97, 61, 32
+    L, R, _ = make(W, H, D, 33, 1)
+    rng = np.random.default_rng(12)
+    eng = api.Stereo3DMST()
+    eng.set_images(L, R)
+    for radius, gamma in ((10, 0.1), (3, 0.25)):
+        tab = api.wmf_table(gamma)
+        assert tab[0] == 1.0 and np.all(np.diff(tab) <= 0)
+        disp = np.round(rng.uniform(0, D - 1, (H, W)) * 4).astype(np.float32) / np.float32(4)   # many equal disparities: the stable order matters
+        mask = (rng.random((H, W)) < 0.15).astype(np.uint8)
+        mask[0, 0] = mask[H - 1, W - 1] = mask[0, W - 1] = 1
+        for view, img in ((0, L), (1, R)):
+            eng.set_disparity(view, disp)
+            eng.weighted_median(view, radius, gamma, mask)
+            want = po.weighted_median(disp, mask, img, tab, radius)
+            got = eng.get_disparity(view).reshape(H, W)
+            assert np.array_equal(bits(got), bits(want)), (radius, view)
+            assert np.array_equal(got[mask == 0], disp[mask == 0]) and np.any(got[mask == 1] != disp[mask == 1])
+    # default mask = the left-right check's: pipeline -> LR check (no fill) -> weighted median of the invalid pixels
+    dl, dr = eng.run_dense(D, fill=False)
+    m = eng.get_lr_mask().reshape(H, W)
+    assert np.array_equal(m == 1, dl.reshape(H, W) == 0) or np.all((dl.reshape(H, W) == 0)[m == 1])
+    eng.weighted_median(0, 10, 0.1)
+    want = po.weighted_median(dl.reshape(H, W), m, L, api.wmf_table(0.1), 10)
+    assert np.array_equal(bits(eng.get_disparity(0).reshape(H, W)), bits(want))
+    eng.close()
+
+
+def test_norm_factor_matches_oracle(api, oracle):
+    """cost_norm_factor (PatchMatchStereoGPU.cu:5333-5429, :5898-5919) = 1 / tree filter of the all-ones volume."""
+    W, H, D = 160, 100, 8
+    L, R, _ = make(W, H, 16, 35, 1)
+    eng = api.Stereo3DMST(fh_c=800.0, min_cc_size=30)
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    eng.build_cost_volume(D)
+    nf = eng.norm_factor(0)
+    F = oracle.forest(L, c=800.0, min_size=30)
+    _, best, _ = oracle.aggregate_dense(F, np.ones((4, W * H), np.float32))
+    assert np.array_equal(bits(nf), bits(1.0 / best))
+    assert nf.max() <= 1.0 and nf.min() > 0.0
+    # the context's own volume is untouched: the dense result afterwards is the oracle's
+    lv, _ = oracle.cost_adgrad(L, R, D)
+    do, bo, _ = oracle.aggregate_dense(F, lv)
+    disp, bst = eng.aggregate_dense(0)
+    assert np.array_equal(disp, do) and np.array_equal(bits(bst), bits(bo))
+    eng.close()
