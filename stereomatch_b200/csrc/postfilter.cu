@@ -37,7 +37,7 @@ __global__ void k_wmf_compact(int N, const uint8_t* __restrict__ mask, int* __re
 
 // one warp per invalid pixel; n2 = window entries padded to a power of two
 __global__ void __launch_bounds__(32 * WMF_WARPS) k_weighted_median(int W, int H, int r, int n2, const int* __restrict__ list, const int* __restrict__ count,
-                                                                     const uchar4* __restrict__ img, const float* __restrict__ tab, const float* __restrict__ din,
+                                                                     const uint8_t* __restrict__ img, const float* __restrict__ tab, const float* __restrict__ din,
                                                                      float* __restrict__ dout) {
     extern __shared__ unsigned long long s_wmf[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(32 * WMF_WARPS) k_weighted_median(int W, int H
     for (int it = blockIdx.x * WMF_WARPS + w; it < total; it += gridDim.x * WMF_WARPS) {
         const int p = list[it];
         const int x = p % W, y = p / W;
-        const uchar4 c0 = img[p];
+        const int b0 = img[3 * (size_t)p], g0 = img[3 * (size_t)p + 1], r0 = img[3 * (size_t)p + 2];  // the view's image as set_images stored it
         for (int i = lane; i < n2; i += 32) {
             unsigned long long k = ~0ull;  // padding sorts last
             float wgt = 0.0f;
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(32 * WMF_WARPS) k_weighted_median(int W, int H
                 float d = 0.0f;
                 if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
                     const int q = yy * W + xx;
-                    const uchar4 c = img[q];
-                    wgt = tab[abs((int)c.x - (int)c0.x) + abs((int)c.y - (int)c0.y) + abs((int)c.z - (int)c0.z)];
+                    const uint8_t* c = img + 3 * (size_t)q;
+                    wgt = tab[abs((int)c[0] - b0) + abs((int)c[1] - g0) + abs((int)c[2] - r0)];
                     d = din[q];
                 }
                 const unsigned b = __float_as_uint(d);
@@ -140,7 +140,7 @@ int s3_weighted_median(s3dmst_ctx* ctx, int view, int radius, float gamma, const
     S3_LAUNCH_CHECK();
     const size_t smem = (size_t)WMF_WARPS * n2 * (sizeof(unsigned long long) + sizeof(float));
     S3_CUDA(cudaFuncSetAttribute(k_weighted_median, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_weighted_median<<<ctx->num_sms * 4, 32 * WMF_WARPS, smem, ctx->stream>>>(ctx->W, ctx->H, radius, n2, list, count, V.raw4, tab, snap, V.disp_f);
+    k_weighted_median<<<ctx->num_sms * 4, 32 * WMF_WARPS, smem, ctx->stream>>>(ctx->W, ctx->H, radius, n2, list, count, V.bgr, tab, snap, V.disp_f);
     S3_LAUNCH_CHECK();
     S3_EV_END(S3DMST_T_POST, 1);
     return 0;
