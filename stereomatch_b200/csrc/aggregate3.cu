@@ -79,7 +79,6 @@ struct Agg3Args {
     float oob;             // label cost outside [0, D)
     // proposal generation inside the kernel (s3dmst_pms_iterate): after a tree's listed proposals (its neighbours' labels),
     // the refinement ladder around a random pixel of the tree itself
-    int l2;                // bit 0: evict-first cost loads, bit 1: discard consumed running-sum rows
     int gen;
     uint32_t seed, round;
     float refine_floor;
@@ -150,21 +149,6 @@ __device__ __forceinline__ void a3_sts_d2(uint32_t a, double2 v) {
 __device__ __forceinline__ void a3_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-// L2 management of the two streams of a tree walk.  Cost rows are read once: loaded with an evict-first policy so that they
-// do not push the running sums out of L2.  A running-sum row is written on the way up and read back once on the way
-// down; what is still in L2 then (the rows nearest the root: last written, first read) is dropped after the read
-// instead of being written back to HBM (discard.L2: the row is scratch from here on).
-__device__ __forceinline__ unsigned long long a3_policy_evict_first() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ float2 a3_ld_f2_hint(const char* a, unsigned long long pol) {
-    float2 v;
-    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol) : "memory");
-    return v;
-}
-__device__ __forceinline__ void a3_discard_l2(const char* a) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory"); }
 // total order on doubles as unsigned 64-bit keys (handles negative costs of the mc-cnn "fast" volumes)
 __device__ __forceinline__ unsigned long long a3_dkey(double x) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -302,7 +286,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     constexpr uint32_t ROWB = NH * HB;                      // bytes of one ring row
     const long long strideC = (long long)WT * (long long)Dp * 4, strideA = (long long)WT * (long long)(PMS ? 64 : A.Dp) * (long long)sizeof(T);  // bytes between a warp's consecutive rows
     T* const aupT = reinterpret_cast<T*>(V.aup);  // running sums in the state type (the buffer is sized for doubles)
-    const unsigned long long pol_ef = a3_policy_evict_first();
     // progress word / ring row of processing position k (see the header: owner CTA k % CL, warp (k / CL) % W)
     auto prog_of = [&](int k) -> uint32_t {
         if constexpr (CL == 1) return prog_a + 4u * (uint32_t)(k & WM);
@@ -410,7 +393,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             else {
 #pragma unroll
                 for (int h = 0; h < NH; h++)
-                    if (act[h]) cf[h] = (A.l2 & 1) ? a3_ld_f2_hint(cost_p + h * 256, pol_ef) : *reinterpret_cast<const float2*>(cost_p + h * 256);
+                    if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
             }
         } else if (lane == 0)
             publish(base);  // a warp without nodes never holds anybody back
@@ -518,7 +501,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 else {
 #pragma unroll
                     for (int h = 0; h < NH; h++)
-                        if (act[h]) cf[h] = (A.l2 & 1) ? a3_ld_f2_hint(cost_p - strideC + h * 256, pol_ef) : *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
+                        if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
                 }
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
@@ -650,14 +633,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             } else {
 #pragma unroll
                 for (int h = 0; h < NH; h++) fin[h] = au[h];  // the root keeps its leaf->root sum
-            }
-            // this node's running-sum row has been consumed: unless a far child will read the final value from the same row,
-            // whatever part of it is still in L2 need not go back to HBM (one lane per 128-byte line)
-            if ((A.l2 & 2) && !PMS && !A.keep && !(CL > 1 ? ((ch.y & 7) > 0 && ch.x + (ch.y & 7) - 1 - v >= NEAR_E) : (bool)(nd.z & S3_ND_FAR)) &&
-                (lane & (128 / (int)sizeof(T2) - 1)) == 0) {
-#pragma unroll
-                for (int h = 0; h < NH; h++)
-                    if (act[h]) a3_discard_l2(aup_p + h * HB);
             }
             // children further than the rings reach read the final value from L2
             const bool far_child = CL > 1 ? ((ch.y & 7) > 0 && ch.x + (ch.y & 7) - 1 - v >= NEAR_E) : (bool)(nd.z & S3_ND_FAR);
@@ -863,12 +838,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.keep = ctx->P.keep_aggregated;
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env < 0 ? 0 : sleep_env ? sleep_env : 20;
-    static const int l2_env = getenv("S3_AGG_L2") ? atoi(getenv("S3_AGG_L2")) : 0;
-    A.l2 = l2_env;
-    {   // a discarded 128-byte line must lie inside ONE running-sum row of ONE slice
-        const size_t tsz = exact ? sizeof(double) : sizeof(float);
-        if (((size_t)Dp * tsz) % 128 != 0 || ((size_t)d0 * tsz) % 128 != 0) A.l2 &= ~2;
-    }
 
     // The giant trees get a thread-block cluster (A3_CLUSTER CTAs = 256 warps on one tree), on the context's second
     // stream so that they run beside the rest; all but the smallest of the others get 32 warps and an SM of their own;
