@@ -62,6 +62,12 @@ typedef struct s3dmst_params {
                            frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
                            frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
     int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel */
+    int pms_cost_mode;  /* data term of the 3D-label (PatchMatch) search: 0 = compute3DLabelCost on the cost volume (the
+                           reference, Stereo3DMST.cpp:103-118); 1 = slanted-plane truncated colour + gradient cost straight from
+                           the two images, at the sub-pixel match position (pm::PatchMatch, src/pm.cpp:97-154): no volume */
+    float pm_alpha;     /* 0.9   stereo_opencv.cpp:156   weight of the gradient term                                  */
+    float pm_tau_c;     /* 10    truncation of the L1 colour difference                                             */
+    float pm_tau_g;     /* 2     truncation of the L1 gradient difference                                           */
     int agg_cluster_nodes; /* 0 = auto (32768): trees of at least this many nodes are walked by a thread-block cluster of
                            8 CTAs (256 warps) instead of one CTA; < 0: never */
 } s3dmst_params;
@@ -159,6 +165,14 @@ double s3dmst_comm_minloc_ms(s3dmst_ctx* ctx);
 
 /* Dense disparity (int) -> float disparity map used by the LR check. */
 int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view);
+
+/* a2' slanted variant (north-star item 1): prepares the data term of params.pms_cost_mode = 1 for Dmax labels — Sobel/8
+ * gradients of both views (pm.cpp:70-88).  After it s3dmst_pms_apply / s3dmst_pms_iterate / s3dmst_run score a plane at
+ * a pixel by the truncated colour + gradient difference to the other image at x -+ d (sub-pixel, pm.cpp:130-154) times
+ * params.cost_scale, and params.oob_cost outside [0, Dmax]; no cost volume is needed or touched. */
+int s3dmst_prepare_plane_cost(s3dmst_ctx* ctx, int Dmax);
+/* the gradients it computed: float [H*W][2] (parity dumps) */
+int s3dmst_get_plane_gradients(s3dmst_ctx* ctx, int view, float* grad);
 
 /* a6/a11/a12 PatchMatch state: labels abc [N][3] fp32 and min_cost [N] fp64 (init DBL_MAX). */
 int s3dmst_set_labels(s3dmst_ctx* ctx, int view, const float* abc);

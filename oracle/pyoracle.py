@@ -100,6 +100,11 @@ class Oracle:
         L.orc_pms_apply.argtypes = [c_p, c_p, C.c_int, c_p, c_p, C.c_int, c_p, c_p]
         L.orc_aggregate_label.argtypes = [c_p, c_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, c_p]
         L.orc_aggregate_dense.argtypes = [c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p]
+        L.orc_pm_gradients.argtypes = [c_p, C.c_int, C.c_int, c_p]
+        L.orc_pm_plane_cost_map.argtypes = [C.c_int, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
+                                            C.c_float, C.c_float, C.c_float, c_p]
+        L.orc_pms_apply_plane.argtypes = [c_p, C.c_int, c_p, c_p, c_p, c_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_p, c_p,
+                                          C.c_int, c_p, c_p]
         L.orc_rand_new.restype = c_p
         L.orc_rand_new.argtypes = [C.c_uint]
         L.orc_rand_free.argtypes = [c_p]
@@ -176,6 +181,32 @@ class Oracle:
         tree_ids = np.ascontiguousarray(tree_ids, np.int32)
         labels = np.ascontiguousarray(labels, np.float32)
         self.lib.orc_pms_apply(F._h, _ptr(vol), Dmax, _ptr(tree_ids), _ptr(labels), len(tree_ids), _ptr(min_cost), _ptr(abc))
+
+    def pm_gradients(self, bgr):
+        """pm.cpp:70-88: Sobel/8 gradients of the BGR2GRAY image, float32 [H, W, 2]."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        H, W, _ = bgr.shape
+        g = np.empty((H, W, 2), np.float32)
+        self.lib.orc_pm_gradients(_ptr(bgr), W, H, _ptr(g))
+        return g
+
+    def plane_cost_map(self, view, left_bgr, right_bgr, label, Dmax, alpha=0.9, tau_c=10.0, tau_g=2.0, scale=1.0, oob=0.5):
+        left_bgr = np.ascontiguousarray(left_bgr, np.uint8); right_bgr = np.ascontiguousarray(right_bgr, np.uint8)
+        H, W, _ = left_bgr.shape
+        gl, gr = self.pm_gradients(left_bgr), self.pm_gradients(right_bgr)
+        out = np.empty(H * W, np.float32)
+        self.lib.orc_pm_plane_cost_map(view, _ptr(left_bgr), _ptr(right_bgr), _ptr(gl), _ptr(gr), W, H, C.c_float(label[0]), C.c_float(label[1]),
+                                       C.c_float(label[2]), Dmax, C.c_float(alpha), C.c_float(tau_c), C.c_float(tau_g), C.c_float(scale), C.c_float(oob), _ptr(out))
+        return out
+
+    def pms_apply_plane(self, F: Forest, view, left_bgr, right_bgr, Dmax, tree_ids, labels, min_cost, abc, alpha=0.9, tau_c=10.0, tau_g=2.0,
+                        scale=1.0, oob=0.5):
+        """pms_apply with the slanted-plane matching cost computed straight from the images (pm.cpp:97-154)."""
+        left_bgr = np.ascontiguousarray(left_bgr, np.uint8); right_bgr = np.ascontiguousarray(right_bgr, np.uint8)
+        gl, gr = self.pm_gradients(left_bgr), self.pm_gradients(right_bgr)
+        tree_ids = np.ascontiguousarray(tree_ids, np.int32); labels = np.ascontiguousarray(labels, np.float32)
+        self.lib.orc_pms_apply_plane(F._h, view, _ptr(left_bgr), _ptr(right_bgr), _ptr(gl), _ptr(gr), Dmax, C.c_float(alpha), C.c_float(tau_c),
+                                     C.c_float(tau_g), C.c_float(scale), C.c_float(oob), _ptr(tree_ids), _ptr(labels), len(tree_ids), _ptr(min_cost), _ptr(abc))
 
     def rand_new(self, seed=1):
         return self.lib.orc_rand_new(seed)

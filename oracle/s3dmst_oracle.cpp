@@ -570,6 +570,89 @@ void orc_aggregate_label(const OrcForest* F, const float* vol, int max_disp, int
 }
 
 // -------------------------------------------------------------------------------------------
+// Slanted-plane matching cost straight from the images (north-star item 1; formula source pm::PatchMatch, src/pm.cpp):
+// gradients pm.cpp:70-88 (cvtColor BGR2GRAY u8 with OpenCV's fixed-point weights, Sobel 3x3 CV_32F reflect-101, / 8),
+// per-pixel cost pm.cpp:130-154 + dissimilarity :97-104 with the reference's byte-vector quirks (cv::Vec3b mcolo,
+// cv::Vec2b mgrad: every scaled term and the sums are saturate_cast<uchar>).  Checked against cv2 for the gradients
+// (tests/test_oracle_golden.py).  Floating-point order: separately rounded fp32 operations, left to right.
+// -------------------------------------------------------------------------------------------
+static inline int pm_reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+static inline int pm_sat_u8(float v) {
+    const long i = lrintf(v);  // cvRound: nearest, ties to even
+    return i < 0 ? 0 : (i > 255 ? 255 : (int)i);
+}
+void orc_pm_gradients(const uint8_t* bgr, int W, int H, float* grad) {
+    std::vector<int> gray((size_t)W * H);
+    for (size_t p = 0; p < (size_t)W * H; p++) gray[p] = (bgr[3 * p] * 3735 + bgr[3 * p + 1] * 19235 + bgr[3 * p + 2] * 9798 + (1 << 14)) >> 15;  // cv2 4.x (3.4.3: 1868/9617/4899 >> 14)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int xm = pm_reflect101(x - 1, W), xp = pm_reflect101(x + 1, W), ym = pm_reflect101(y - 1, H), yp = pm_reflect101(y + 1, H);
+            auto g = [&](int yy, int xx) { return gray[(size_t)yy * W + xx]; };
+            const int gx = (g(ym, xp) + 2 * g(y, xp) + g(yp, xp)) - (g(ym, xm) + 2 * g(y, xm) + g(yp, xm));
+            const int gy = (g(yp, xm) + 2 * g(yp, x) + g(yp, xp)) - (g(ym, xm) + 2 * g(ym, x) + g(ym, xp));
+            grad[2 * ((size_t)y * W + x)] = (float)gx / 8.f;
+            grad[2 * ((size_t)y * W + x) + 1] = (float)gy / 8.f;
+        }
+}
+static inline float pm_plane_cost(const uint8_t* simg, const float* sgrad, const uint8_t* oimg, const float* ograd, int pix, int W, int view, float a,
+                                  float b, float c, int max_disp, float alpha, float tau_c, float tau_g, float scale, float oob) {
+    const int x = pix % W, y = pix / W;
+    const float d = a * x + b * y + c;                      // pm.h:153-156
+    if (!(d >= 0.0f) || d > (float)max_disp || W < 2) return oob;    // :132-135 (PLANE_PENALTY)
+    const float match = view ? x + d : x - d;               // :139 sign = -1 + 2*cpv
+    int xm = (int)match;                                    // :140
+    const float wm = 1.0f - (match - xm);                   // :142
+    if (xm > W - 2) xm = W - 2;                             // :144-147
+    if (xm < 0) xm = 0;
+    const uint8_t* o0 = oimg + 3 * ((size_t)y * W + xm);
+    const float* g0 = ograd + 2 * ((size_t)y * W + xm);
+    float cc = 0.0f, cg = 0.0f;
+    for (int k = 0; k < 3; k++) {                           // :150 Vec3b = wm * p0 + (1 - wm) * p1 in byte vectors
+        int m = pm_sat_u8(wm * o0[k]) + pm_sat_u8((1.0f - wm) * o0[3 + k]);
+        if (m > 255) m = 255;
+        cc += std::fabs((float)((int)simg[3 * (size_t)pix + k] - m));
+    }
+    for (int k = 0; k < 2; k++) {                           // :151 Vec2b <- Vec2f average
+        const float gm = (float)pm_sat_u8(wm * g0[k] + (1.0f - wm) * g0[2 + k]);
+        cg += std::fabs(sgrad[2 * (size_t)pix + k] - gm);
+    }
+    cc = std::min(cc, tau_c);                               // :99-103
+    cg = std::min(cg, tau_g);
+    return ((1.0f - alpha) * cc + alpha * cg) * scale;
+}
+// the plane cost of one label at every pixel of a view (parity dumps)
+void orc_pm_plane_cost_map(int view, const uint8_t* left_bgr, const uint8_t* right_bgr, const float* left_grad, const float* right_grad, int W, int H,
+                           float a, float b, float c, int max_disp, float alpha, float tau_c, float tau_g, float scale, float oob, float* out) {
+    const uint8_t* simg = view ? right_bgr : left_bgr; const uint8_t* oimg = view ? left_bgr : right_bgr;
+    const float* sgrad = view ? right_grad : left_grad; const float* ograd = view ? left_grad : right_grad;
+    for (int p = 0; p < W * H; p++) out[p] = pm_plane_cost(simg, sgrad, oimg, ograd, p, W, view, a, b, c, max_disp, alpha, tau_c, tau_g, scale, oob);
+}
+// injected proposals evaluated with the plane cost (MSTCostAggregationAndLabelUpdate with the data term above)
+void orc_pms_apply_plane(const OrcForest* F, int view, const uint8_t* left_bgr, const uint8_t* right_bgr, const float* left_grad, const float* right_grad,
+                         int max_disp, float alpha, float tau_c, float tau_g, float scale, float oob, const int* tree_ids, const float* labels, int n,
+                         double* min_cost, float* abc) {
+    std::vector<double> agg(F->N, 0.0);
+    const uint8_t* simg = view ? right_bgr : left_bgr; const uint8_t* oimg = view ? left_bgr : right_bgr;
+    const float* sgrad = view ? right_grad : left_grad; const float* ograd = view ? left_grad : right_grad;
+    for (int i = 0; i < n; i++) {
+        const float a = labels[3 * i], b = labels[3 * i + 1], c = labels[3 * i + 2];
+        const int tree = tree_ids[i];
+        tree_filter(F, tree, agg.data(), [&](int pix) { return pm_plane_cost(simg, sgrad, oimg, ograd, pix, F->W, view, a, b, c, max_disp, alpha, tau_c, tau_g, scale, oob); });
+        for (int g = F->tree_start[tree]; g < F->tree_start[tree + 1]; g++) {
+            const int pix = F->node_pixel[g];
+            if (agg[pix] < min_cost[pix]) {
+                min_cost[pix] = agg[pix];
+                abc[3 * pix] = a; abc[3 * pix + 1] = b; abc[3 * pix + 2] = c;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // A13 dense-label mode: for d ascending, cost = C[d][p] (selectDisparity, PatchMatchStereoGPU.cu:1706-1717),
 // tree filter with the reference arithmetic, strict '<' so the lowest d wins ties.
 // agg_out (optional) is [D][N] double; disp [N] int32; best [N] double.  Labels d0..d1-1 only.

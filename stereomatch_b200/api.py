@@ -33,7 +33,8 @@ class S3Params(C.Structure):
                 ("cost_cap", C.c_float), ("cost_offset", C.c_float), ("cost_scale", C.c_float), ("oob_cost", C.c_float),
                 ("num_iter", C.c_int), ("refine_floor", C.c_float), ("exact", C.c_int), ("keep_aggregated", C.c_int),
                 ("agg_threads", C.c_int), ("agg_cache_nodes", C.c_int), ("agg_ring_nodes", C.c_int), ("agg_kernel", C.c_int),
-                ("fh_ctas", C.c_int), ("fh_threads", C.c_int), ("agg_cluster_nodes", C.c_int)]
+                ("fh_ctas", C.c_int), ("fh_threads", C.c_int), ("pms_cost_mode", C.c_int), ("pm_alpha", C.c_float), ("pm_tau_c", C.c_float),
+                ("pm_tau_g", C.c_float), ("agg_cluster_nodes", C.c_int)]
 
 
 # every symbol include/s3dmst.h declares (tests/test_abi.py checks the library exports all of them)
@@ -47,6 +48,7 @@ ABI_SYMBOLS = [
     "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
     "s3dmst_comm_unique_id", "s3dmst_comm_init", "s3dmst_comm_destroy", "s3dmst_comm_label_range", "s3dmst_reduce_minloc", "s3dmst_aggregate_dense_sharded",
     "s3dmst_comm_minloc_ms", "s3dmst_get_lr_mask", "s3dmst_weighted_median", "s3dmst_wmf_table", "s3dmst_norm_factor",
+    "s3dmst_prepare_plane_cost", "s3dmst_get_plane_gradients",
 ]
 
 _lib = None
@@ -121,6 +123,8 @@ def load_library():
     L.s3dmst_stage_ms.restype = C.c_double
     L.s3dmst_launch_count.argtypes = [c_p]
     L.s3dmst_launch_count.restype = C.c_longlong
+    L.s3dmst_prepare_plane_cost.argtypes = [c_p, C.c_int]
+    L.s3dmst_get_plane_gradients.argtypes = [c_p, C.c_int, c_p]
     L.s3dmst_get_lr_mask.argtypes = [c_p, c_p]
     L.s3dmst_weighted_median.argtypes = [c_p, C.c_int, C.c_int, C.c_float, c_p]
     L.s3dmst_wmf_table.argtypes = [C.c_float, c_p]
@@ -378,6 +382,16 @@ class Stereo3DMST:
 
     def dense_to_disparity(self, view):
         self._ck(self.L.s3dmst_dense_to_disparity(self.h, view))
+
+    def prepare_plane_cost(self, Dmax):
+        """Data term of pms_cost_mode = 1 (slanted-plane colour + gradient cost from the images, pm.cpp:97-154)."""
+        self._ck(self.L.s3dmst_prepare_plane_cost(self.h, int(Dmax)))
+        self.D = Dmax
+
+    def get_plane_gradients(self, view):
+        g = np.empty((self.H, self.W, 2), np.float32)
+        self._ck(self.L.s3dmst_get_plane_gradients(self.h, view, _ptr(g)))
+        return g
 
     # -- PatchMatch state ---------------------------------------------------------------------------
     def set_labels(self, view, abc):

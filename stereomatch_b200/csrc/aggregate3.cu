@@ -59,6 +59,11 @@ struct Agg3View {
     double* best;
     int32_t* pdisp;   // [slice][node] partial results otherwise
     double* pbest;
+    // proposal mode with the plane cost (params.pms_cost_mode = 1): this view's and the other view's image and gradients
+    const uint8_t* img_self;
+    const uint8_t* img_other;
+    const float* grad_self;
+    const float* grad_other;
 };
 
 struct Agg3Args {
@@ -79,6 +84,8 @@ struct Agg3Args {
     float oob;             // label cost outside [0, D)
     // proposal generation inside the kernel (s3dmst_pms_iterate): after a tree's listed proposals (its neighbours' labels),
     // the refinement ladder around a random pixel of the tree itself
+    int cost_mode, view, img_h;            // proposal mode: 1 = plane cost from the images (hd_math.h: s3_plane_cost)
+    float pm_alpha, pm_tau_c, pm_tau_g, pm_scale;
     int gen;
     uint32_t seed, round;
     float refine_floor;
@@ -364,9 +371,18 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     auto pms_cost = [&](int vv) -> float2 {
         const int pix = V.node_pixel[vv];
         const int x = pix % A.img_w, y = pix / A.img_w;
-        const float* row = V.cost + (size_t)vv * Dp;
         const int k = 2 * lane;
         float2 c = make_float2(0.f, 0.f);
+        if (A.cost_mode) {  // slanted-plane colour + gradient cost at the sub-pixel match position (pm.cpp:97-154)
+            const uint8_t* sb = V.img_self + 3 * (size_t)pix;
+            const float* sg = V.grad_self + 2 * (size_t)pix;
+            const uint8_t* ob = V.img_other + 3 * (size_t)y * A.img_w;
+            const float* og = V.grad_other + 2 * (size_t)y * A.img_w;
+            if (b0 + k < b_end) c.x = s3_plane_cost(sb, sg, ob, og, x, y, A.img_w, A.view, s_lab[3 * k], s_lab[3 * k + 1], s_lab[3 * k + 2], A.D, A.pm_alpha, A.pm_tau_c, A.pm_tau_g, A.pm_scale, A.oob);
+            if (b0 + k + 1 < b_end) c.y = s3_plane_cost(sb, sg, ob, og, x, y, A.img_w, A.view, s_lab[3 * k + 3], s_lab[3 * k + 4], s_lab[3 * k + 5], A.D, A.pm_alpha, A.pm_tau_c, A.pm_tau_g, A.pm_scale, A.oob);
+            return c;
+        }
+        const float* row = V.cost + (size_t)vv * Dp;
         if (b0 + k < b_end) c.x = s3_label_cost(row, s_lab[3 * k], s_lab[3 * k + 1], s_lab[3 * k + 2], x, y, A.D, A.oob);
         if (b0 + k + 1 < b_end) c.y = s3_label_cost(row, s_lab[3 * k + 3], s_lab[3 * k + 4], s_lab[3 * k + 5], x, y, A.D, A.oob);
         return c;
@@ -505,7 +521,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 }
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
-            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base)
+            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base && !(PMS && A.cost_mode))
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - (PMS ? 0 : 2 * lane * 4) - A3_PF * strideC + lane * 128));
             if (store_late) {  // read back on the way down
 #pragma unroll
@@ -943,6 +959,7 @@ int s3_pms_flow_plan(s3dmst_ctx* ctx, int view, const int* h_prop_off, double* s
     memset(&G, 0, sizeof G);
     G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
     G.cost = V.cost; G.aup = scratch_dev;
+    G.img_self = V.bgr; G.img_other = ctx->v[view ^ 1].bgr; G.grad_self = V.pgrad; G.grad_other = ctx->v[view ^ 1].pgrad;
     const size_t ubytes = units.size() * sizeof(int4), tbytes = (sizeof(Agg3View) + 15) / 16 * 16;
     if (ctx->units_cap < ubytes + tbytes) {
         if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
@@ -978,6 +995,8 @@ int s3_pms_flow_launch(s3dmst_ctx* ctx, int view, const PmsFlowPlan* plan, const
     A.prop_off = prop_off_dev; A.labels = labels_dev; A.min_cost = V.min_cost; A.abc = V.abc;
     A.img_w = ctx->W; A.D = V.D; A.oob = ctx->P.oob_cost;
     A.gen = gen; A.seed = seed; A.round = round; A.refine_floor = ctx->P.refine_floor;
+    A.cost_mode = ctx->P.pms_cost_mode == 1; A.view = view; A.img_h = ctx->H;
+    A.pm_alpha = ctx->P.pm_alpha; A.pm_tau_c = ctx->P.pm_tau_c; A.pm_tau_g = ctx->P.pm_tau_g; A.pm_scale = ctx->P.cost_scale;
     S3_EV_BEGIN(S3DMST_T_PMS, view);
     if (n_cl) {
         S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));

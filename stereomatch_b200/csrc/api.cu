@@ -74,7 +74,7 @@ static cudaError_t dalloc(T** p, size_t n) {
     } while (0)
 
 static void free_view(View& V) {
-    DFREE(V.bgr); DFREE(V.raw4); DFREE(V.med); DFREE(V.gray); DFREE(V.ew);
+    DFREE(V.bgr); DFREE(V.raw4); DFREE(V.med); DFREE(V.gray); DFREE(V.ew); DFREE(V.pgrad); V.plane_ready = false;
     DFREE(V.uf_comp); DFREE(V.uf_parent); DFREE(V.adjw); DFREE(V.bfs_front); DFREE(V.fh_ent[0]); DFREE(V.fh_ent[1]); DFREE(V.uf_resv);
     DFREE(V.mask); DFREE(V.elist); DFREE(V.e_ra); DFREE(V.e_rb); DFREE(V.e_flag);
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
@@ -152,6 +152,10 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->fh_ctas = 0;
     p->fh_threads = 0;
     p->agg_cluster_nodes = 0;
+    p->pms_cost_mode = 0;
+    p->pm_alpha = 0.9f;
+    p->pm_tau_c = 10.0f;
+    p->pm_tau_g = 2.0f;
 }
 
 int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, void* stream) {
@@ -275,7 +279,7 @@ static int set_images_impl(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8
     for (int i = 0; i < 2; i++) {
         S3_CUDA(cudaMemcpy2DAsync(ctx->v[i].bgr, 3 * (size_t)W, src[i], stride, 3 * (size_t)W, H, cudaMemcpyHostToDevice,
                                   ctx->stream));
-        ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
+        ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = ctx->v[i].plane_ready = false;
     }
     ctx->forest_pending = 0;
     if (sync) S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
@@ -560,6 +564,19 @@ int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view) {
     return s3_dense_to_disp(ctx, view);
 }
 
+int s3dmst_prepare_plane_cost(s3dmst_ctx* ctx, int Dmax) {
+    if (ctx->N == 0 || Dmax <= 0) return s3_fail(ctx, S3DMST_E_ARG, "prepare_plane_cost: images and Dmax > 0 required");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    return s3_prepare_plane_cost(ctx, Dmax);
+}
+int s3dmst_get_plane_gradients(s3dmst_ctx* ctx, int view, float* grad) {
+    if (view < 0 || view > 1 || !grad || !ctx->v[view].plane_ready) return s3_fail(ctx, S3DMST_E_STATE, "get_plane_gradients: s3dmst_prepare_plane_cost first");
+    S3_CUDA(cudaSetDevice(ctx->device));
+    S3_CUDA(cudaMemcpyAsync(grad, ctx->v[view].pgrad, sizeof(float) * 2 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    S3_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int s3dmst_set_labels(s3dmst_ctx* ctx, int view, const float* abc) {
     if (view < 0 || view > 1 || !abc || ctx->N == 0) return s3_fail(ctx, S3DMST_E_ARG, "set_labels: bad arguments");
     S3_CUDA(cudaSetDevice(ctx->device));
@@ -704,7 +721,8 @@ int s3dmst_run(s3dmst_ctx* ctx, int Dmax, unsigned seed, int fill, float* left_d
         S3_TRY(s3_forest_stage_mask(ctx, 3));
         S3_EV_END(S3DMST_T_FOREST, 0);
     }
-    if (!ctx->v[0].cost_ready || !ctx->v[1].cost_ready || ctx->v[0].D != Dmax || ctx->v[1].D != Dmax) S3_TRY(s3_cost_adgrad(ctx, Dmax, 1));
+    if (ctx->P.pms_cost_mode == 1) S3_TRY(s3_prepare_plane_cost(ctx, Dmax));  // no volume: planes are scored straight from the images
+    else if (!ctx->v[0].cost_ready || !ctx->v[1].cost_ready || ctx->v[0].D != Dmax || ctx->v[1].D != Dmax) S3_TRY(s3_cost_adgrad(ctx, Dmax, 1));
     for (int view = 0; view < 2; view++) {
         S3_TRY(s3_init_labels(ctx, view, Dmax));
         S3_TRY(s3_pms_iterate(ctx, view, ctx->P.num_iter, seed));

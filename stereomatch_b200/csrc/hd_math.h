@@ -146,3 +146,57 @@ S3_HD int s3_refine_ladder(float a, float b, float c, float px, float py, int ma
     }
     return n;
 }
+
+// ---- slanted-plane matching cost straight from the two images (north-star item 1; pm::PatchMatch, src/pm.cpp).
+// Gradients (pm.cpp:70-88): cv::cvtColor(BGR2GRAY) on u8 — OpenCV's fixed-point weights — then cv::Sobel(CV_32F, ksize 3,
+// BORDER_DEFAULT = reflect-101) / 8.  The gray weights are those of the OpenCV this repo can check against (cv2 4.13:
+// (B*3735 + G*19235 + R*9798 + 2^14) >> 15); the reference's OpenCV 3.4.3 used the 14-bit set (1868, 9617, 4899), which
+// differs by one gray level on ~0.3 % of pixels.
+S3_HD int s3_cv_gray(int b, int g, int r) { return (b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15; }
+S3_HD int s3_reflect101(int i, int n) {  // cv::borderInterpolate(BORDER_REFLECT_101)
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+// cv::saturate_cast<uchar>(float): cvRound (nearest, ties to even) then clamped to 0..255
+S3_HD int s3_sat_u8(float v) {
+    const int i = (int)rintf(v);
+    return i < 0 ? 0 : (i > 255 ? 255 : i);
+}
+// Cost of plane (a, b, c) at pixel (x, y) of view `view` (0 = left: the match lies at x - d in the other image; 1 = right:
+// x + d), pm.cpp:130-154 for ONE pixel (the reference sums it over a 35x35 window with adaptive weights; here the tree
+// filter is the aggregation) and dissimilarity :97-104:
+//   d = a*x + b*y + c (pm.h:153-156); outside [0, max_disp] -> oob (the reference's PLANE_PENALTY);
+//   match = x -+ d; xm = (int)match; wm = 1 - (match - xm); xm clamped to [0, W-2];
+//   colour and gradient of the match = vecAverage(pixel xm, pixel xm+1, wm) (pm.h:166-169) — both assigned to BYTE vectors
+//   in the reference (cv::Vec3b mcolo, cv::Vec2b mgrad, :150-151), so every product wm*v and (1-wm)*v and their sum is
+//   saturate_cast to u8 (negative gradients clamp to 0: reproduced);
+//   cost = (1-alpha) * min(L1 colour, tau_c) + alpha * min(L1 gradient, tau_g), then * scale (the path's cost range).
+// self_bgr / self_grad: this pixel; orow_bgr / orow_grad: row y of the other view (BGR u8 triples, gradient float pairs).
+S3_HD float s3_plane_cost(const uint8_t* self_bgr, const float* self_grad, const uint8_t* orow_bgr, const float* orow_grad, int x, int y, int W,
+                          int view, float a, float b, float c, int max_disp, float alpha, float tau_c, float tau_g, float scale, float oob) {
+    const float d = S3_FADD(S3_FADD(S3_FMUL(a, (float)x), S3_FMUL(b, (float)y)), c);
+    if (!(d >= 0.0f) || d > (float)max_disp || W < 2) return oob;
+    const float match = view ? S3_FADD((float)x, d) : S3_FSUB((float)x, d);
+    int xm = (int)match;
+    const float wm = S3_FSUB(1.0f, S3_FSUB(match, (float)xm));
+    if (xm > W - 2) xm = W - 2;
+    if (xm < 0) xm = 0;
+    const float w1 = S3_FSUB(1.0f, wm);
+    float cc = 0.0f;
+    for (int k = 0; k < 3; k++) {  // Vec3b = sat(wm * p0) + sat((1 - wm) * p1), saturated again
+        int m = s3_sat_u8(S3_FMUL(wm, (float)orow_bgr[3 * xm + k])) + s3_sat_u8(S3_FMUL(w1, (float)orow_bgr[3 * (xm + 1) + k]));
+        m = m > 255 ? 255 : m;
+        const int df = (int)self_bgr[k] - m;
+        cc = S3_FADD(cc, (float)(df < 0 ? -df : df));
+    }
+    float cg = 0.0f;
+    for (int k = 0; k < 2; k++) {  // Vec2f average, then converted to Vec2b
+        const float gm = (float)s3_sat_u8(S3_FADD(S3_FMUL(wm, orow_grad[2 * xm + k]), S3_FMUL(w1, orow_grad[2 * (xm + 1) + k])));
+        const float df = S3_FSUB(self_grad[k], gm);
+        cg = S3_FADD(cg, df < 0.0f ? -df : df);
+    }
+    cc = cc < tau_c ? cc : tau_c;
+    cg = cg < tau_g ? cg : tau_g;
+    return S3_FMUL(S3_FADD(S3_FMUL(S3_FSUB(1.0f, alpha), cc), S3_FMUL(alpha, cg)), scale);
+}

@@ -30,6 +30,8 @@ struct View {
     uchar4* raw4 = nullptr;    // [N] raw (b,g,r,0)
     uchar4* med = nullptr;     // [N] median-filtered (b,g,r,0)
     float* gray = nullptr;     // [N] s3_gray of the RAW image (cost kernel)
+    float* pgrad = nullptr;    // [N][2] Sobel/8 gradients of the BGR2GRAY image (pms_cost_mode 1, pm.cpp:70-88), lazily allocated
+    bool plane_ready = false;
     uint16_t* ew = nullptr;    // [2N] edge weights by canonical id
     // ---- union-find / forest construction
     void* uf_comp = nullptr;   // [N] x 32 B component records (forest.cu: FHComp)
@@ -223,5 +225,6 @@ int s3_lr_check(s3dmst_ctx* ctx, int fill);
 int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
 int s3_reproject(s3dmst_ctx* ctx, const double* Q16, float disp_floor, int handle_missing, float* h_xyz, uint32_t* h_rgb);
 int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D);
+int s3_prepare_plane_cost(s3dmst_ctx* ctx, int Dmax);              // pms.cu
 int s3_weighted_median(s3dmst_ctx* ctx, int view, int radius, float gamma, const uint8_t* h_mask);  // postfilter.cu
 int s3_norm_factor(s3dmst_ctx* ctx, int view, double* h_out);

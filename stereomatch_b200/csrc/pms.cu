@@ -129,6 +129,40 @@ __global__ void __launch_bounds__(256) k_pms(PmsArgs A) {
     }
 }
 
+// ---- data term of params.pms_cost_mode = 1: gradients of both views (pm.cpp:70-88: cvtColor BGR2GRAY, Sobel 3x3 / 8)
+__global__ void k_pm_gradients(int W, int H, const uint8_t* __restrict__ bgr, float* __restrict__ grad) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int x = p % W, y = p / W;
+    const int xs[3] = {s3_reflect101(x - 1, W), x, s3_reflect101(x + 1, W)}, ys[3] = {s3_reflect101(y - 1, H), y, s3_reflect101(y + 1, H)};
+    int g[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const uint8_t* c = bgr + 3 * ((size_t)ys[j] * W + xs[i]);
+            g[j][i] = s3_cv_gray(c[0], c[1], c[2]);
+        }
+    const int gx = (g[0][2] + 2 * g[1][2] + g[2][2]) - (g[0][0] + 2 * g[1][0] + g[2][0]);
+    const int gy = (g[2][0] + 2 * g[2][1] + g[2][2]) - (g[0][0] + 2 * g[0][1] + g[0][2]);
+    grad[2 * (size_t)p] = (float)gx / 8.f;
+    grad[2 * (size_t)p + 1] = (float)gy / 8.f;
+}
+
+int s3_prepare_plane_cost(s3dmst_ctx* ctx, int Dmax) {
+    const int N = ctx->N;
+    for (int view = 0; view < 2; view++) {
+        View& V = ctx->v[view];
+        if (V.cost_ready && V.D != Dmax) return s3_fail(ctx, S3DMST_E_ARG, "prepare_plane_cost: the view holds a cost volume of %d labels", V.D);
+        if (!V.pgrad) S3_CUDA(cudaMalloc(&V.pgrad, sizeof(float) * 2 * (size_t)N));
+        k_pm_gradients<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->W, ctx->H, V.bgr, V.pgrad);
+        S3_LAUNCH_CHECK();
+        if (!V.cost_ready) { V.D = Dmax; V.Dp = (Dmax + 3) / 4 * 4; }
+        V.plane_ready = true;
+    }
+    return 0;
+}
+
 // scratch of the proposal kernels: [N][64] doubles + the label list + the offsets
 static int pms_scratch(s3dmst_ctx* ctx, size_t n_labels, int T, double** scr, float** d_lab, int** d_off) {
     const size_t scr_bytes = (size_t)ctx->N * 64 * sizeof(double);  // [node][64] (dataflow kernel) / [node][PMS_KB] (simple kernel)
@@ -151,8 +185,10 @@ static int pms_scratch(s3dmst_ctx* ctx, size_t n_labels, int T, double** scr, fl
 
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n) {
     View& V = ctx->v[view];
-    if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
-        return s3_fail(ctx, S3DMST_E_STATE, "pms_apply: forest, cost volume and labels required");
+    const bool plane = ctx->P.pms_cost_mode == 1;
+    if (!V.forest_ready || !(plane ? ctx->v[0].plane_ready && ctx->v[1].plane_ready : V.cost_ready) || !V.labels_ready)
+        return s3_fail(ctx, S3DMST_E_STATE, "pms_apply: forest, %s and labels required", plane ? "s3dmst_prepare_plane_cost" : "cost volume");
+    if (plane && ctx->P.agg_kernel == 1) return s3_fail(ctx, S3DMST_E_ARG, "pms_apply: the plane cost runs in the dataflow kernel only");
     if (n == 0) return 0;
     S3_TRY(s3_forest_finish_host(ctx));
     const int T = V.T;
@@ -418,8 +454,9 @@ __global__ void k_pms_gen_prop(int T, const int* __restrict__ adj_ptr, const int
 // (Q6/Q8/Q9), and a "random pixel of a tree" indexes the tree's BFS order instead of its raster order.
 int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed) {
     View& V = ctx->v[view];
-    if (!V.forest_ready || !V.cost_ready || !V.labels_ready)
-        return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: forest, cost volume and labels required");
+    const bool plane = ctx->P.pms_cost_mode == 1;
+    if (!V.forest_ready || !(plane ? ctx->v[0].plane_ready && ctx->v[1].plane_ready : V.cost_ready) || !V.labels_ready)
+        return s3_fail(ctx, S3DMST_E_STATE, "pms_iterate: forest, %s and labels required", plane ? "s3dmst_prepare_plane_cost" : "cost volume");
     if (!ctx->P.exact) return s3_fail(ctx, S3DMST_E_ARG, "pms_iterate: proposals are evaluated in the exact mode only");
     S3_TRY(s3_forest_finish_host(ctx));
     S3_TRY(s3_tree_adjacency(ctx, view));

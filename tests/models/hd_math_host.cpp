@@ -82,3 +82,29 @@ int hd_gen_refinement(int T, int W, const int* tree_start, const int* node_pixel
     return n;
 }
 }
+
+// ---- host build of the plane cost (pms_cost_mode 1) for the CPU parity test against the oracle
+extern "C" void hd_plane_cost_map(int view, const uint8_t* left_bgr, const uint8_t* right_bgr, const float* left_grad, const float* right_grad, int W, int H,
+                                  float a, float b, float c, int max_disp, float alpha, float tau_c, float tau_g, float scale, float oob, float* out) {
+    const uint8_t* simg = view ? right_bgr : left_bgr; const uint8_t* oimg = view ? left_bgr : right_bgr;
+    const float* sgrad = view ? right_grad : left_grad; const float* ograd = view ? left_grad : right_grad;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const size_t p = (size_t)y * W + x;
+            out[p] = s3_plane_cost(simg + 3 * p, sgrad + 2 * p, oimg + 3 * (size_t)y * W, ograd + 2 * (size_t)y * W, x, y, W, view, a, b, c, max_disp, alpha, tau_c,
+                                   tau_g, scale, oob);
+        }
+}
+extern "C" void hd_pm_gradients(const uint8_t* bgr, int W, int H, float* grad) {
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int g[3][3];
+            for (int j = 0; j < 3; j++)
+                for (int i = 0; i < 3; i++) {
+                    const uint8_t* c = bgr + 3 * ((size_t)s3_reflect101(y + j - 1, H) * W + s3_reflect101(x + i - 1, W));
+                    g[j][i] = s3_cv_gray(c[0], c[1], c[2]);
+                }
+            grad[2 * ((size_t)y * W + x)] = (float)((g[0][2] + 2 * g[1][2] + g[2][2]) - (g[0][0] + 2 * g[1][0] + g[2][0])) / 8.f;
+            grad[2 * ((size_t)y * W + x) + 1] = (float)((g[2][0] + 2 * g[2][1] + g[2][2]) - (g[0][0] + 2 * g[0][1] + g[0][2])) / 8.f;
+        }
+}

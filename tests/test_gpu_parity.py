@@ -923,3 +923,48 @@ def test_norm_factor_matches_oracle(api, oracle):
     disp, bst = eng.aggregate_dense(0)
     assert np.array_equal(disp, do) and np.array_equal(bits(bst), bits(bo))
     eng.close()
+
+
+@pytest.mark.parametrize("cluster", [-1, 64])
+def test_plane_cost_mode_matches_oracle(api, oracle, cluster):
+    """North-star item 1, slanted variant (params.pms_cost_mode = 1): proposals are scored by the truncated colour + gradient
+    difference to the other image at the sub-pixel match position (pm::PatchMatch, src/pm.cpp:97-154) instead of by a lerp
+    in a cost volume — no volume exists.  Gradients bit-identical to the oracle's (= cv2's), an injected proposal list
+    gives the oracle's labels and costs on both views, and the library's own generator runs on top of it."""
+    W, H, D = 150, 90, 20
+    L, R, gt = make(W, H, D, 21, 0)
+    N = W * H
+    c, ms = 700.0, 30
+    rng = np.random.default_rng(4)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, pms_cost_mode=1, cost_scale=0.25, agg_cluster_nodes=cluster)
+    eng.set_images(L, R)
+    eng.build_forest(0); eng.build_forest(1)
+    eng.prepare_plane_cost(D)
+    for view, img in ((0, L), (1, R)):
+        assert np.array_equal(bits(eng.get_plane_gradients(view)), bits(oracle.pm_gradients(img)))
+    for view, img in ((0, L), (1, R)):
+        F = oracle.forest(img, c=c, min_size=ms)
+        n = 70 * F.T + 13                      # more than 64 proposals on some trees: several batches
+        trees = rng.integers(0, F.T, n).astype(np.int32)
+        labels = np.stack([rng.uniform(-0.05, 0.05, n), rng.uniform(-0.05, 0.05, n), rng.uniform(-3, D + 3, n)], 1).astype(np.float32)
+        labels[5] = (0, 0, 3.0); labels[6] = (np.nan, 0, 3.0); labels[7] = (0, 0, 1e12); labels[8] = (0, 0, float(D))
+        abc_o = oracle.plane_init(W, H, D)
+        mn_o = np.full(N, np.finfo(np.float64).max)
+        eng.set_labels(view, abc_o)
+        eng.reset_min_cost(view)
+        eng.pms_apply(view, trees, labels)
+        oracle.pms_apply_plane(F, view, L, R, D, trees, labels, mn_o, abc_o, scale=0.25)
+        assert np.array_equal(bits(eng.get_min_cost(view)), bits(mn_o)), view
+        assert np.array_equal(bits(eng.get_labels(view)), bits(abc_o)), view
+    # the whole reference-mode pipeline on this data term (no cost volume anywhere)
+    e2 = api.Stereo3DMST(pms_cost_mode=1, cost_scale=0.25, num_iter=16)
+    W2, H2, D2 = 256, 160, 32
+    L2, R2, gt2 = make(W2, H2, D2, 77, 0)
+    e2.set_images(L2, R2)
+    dl, dr = e2.run(D2, seed=3)
+    valid = dl.reshape(H2, W2) > 0
+    err = np.abs(dl.reshape(H2, W2) - gt2)
+    assert valid.mean() > 0.3 and (err[valid] <= 1.0).mean() > 0.5
+    with pytest.raises(api.S3Error):
+        e2.aggregate_dense(0, 0, D2)           # there is no volume to aggregate
+    eng.close(); e2.close()

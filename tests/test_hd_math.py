@@ -92,3 +92,33 @@ def test_label_disp_and_ingest(hd, oracle):
         want = oracle.ingest(v, cap, off, sc)
         got = np.float32([hd.hd_ingest(x, cap, off, sc) for x in v])
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_plane_cost_and_gradients(hd, oracle):
+    """pms_cost_mode 1 (north-star item 1, slanted variant): the shared header's gradients equal cv2's (cvtColor + Sobel/8,
+    pm.cpp:70-88) and the oracle's; its per-pixel plane cost equals the oracle's restatement of pm.cpp:97-154 bit for bit,
+    for both views, incl. planes leaving [0, Dmax], matches beyond both image borders and integer disparities."""
+    import cv2
+    hd.hd_pm_gradients.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    hd.hd_plane_cost_map.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int] + [C.c_float] * 5 + [C.c_void_p]
+    rng = np.random.default_rng(3)
+    for (W, H, D, seed, nat) in ((97, 61, 24, 3, 1), (64, 7, 16, 4, 0), (2, 5, 4, 5, 0)):
+        L, R, _ = (synth.make_natural_pair if nat else synth.make_pair)(W, H, max(D, 12), seed=seed)
+        grads = []
+        for img in (L, R):
+            g = np.empty((H, W, 2), np.float32)
+            hd.hd_pm_gradients(p(img), W, H, p(g))
+            gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+            assert np.array_equal(g[..., 0], cv2.Sobel(gray, cv2.CV_32F, 1, 0, ksize=3) / np.float32(8))
+            assert np.array_equal(g[..., 1], cv2.Sobel(gray, cv2.CV_32F, 0, 1, ksize=3) / np.float32(8))
+            assert np.array_equal(g, oracle.pm_gradients(img))
+            grads.append(g)
+        labels = [(0.0, 0.0, 3.0), (0.0, 0.0, 3.5), (0.01, -0.02, 5.25), (-0.3, 0.1, 9.0), (0.0, 0.0, -1.0), (0.0, 0.0, D + 0.5), (0.0, 0.0, float(D))]
+        labels += [tuple(x) for x in np.stack([rng.uniform(-.05, .05, 6), rng.uniform(-.05, .05, 6), rng.uniform(-2, D + 2, 6)], 1)]
+        for view in (0, 1):
+            for lab in labels:
+                lab = np.float32(lab)
+                out = np.empty(W * H, np.float32)
+                hd.hd_plane_cost_map(view, p(L), p(R), p(grads[0]), p(grads[1]), W, H, lab[0], lab[1], lab[2], D, 0.9, 10.0, 2.0, 0.25, 0.5, p(out))
+                want = oracle.plane_cost_map(view, L, R, lab, D, scale=0.25)
+                assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (W, view, lab)
