@@ -169,7 +169,8 @@ int s3dmst_dense_to_disparity(s3dmst_ctx* ctx, int view);
 /* a2' slanted variant (north-star item 1): prepares the data term of params.pms_cost_mode = 1 for Dmax labels — Sobel/8
  * gradients of both views (pm.cpp:70-88).  After it s3dmst_pms_apply / s3dmst_pms_iterate / s3dmst_run score a plane at
  * a pixel by the truncated colour + gradient difference to the other image at x -+ d (sub-pixel, pm.cpp:130-154) times
- * params.cost_scale, and params.oob_cost outside [0, Dmax]; no cost volume is needed or touched. */
+ * params.cost_scale, and params.oob_cost outside [0, Dmax] (the reference's PLANE_PENALTY is 120: set oob_cost to
+ * 120 * cost_scale, well above the 2.8 * cost_scale of a mismatch); no cost volume is needed or touched. */
 int s3dmst_prepare_plane_cost(s3dmst_ctx* ctx, int Dmax);
 /* the gradients it computed: float [H*W][2] (parity dumps) */
 int s3dmst_get_plane_gradients(s3dmst_ctx* ctx, int view, float* grad);

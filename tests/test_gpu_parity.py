@@ -957,7 +957,8 @@ def test_plane_cost_mode_matches_oracle(api, oracle, cluster):
         assert np.array_equal(bits(eng.get_min_cost(view)), bits(mn_o)), view
         assert np.array_equal(bits(eng.get_labels(view)), bits(abc_o)), view
     # the whole reference-mode pipeline on this data term (no cost volume anywhere)
-    e2 = api.Stereo3DMST(pms_cost_mode=1, cost_scale=0.25, num_iter=16)
+    # (out-of-range planes must cost more than a mismatch, as the reference's PLANE_PENALTY = 120 does: 120 x scale)
+    e2 = api.Stereo3DMST(pms_cost_mode=1, cost_scale=0.25, oob_cost=30.0, num_iter=16)
     W2, H2, D2 = 256, 160, 32
     L2, R2, gt2 = make(W2, H2, D2, 77, 0)
     e2.set_images(L2, R2)
