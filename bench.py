@@ -417,7 +417,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = max(1, args.batch)
     # one context (and stream) per frame of the batch; in a batch the cooperative forest kernel takes a share of the SMs
-    engs = [api.Stereo3DMST(device=local, fh_ctas=(args.fh_ctas if B > 1 else 0), fh_threads=(args.fh_threads if B > 1 else 0)) for _ in range(B)]
+    engs = [api.Stereo3DMST(device=local, fh_ctas=(args.fh_ctas if B > 1 else 0), fh_threads=(args.fh_threads if B > 1 else 0), fh_cluster=args.fh_cluster) for _ in range(B)]
     frames = [synth.make_pair(W, H, D, seed=synth.BASE_SEED + 10 + rank * B + i) for i in range(B)]   # different frames per rank (C4: seed+10 ...)
     # pinned host staging for the e2e leg
     pin = [(torch.from_numpy(L.copy()).pin_memory(), torch.from_numpy(R.copy()).pin_memory()) for L, R, _ in frames]
@@ -570,6 +570,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="stereo pairs per step per GPU")
     ap.add_argument("--fh-ctas", type=int, default=36, help="CTAs of the forest kernel per frame when batching")
     ap.add_argument("--fh-threads", type=int, default=1024, help="threads per CTA of the forest kernel when batching")
+    ap.add_argument("--fh-cluster", type=int, default=0, help="CTAs of the thread-block cluster a view's forest kernel runs in (0: cooperative grid)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the c1_flir / c2 objects")
     ap.add_argument("--no-label-sharded", action="store_true", help="skip the C5 leg at N >= 2")

@@ -152,6 +152,7 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->fh_ctas = 0;
     p->fh_threads = 0;
     p->agg_cluster_nodes = 0;
+    p->fh_cluster = 0;
     p->pms_cost_mode = 0;
     p->pm_alpha = 0.9f;
     p->pm_tau_c = 10.0f;
@@ -450,13 +451,13 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.node_pixel, node_pixel, sizeof(int) * N);
     H2D(V.parent, parent, sizeof(int) * N);
     H2D(V.pw, parent_weight, sizeof(uint16_t) * N);
-    H2D(V.node_up, nu.data(), sizeof(NodeUp) * N);
     std::vector<int4> nd(N);
-    for (int i = 0; i < N; i++) {
+    for (int i = 0; i < N; i++) {  // (the records are uploaded only once they are complete)
         if (parent[i] != i && i - parent[i] >= S3_AGG_NEAR) nu[i].child_count |= S3_NU_FARPARENT;
         const bool far_child = (nu[i].child_count & 7) > 0 && nu[i].child_begin + (nu[i].child_count & 7) - 1 - i >= S3_AGG_NEAR;
         nd[i] = make_int4(parent[i], parent_weight[i], level[i] | (far_child ? S3_ND_FAR : 0) | ((nu[i].child_count & 7) == 0 ? S3_ND_LEAF : 0), node_pixel[i]);
     }
+    H2D(V.node_up, nu.data(), sizeof(NodeUp) * N);
     H2D(V.node_dn, nd.data(), sizeof(int4) * N);
     std::vector<uint32_t> lbits(N / 32 + 2, 0u);
     for (int i = 0; i < N; i++)

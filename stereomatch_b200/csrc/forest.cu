@@ -135,6 +135,7 @@ struct FHArgs2 {
     FHArgs v[S3_FH_MAX_VIEWS];
     int nviews;
     int seg_cap;         // capacity of one CTA's segment of the live-edge lists (entries)
+    int cluster;         // > 0: the launch gives every view ONE thread-block cluster of this many CTAs (hardware barrier)
     unsigned* bar;       // [S3_FH_MAX_VIEWS][32] one barrier counter per view (zeroed by the host)
     int* gcnt;           // [S3_FH_ROUNDS][S3_FH_MAX_VIEWS] per-round, per-view live counts (zeroed by the host)
 };
@@ -154,6 +155,13 @@ __device__ __forceinline__ void fh_grid_bar(unsigned* bar, unsigned& target, uns
         __threadfence();
     }
     __syncthreads();
+}
+
+// The same for a view that owns one thread-block cluster: the hardware cluster barrier (release / acquire at cluster
+// scope orders the L2 accesses of the view's CTAs) costs a few hundred cycles instead of a round trip of atomics
+// through L2 per CTA — the ~300 barriers of a forest were most of its time when one pair is alone on the GPU.
+__device__ __forceinline__ void fh_cluster_bar() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // FH phase — asynchronous exact formulation.  Sequential FH visits edges in key order (w, id) and accepts an edge iff
@@ -177,11 +185,12 @@ __device__ __forceinline__ void fh_grid_bar(unsigned* bar, unsigned& target, uns
 // the CTA that looked at them, new levels are dealt out evenly), so compaction needs no global cursor.
 __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
     const int nblk_all = gridDim.x;
-    const int per_view = nblk_all / AA.nviews;
+    const bool cl = AA.cluster > 0;
+    const int per_view = cl ? AA.cluster : nblk_all / AA.nviews;
     const int vi = min((int)blockIdx.x / per_view, AA.nviews - 1);
     const FHArgs& A = AA.v[vi];
-    const int crank = blockIdx.x - vi * per_view;                                   // CTA rank inside its view
-    const int nblk = vi == AA.nviews - 1 ? nblk_all - vi * per_view : per_view;     // CTAs of this view
+    const int crank = blockIdx.x - vi * per_view;                                   // CTA rank inside its view (= its rank in the cluster)
+    const int nblk = cl ? per_view : (vi == AA.nviews - 1 ? nblk_all - vi * per_view : per_view);     // CTAs of this view
     const int gtid = crank * blockDim.x + threadIdx.x;
     const int gstride = nblk * blockDim.x;
     const int cbase = crank * blockDim.x;
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
     unsigned bar_target = 0;
     int round = 0;
     __shared__ int s_cnt;
-#define FH_BAR() fh_grid_bar(AA.bar + 32 * vi, bar_target, (unsigned)nblk)  // the views never wait for each other
+#define FH_BAR() do { if (cl) fh_cluster_bar(); else fh_grid_bar(AA.bar + 32 * vi, bar_target, (unsigned)nblk); } while (0)  // the views never wait for each other
 
     // ------------------------------------------------------------------ FH
     {
@@ -797,9 +806,10 @@ int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask) {
     S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fh_merge, threads, 0));
     if (ctas_per_sm < 1) return s3_fail(ctx, S3DMST_E_CUDA, "k_fh_merge does not fit on an SM");
     const int want = (nctx > 1 || ctx->P.fh_ctas <= 0) ? ctx->num_sms : ctx->P.fh_ctas;  // a joint launch takes every SM
-    const int per_view = std::max(1, std::min(std::min(want, ctx->num_sms * ctas_per_sm), S3_FH_MAX_CTAS) / nv);
+    const int cluster = ctx->P.fh_cluster > 0 ? std::min(16, ctx->P.fh_cluster) : 0;
+    const int per_view = cluster ? cluster : std::max(1, std::min(std::min(want, ctx->num_sms * ctas_per_sm), S3_FH_MAX_CTAS) / nv);
     const int grid = per_view * nv;  // every view gets the same number of CTAs (and list segments of one size)
-    if (grid > ctx->num_sms * ctas_per_sm) return s3_fail(ctx, S3DMST_E_ARG, "forest kernel: %d views do not fit the GPU in one cooperative launch", nv);
+    if (!cluster && grid > ctx->num_sms * ctas_per_sm) return s3_fail(ctx, S3DMST_E_ARG, "forest kernel: %d views do not fit the GPU in one cooperative launch", nv);
     AA.nviews = nv;
     AA.seg_cap = (2 * ctx->N + per_view - 1) / per_view + S3_FH_SEG_SLACK;
     const size_t sync_ints = 32 * S3_FH_MAX_VIEWS + (size_t)S3_FH_ROUNDS * S3_FH_MAX_VIEWS;  // one barrier word (own 128-byte line) per view + counters
@@ -811,8 +821,24 @@ int s3_fh_launch_multi(s3dmst_ctx** ctxs, int nctx, int mask) {
         S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
         S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[c]->ev_xctx, 0));
     }
-    void* args[] = {&AA};
-    S3_CUDA(cudaLaunchCooperativeKernel((const void*)k_fh_merge, dim3(grid), dim3(threads), args, 0, ctx->stream));
+    AA.cluster = cluster;
+    if (cluster) {  // one cluster per view: its CTAs are co-scheduled by the hardware, the views are independent
+        if (cluster > 8) S3_CUDA(cudaFuncSetAttribute(k_fh_merge, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        S3_CUDA(cudaLaunchKernelEx(&cfg, k_fh_merge, AA));
+    } else {
+        void* args[] = {&AA};
+        S3_CUDA(cudaLaunchCooperativeKernel((const void*)k_fh_merge, dim3(grid), dim3(threads), args, 0, ctx->stream));
+    }
     ctx->launches++;
     if (nctx > 1) {
         S3_CUDA(cudaEventRecord(ctx->ev_xctx, ctx->stream));
