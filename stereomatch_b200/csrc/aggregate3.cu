@@ -59,8 +59,6 @@ struct Agg3View {
     double* best;
     int32_t* pdisp;   // [slice][node] partial results otherwise
     double* pbest;
-    int32_t* bdisp;   // the same for the bottom subtrees' nodes (k_agg_bottom: slices of 64 labels)
-    double* bbest;
     const int4* bottom_list;      // the view's bottom subtrees {root, first descriptor, nodes} (forest.cu: k_subtree_flags), *bottom_count of them
     const int4* bottom_desc;      // their node descriptors (forest.cu: k_bottom_desc)
     const int* bottom_count;
@@ -93,7 +91,6 @@ struct Agg3Args {
     // after this kernel); the walk passes over them, reads a bottom child's leaf->root row from HBM and leaves the final
     // row of a node with bottom children there
     int bottom;
-    int b_slices;          // 64-label slices of k_agg_bottom
     const int4* bunits;    // k_agg_bottom: {view, first label, slice index, 0} per (view, slice) of the launch
     int n_bunits;
     int cost_mode, view, img_h;            // proposal mode: 1 = plane cost from the images (hd_math.h: s3_plane_cost)
@@ -767,20 +764,19 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 // order, local indices of the children and of the parent, weights, pixel), and the cost rows of the whole subtree are
 // fetched at once with cp.async.  Lanes own label pairs, as in the walk: a lane only ever touches its own columns of the
 // shared rows, so the passes need no synchronisation inside the warp.
-#define AB_WARPS 24   // warps per CTA of k_agg_bottom: 24 x (16 rows of 64 doubles + descriptors) + the weight tables fill the SM's shared memory
-template <bool FULL, bool DOWN>
-__global__ void __launch_bounds__(32 * AB_WARPS, 1) k_agg_bottom(Agg3Args A) {
+template <int NH, bool FULL, bool DOWN, int WPB>
+__global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int M = S3_BOTTOM_M;
     using TT = A3T<double>;
-    constexpr uint32_t ROWB = 64 * sizeof(double);   // a row = 64 labels: one double2 per lane
+    constexpr uint32_t HB = 64 * sizeof(double), ROWB = NH * HB;
     constexpr uint32_t LUTB = ((2 * S3_NUM_W * sizeof(double) + 15) / 16) * 16;
-    constexpr uint32_t WB = M * ROWB + M * 32;       // the batch's rows and descriptors
+    constexpr uint32_t WB = M * ROWB + M * 32;   // the subtree's rows and descriptors
     double* s_w = reinterpret_cast<double*>(s_raw);
     double* s_w2 = s_w + S3_NUM_W;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     unsigned char* wb = s_raw + LUTB + (size_t)w * WB;
-    const uint32_t rows_a = a3_smem(wb) + (uint32_t)sizeof(double2) * lane;   // this lane's column of the rows
+    const uint32_t rows_a = a3_smem(wb) + (uint32_t)sizeof(double2) * lane;   // this lane's column of the subtree's rows
     int4* s_d = reinterpret_cast<int4*>(wb + M * ROWB);                       // [M][2] descriptors (forest.cu: k_bottom_desc)
     for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
         s_w[i] = reinterpret_cast<const double*>(A.lut_w)[i];
@@ -788,7 +784,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 1) k_agg_bottom(Agg3Args A) {
     }
     __syncthreads();
     const uint32_t w_a = a3_smem(s_w);
-    const int gwarp = blockIdx.x * AB_WARPS + w, nwarps = gridDim.x * AB_WARPS;
+    const int gwarp = blockIdx.x * WPB + w, nwarps = gridDim.x * WPB;
     const size_t Dp = (size_t)A.Dp;
 
     for (int bu = 0; bu < A.n_bunits; bu++) {
@@ -796,145 +792,145 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 1) k_agg_bottom(Agg3Args A) {
         const Agg3View V = A.views[unit.x];
         const int l0 = unit.y, slice = unit.z;
         const int nb = *V.bottom_count;
-        const bool act = FULL || l0 + 2 * lane < A.d1;   // the lane's pair holds at least one real label
-        // 32 consecutive subtrees per trip (one coalesced read of the list), packed into batches of at most M rows: the list
-        // is in descriptor order, so a batch is ONE run of descriptors and ONE burst of cost rows
-        for (int chunk = gwarp * 32; chunk < nb; chunk += nwarps * 32) {
-            int n_l = 0, off_l = 0;
-            if (chunk + lane < nb) {
-                const int4 e = __ldg(V.bottom_list + chunk + lane);
-                off_l = e.y; n_l = e.z;
-            }
-            int pre = n_l;  // inclusive prefix of the subtree sizes
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, pre, o);
-                if (lane >= o) pre += u;
-            }
-            const int cnt = min(32, nb - chunk);
-            int j0 = 0, done = 0;   // first subtree of the batch, rows before it
-            while (j0 < cnt) {
-                // subtrees j0 .. j1-1: as many as fit M rows (a subtree has at most M nodes, so at least one does)
-                const unsigned fit = __ballot_sync(0xffffffffu, lane >= j0 && lane < cnt && pre - done <= M);
-                const int j1 = j0 + __popc(fit);
-                const int rows = __shfl_sync(0xffffffffu, pre, j1 - 1) - done;
-                const int d_start = __shfl_sync(0xffffffffu, off_l, j0);
-                __syncwarp();  // the previous batch is done with the descriptors
-                if (lane < rows) {
-                    const int4* dp = V.bottom_desc + 2 * ((size_t)d_start + lane);
-                    s_d[2 * lane] = __ldg(dp);
-                    s_d[2 * lane + 1] = __ldg(dp + 1);
-                }
-                __syncwarp();
-                // ---- cost rows -> shared rows: every row of the batch in flight at once (cp.async: no registers held)
-                if (act)
-                    for (int i = 0; i < rows; i++)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rows_a + (uint32_t)i * ROWB),
-                                     "l"(V.cost + (size_t)s_d[2 * i].x * Dp + l0 + 2 * lane)
-                                     : "memory");
-                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-                // ---- leaf -> root inside every subtree of the batch: (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost
-                // (Stereo3DMST.cpp:125-137); a cell holds the node's cost (fp32, as copied) until the node is reached, then its sum;
-                // children sit behind their parent in the run, so descending order serves every subtree at once
-                for (int i = rows - 1; i >= 0; i--) {
-                    const int4 d0 = s_d[2 * i];
-                    const int4 d1 = s_d[2 * i + 1];
-                    const int cc = d0.z & 7;
-                    const int sb = i - (int)((unsigned)d0.z >> 26);        // first row of this node's subtree
-                    const int cl0 = sb + ((d0.z >> 3) & 63);
-                    double2 acc = make_double2(0.0, 0.0);
+        bool act[NH];
 #pragma unroll
-                    for (int j = 3; j >= 0; j--)
-                        if (cc > j) {
-                            const uint32_t iw = ((j & 2) ? (uint32_t)d1.x : (uint32_t)d0.w) >> ((j & 1) * 16) & 0xFFFFu;
-                            const double wk = TT::ldsw(w_a + 8u * iw);
-                            const double2 cv = TT::lds2(rows_a + (uint32_t)(cl0 + j) * ROWB);
-                            acc.x = TT::add(acc.x, TT::mul(wk, cv.x));
-                            acc.y = TT::add(acc.y, TT::mul(wk, cv.y));
+        for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;
+        for (int it = gwarp; it < nb; it += nwarps) {
+            const int4 e = __ldg(V.bottom_list + it);   // {root, first descriptor, nodes}
+            const int n = e.z;
+            __syncwarp();  // the previous subtree is done with the descriptors
+            if (lane < n) {
+                const int4* dp = V.bottom_desc + 2 * ((size_t)e.y + lane);
+                s_d[2 * lane] = __ldg(dp);
+                s_d[2 * lane + 1] = __ldg(dp + 1);
+            }
+            __syncwarp();
+            // ---- cost rows -> shared rows: every row of the subtree in flight at once (cp.async: no registers held)
+            for (int i = 0; i < n; i++) {
+                const char* cp = reinterpret_cast<const char*>(V.cost + (size_t)s_d[2 * i].x * Dp + l0 + 2 * lane);
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rows_a + (uint32_t)i * ROWB + h * HB), "l"(cp + h * 256) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            // ---- leaf -> root inside the subtree: (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost (Stereo3DMST.cpp:125-137);
+            // a cell holds the node's cost (fp32, as copied) until the node is reached, then its sum
+            for (int i = n - 1; i >= 0; i--) {
+                const int4 d0 = s_d[2 * i];
+                const int cc = d0.z & 7, cl0 = (d0.z >> 3) & 63;
+                const uint32_t cw23 = (uint32_t)s_d[2 * i + 1].x;
+                double2 acc[NH];
+#pragma unroll
+                for (int h = 0; h < NH; h++) acc[h] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int j = 3; j >= 0; j--)
+                    if (cc > j) {
+                        const uint32_t iw = ((j & 2) ? cw23 : (uint32_t)d0.w) >> ((j & 1) * 16) & 0xFFFFu;
+                        const double wk = TT::ldsw(w_a + 8u * iw);
+                        const uint32_t ra = rows_a + (uint32_t)(cl0 + j) * ROWB;
+#pragma unroll
+                        for (int h = 0; h < NH; h++) {
+                            const double2 cv = TT::lds2(ra + h * HB);
+                            acc[h].x = TT::add(acc[h].x, TT::mul(wk, cv.x));
+                            acc[h].y = TT::add(acc[h].y, TT::mul(wk, cv.y));
                         }
-                    const uint32_t sa = rows_a + (uint32_t)i * ROWB;
+                    }
+                const uint32_t sa = rows_a + (uint32_t)i * ROWB;
+#pragma unroll
+                for (int h = 0; h < NH; h++) {
                     float2 cf = make_float2(0.f, 0.f);
-                    if (act) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf.x), "=f"(cf.y) : "r"(sa) : "memory");
-                    acc.x = TT::add(acc.x, (double)cf.x);
-                    acc.y = TT::add(acc.y, (double)cf.y);
-                    TT::sts2(sa, acc);
-                    if constexpr (!DOWN) {  // a subtree root's row: read by its parent in the walk
-                        if (sb == i && d1.y != d0.x && act) *reinterpret_cast<double2*>(V.aup + (size_t)d0.x * Dp + l0 + 2 * lane) = acc;
-                    }
+                    if (act[h]) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf.x), "=f"(cf.y) : "r"(sa + h * HB) : "memory");
+                    acc[h].x = TT::add(acc[h].x, (double)cf.x);
+                    acc[h].y = TT::add(acc[h].y, (double)cf.y);
+                    TT::sts2(sa + h * HB, acc[h]);
                 }
-                if constexpr (DOWN) {
-                    // ---- root -> leaf: A[c] = w * A[parent] + (1 - w*w) * A_up[c] (Stereo3DMST.cpp:155), WTA per node
-                    for (int i = 0; i < rows; i++) {
-                        const int4 d0 = s_d[2 * i];
-                        const int pg = s_d[2 * i + 1].y;   // parent node (global)
-                        const int li = (int)((unsigned)d0.z >> 26);
-                        const uint32_t sa = rows_a + (uint32_t)i * ROWB;
-                        double2 fin = TT::lds2(sa);
-                        if (pg != d0.x) {
-                            const uint32_t iw = ((uint32_t)d0.z >> 16) & 0x3FFu;
-                            const double wp = TT::ldsw(w_a + 8u * iw), wq = TT::ldsw(w_a + 8u * (S3_NUM_W + iw));
-                            double2 pv;
-                            if (li == 0)  // the parent is a node of the walk: its final row is in HBM
-                                pv = act ? TT::ldcg2(reinterpret_cast<const char*>(V.aup + (size_t)pg * Dp + l0 + 2 * lane)) : make_double2(0.0, 0.0);
-                            else
-                                pv = TT::lds2(rows_a + (uint32_t)(i - li + ((d0.z >> 9) & 63)) * ROWB);
-                            fin.x = TT::add(TT::mul(wp, pv.x), TT::mul(wq, fin.x));
-                            fin.y = TT::add(TT::mul(wp, pv.y), TT::mul(wq, fin.y));
-                            TT::sts2(sa, fin);
-                        }
-                        // WTA over the node's 64 labels: strict '<', lowest label wins ties
-                        double bc = DBL_MAX;
-                        int bd = 0x7fffffff;
-                        const int lab = l0 + 2 * lane;
-                        if ((FULL || lab < A.d1) && fin.x < bc) { bc = fin.x; bd = lab; }
-                        if ((FULL || lab + 1 < A.d1) && fin.y < bc) { bc = fin.y; bd = lab + 1; }
-                        double mc;
-                        const unsigned md = TT::warp_argmin(bc, bd, mc);
-                        if (lane == 0) {
-                            if (A.b_slices == 1) {
-                                V.disp[d0.y] = (int)md;
-                                V.best[d0.y] = mc;
-                            } else {
-                                V.bdisp[(size_t)slice * A.N + d0.x] = (int)md;
-                                V.bbest[(size_t)slice * A.N + d0.x] = mc;
-                            }
+            }
+            if constexpr (!DOWN) {  // the subtree root's row: read by its parent in the walk
+                const int r = e.x;
+                if (s_d[1].y != r) {
+                    char* arow = reinterpret_cast<char*>(V.aup + (size_t)r * Dp + l0 + 2 * lane);
+#pragma unroll
+                    for (int h = 0; h < NH; h++)
+                        if (act[h]) *reinterpret_cast<double2*>(arow + h * HB) = TT::lds2(rows_a + h * HB);
+                }
+            } else {
+                // ---- root -> leaf: A[c] = w * A[parent] + (1 - w*w) * A_up[c] (Stereo3DMST.cpp:155), WTA per node
+                auto wta = [&](const double2* f, int g, int pix) {
+                    double bc = DBL_MAX;
+                    int bd = 0x7fffffff;
+#pragma unroll
+                    for (int h = 0; h < NH; h++) {
+                        const int lab = l0 + h * 64 + 2 * lane;
+                        if ((FULL || lab < A.d1) && f[h].x < bc) { bc = f[h].x; bd = lab; }
+                        if ((FULL || lab + 1 < A.d1) && f[h].y < bc) { bc = f[h].y; bd = lab + 1; }
+                    }
+                    double mc;
+                    const unsigned md = TT::warp_argmin(bc, bd, mc);
+                    if (lane == 0) {
+                        if (A.n_slices == 1) {
+                            V.disp[pix] = (int)md;
+                            V.best[pix] = mc;
+                        } else {
+                            V.pdisp[(size_t)slice * A.N + g] = (int)md;
+                            V.pbest[(size_t)slice * A.N + g] = mc;
                         }
                     }
+                };
+                for (int i = 0; i < n; i++) {
+                    const int4 d0 = s_d[2 * i];
+                    const int pg = s_d[2 * i + 1].y;   // parent node (global)
+                    const uint32_t sa = rows_a + (uint32_t)i * ROWB;
+                    double2 fin[NH];
+#pragma unroll
+                    for (int h = 0; h < NH; h++) fin[h] = TT::lds2(sa + h * HB);
+                    if (pg != d0.x) {
+                        const uint32_t iw = ((uint32_t)d0.z >> 16) & 0x3FFu;
+                        const double wp = TT::ldsw(w_a + 8u * iw), wq = TT::ldsw(w_a + 8u * (S3_NUM_W + iw));
+                        double2 pv[NH];
+                        if (i == 0) {  // the parent is a node of the walk: its final row is in HBM
+                            const char* gp = reinterpret_cast<const char*>(V.aup + (size_t)pg * Dp + l0 + 2 * lane);
+#pragma unroll
+                            for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : make_double2(0.0, 0.0);
+                        } else {
+                            const uint32_t pa = rows_a + (uint32_t)((d0.z >> 9) & 63) * ROWB;
+#pragma unroll
+                            for (int h = 0; h < NH; h++) pv[h] = TT::lds2(pa + h * HB);
+                        }
+#pragma unroll
+                        for (int h = 0; h < NH; h++) {
+                            fin[h].x = TT::add(TT::mul(wp, pv[h].x), TT::mul(wq, fin[h].x));
+                            fin[h].y = TT::add(TT::mul(wp, pv[h].y), TT::mul(wq, fin[h].y));
+                            TT::sts2(sa + h * HB, fin[h]);
+                        }
+                    }
+                    wta(fin, d0.x, d0.y);
                 }
-                done += rows;
-                j0 = j1;
             }
         }
     }
 }
+template <int NH, int WPB>
 static size_t agg_bottom_smem() {
     const size_t lut = ((2 * S3_NUM_W * sizeof(double) + 15) / 16) * 16;
-    return lut + (size_t)AB_WARPS * (S3_BOTTOM_M * 512 + S3_BOTTOM_M * 32);
+    return lut + (size_t)WPB * (S3_BOTTOM_M * NH * 512 + S3_BOTTOM_M * 32);
 }
 
 static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
 
-// combines the per-slice winners of a node: the walk's nodes over its n_slices (128 or 64 labels wide), the bottom
-// subtrees' nodes over k_agg_bottom's b_slices (64 labels wide); a kind with one slice wrote its final result itself
-__global__ void k_wta_finish3(int N, int n_slices, int b_slices, int bottom, const int4* __restrict__ node_dn, const int32_t* __restrict__ pdisp,
-                              const double* __restrict__ pbest, const int32_t* __restrict__ bdisp, const double* __restrict__ bbest,
-                              int32_t* __restrict__ disp, double* __restrict__ best) {
+__global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node_dn, const int32_t* __restrict__ pdisp,
+                              const double* __restrict__ pbest, int32_t* __restrict__ disp, double* __restrict__ best) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
-    const int4 nd = node_dn[v];
-    const bool isb = bottom && (nd.y & S3_NDY_BOTTOM);
-    const int ns = isb ? b_slices : n_slices;
-    if (ns == 1) return;
-    const int32_t* pd = isb ? bdisp : pdisp;
-    const double* pb = isb ? bbest : pbest;
-    double bc = pb[v];
-    int bd = pd[v];
-    for (int s = 1; s < ns; s++) {
-        const double c = pb[(size_t)s * N + v];
-        const int d = pd[(size_t)s * N + v];
+    double bc = pbest[v];
+    int bd = pdisp[v];
+    for (int s = 1; s < n_slices; s++) {
+        const double c = pbest[(size_t)s * N + v];
+        const int d = pdisp[(size_t)s * N + v];
         if (c < bc || (c == bc && d < bd)) { bc = c; bd = d; }
     }
-    disp[nd.w] = bd;
-    best[nd.w] = bc;
+    const int pix = node_dn[v].w;
+    disp[pix] = bd;
+    best[pix] = bc;
 }
 
 #define A3_CLUSTER 8   // CTAs walking one giant tree
@@ -1028,21 +1024,15 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     std::vector<int4> units(u.size());
     for (size_t i = 0; i < u.size(); i++) units[i] = u[i].second;
 
-    // bottom subtrees (k_agg_bottom, slices of 64 labels): exact dense mode without the aggregated-volume dump
-    static const int bottom_env = getenv("S3_AGG_BOTTOM") ? atoi(getenv("S3_AGG_BOTTOM")) : 0;
-    const bool bottom = ctx->P.exact != 0 && !ctx->P.keep_aggregated && (ctx->P.agg_bottom > 0 || (ctx->P.agg_bottom == 0 && bottom_env > 0));
-    const int b_slices = bottom ? (nl + 63) / 64 : 1;
-    // per-view tables and (for several slices) partial WTA results: the walk's, then the bottom subtrees'
+    // per-view tables and (for several slices) partial WTA results
     std::vector<Agg3View> table(2 * (size_t)nctx);
     memset(table.data(), 0, table.size() * sizeof(Agg3View));
-    std::vector<int32_t*> pdisp(2 * (size_t)nctx, nullptr), bdisp(2 * (size_t)nctx, nullptr);
-    std::vector<double*> pbest(2 * (size_t)nctx, nullptr), bbest(2 * (size_t)nctx, nullptr);
+    std::vector<int32_t*> pdisp(2 * (size_t)nctx, nullptr);
+    std::vector<double*> pbest(2 * (size_t)nctx, nullptr);
     for (int c = 0; c < nctx; c++) {
         s3dmst_ctx* cx = ctxs[c];
-        const int ns_a = n_slices > 1 ? n_slices : 0, ns_b = b_slices > 1 ? b_slices : 0;
-        if (ns_a + ns_b) {
-            const size_t per_slice = (size_t)cx->N * (sizeof(double) + sizeof(int32_t));
-            const size_t per_view = (size_t)(ns_a + ns_b) * per_slice;
+        if (n_slices > 1) {
+            const size_t per_view = (size_t)n_slices * cx->N * (sizeof(double) + sizeof(int32_t));
             const size_t need = 2 * per_view;
             if (cx->pms_scratch_cap < need) {
                 if (cx->pms_scratch) S3_CUDA(cudaFree(cx->pms_scratch));
@@ -1051,15 +1041,8 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
                 cx->pms_scratch_cap = need;
             }
             for (int view = 0; view < 2; view++) {
-                char* vb = (char*)cx->pms_scratch + view * per_view;
-                if (ns_a) {
-                    pbest[2 * c + view] = (double*)vb;
-                    pdisp[2 * c + view] = (int32_t*)(pbest[2 * c + view] + (size_t)ns_a * cx->N);
-                }
-                if (ns_b) {
-                    bbest[2 * c + view] = (double*)(vb + (size_t)ns_a * per_slice);
-                    bdisp[2 * c + view] = (int32_t*)(bbest[2 * c + view] + (size_t)ns_b * cx->N);
-                }
+                pbest[2 * c + view] = (double*)((char*)cx->pms_scratch + view * per_view);
+                pdisp[2 * c + view] = (int32_t*)(pbest[2 * c + view] + (size_t)n_slices * cx->N);
             }
         }
         for (int view = 0; view < 2; view++) {
@@ -1068,16 +1051,18 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
             G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
             G.cost = V.cost; G.aup = V.aup;
             G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
-            G.bdisp = bdisp[2 * c + view]; G.bbest = bbest[2 * c + view];
             G.bottom_list = V.bottom_list; G.bottom_desc = V.bottom_desc; G.bottom_count = V.counters + S3_CNT_NBOT;
         }
     }
-    std::vector<int4> bunits;   // k_agg_bottom: one work item per (view, 64-label slice)
+    // bottom subtrees (k_agg_bottom): one work item per (view, slice); exact dense mode without the aggregated-volume dump
+    static const int bottom_env = getenv("S3_AGG_BOTTOM") ? atoi(getenv("S3_AGG_BOTTOM")) : 0;
+    const bool bottom = ctx->P.exact != 0 && !ctx->P.keep_aggregated && (ctx->P.agg_bottom > 0 || (ctx->P.agg_bottom == 0 && bottom_env > 0));
+    std::vector<int4> bunits;
     if (bottom)
         for (int c = 0; c < nctx; c++)
             for (int view = 0; view < 2; view++)
                 if (views_mask & (1 << view))
-                    for (int s = 0; s < b_slices; s++) bunits.push_back(make_int4(2 * c + view, d0 + s * 64, s, 0));
+                    for (int s = 0; s < n_slices; s++) bunits.push_back(make_int4(2 * c + view, d0 + s * SW, s, 0));
     const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16, bbytes = bunits.size() * sizeof(int4);
     if (ctx->units_cap < ubytes + tbytes + bbytes) {
         if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
@@ -1105,7 +1090,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
     A.bottom = bottom;
-    A.b_slices = b_slices;
     A.bunits = reinterpret_cast<const int4*>(ubase + tbytes + ubytes);
     A.n_bunits = (int)bunits.size();
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
@@ -1126,8 +1110,13 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     cudaStream_t launch_stream = ctx->stream;
 #define AB_LAUNCH(DOWN_)                                                                                                          \
     do {                                                                                                                         \
-        if (nl % 64 == 0) S3_TRY(agg3_launch(ctx, k_agg_bottom<true, DOWN_>, ctx->num_sms, 32 * AB_WARPS, agg_bottom_smem(), 1, ctx->stream, A));   \
-        else S3_TRY(agg3_launch(ctx, k_agg_bottom<false, DOWN_>, ctx->num_sms, 32 * AB_WARPS, agg_bottom_smem(), 1, ctx->stream, A));              \
+        if (NH == 2) {                                                                                                           \
+            if (full) S3_TRY(agg3_launch(ctx, k_agg_bottom<2, true, DOWN_, 6>, ctx->num_sms, 32 * 6, agg_bottom_smem<2, 6>(), 1, ctx->stream, A));   \
+            else S3_TRY(agg3_launch(ctx, k_agg_bottom<2, false, DOWN_, 6>, ctx->num_sms, 32 * 6, agg_bottom_smem<2, 6>(), 1, ctx->stream, A));       \
+        } else {                                                                                                                 \
+            if (full) S3_TRY(agg3_launch(ctx, k_agg_bottom<1, true, DOWN_, 12>, ctx->num_sms, 32 * 12, agg_bottom_smem<1, 12>(), 1, ctx->stream, A)); \
+            else S3_TRY(agg3_launch(ctx, k_agg_bottom<1, false, DOWN_, 12>, ctx->num_sms, 32 * 12, agg_bottom_smem<1, 12>(), 1, ctx->stream, A));     \
+        }                                                                                                                        \
     } while (0)
     if (bottom) AB_LAUNCH(false);  // leaf->root sums of the bottom subtrees: their roots' rows feed the walk
 #define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, CL_, BOT_, GRID_, THREADS_)                                                \
@@ -1174,13 +1163,12 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
 #undef A3_DISPATCH
 #undef A3_LAUNCH
 #undef A3_LAUNCH_T
-    if (n_slices > 1 || b_slices > 1) {
+    if (n_slices > 1) {
         for (int c = 0; c < nctx; c++)
             for (int view = 0; view < 2; view++) {
                 if (!(views_mask & (1 << view))) continue;
                 View& V = ctxs[c]->v[view];
-                k_wta_finish3<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, n_slices, b_slices, bottom ? 1 : 0, V.node_dn, pdisp[2 * c + view], pbest[2 * c + view],
-                                                                             bdisp[2 * c + view], bbest[2 * c + view], V.disp_i, V.best);
+                k_wta_finish3<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->N, n_slices, V.node_dn, pdisp[2 * c + view], pbest[2 * c + view], V.disp_i, V.best);
                 S3_LAUNCH_CHECK();
             }
     }

@@ -814,14 +814,8 @@ __global__ void k_subtree_flags(int N, const uint8_t* __restrict__ sub, const in
             if (lane >= o) pre += u;
         }
         const int total = __shfl_sync(0xffffffffu, pre, 31);
-        // ONE 64-bit atomic hands out the list slots (low word) and the descriptor run (high word) together, so that the
-        // list is in the order of the descriptor array: consecutive subtrees are consecutive runs (k_agg_bottom batches them)
         int slot0 = 0, desc0 = 0;
-        if (lane == 0) {
-            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(count), ((unsigned long long)total << 32) | (unsigned)__popc(bal));
-            slot0 = (int)(unsigned)old;
-            desc0 = (int)(old >> 32);
-        }
+        if (lane == 0) { slot0 = atomicAdd(count, __popc(bal)); desc0 = atomicAdd(count + 1, total); }
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
         desc0 = __shfl_sync(0xffffffffu, desc0, 0);
         if (root) list[slot0 + __popc(bal & ((1u << lane) - 1))] = make_int4(v, desc0 + pre - size, size, 0);
@@ -829,8 +823,7 @@ __global__ void k_subtree_flags(int N, const uint8_t* __restrict__ sub, const in
 }
 // Descriptors of a bottom subtree: its nodes in BFS order (level ranges), each with everything the bottom kernels need,
 // so that they read ONE contiguous run per subtree instead of chasing records:
-//   d0 = {node, pixel, children | first child's local index << 3 | parent's local index << 9 | weight to the parent << 16
-//         | own local index << 26, cw01}
+//   d0 = {node, pixel, children | first child's local index << 3 | parent's local index << 9 | weight to the parent << 16, cw01}
 //   d1 = {cw23, parent node (global), 0, 0}
 __global__ void k_bottom_desc(const int* __restrict__ count, const int4* __restrict__ list, const NodeUp* __restrict__ node_up,
                               const int4* __restrict__ node_dn, int4* __restrict__ desc) {
@@ -850,7 +843,7 @@ __global__ void k_bottom_desc(const int* __restrict__ count, const int4* __restr
             const int i = off + g - lo;
             const int cl0 = cc ? off + n_here + nu.child_begin - nlo : 0;
             const int pl = g == e.x ? 0 : poff + nd.x - plo;
-            out[2 * i] = make_int4(g, nd.w, (int)((unsigned)cc | ((unsigned)cl0 << 3) | ((unsigned)pl << 9) | ((unsigned)(nd.y & S3_NDY_W_MASK) << 16) | ((unsigned)i << 26)), (int)nu.cw01);
+            out[2 * i] = make_int4(g, nd.w, cc | (cl0 << 3) | (pl << 9) | ((nd.y & S3_NDY_W_MASK) << 16), (int)nu.cw01);
             out[2 * i + 1] = make_int4((int)nu.cw23, nd.x, 0, 0);
         }
         plo = lo; poff = off;

@@ -19,7 +19,7 @@
 // Bottom subtrees (aggregate3.cu: k_agg_bottom): a node whose whole subtree has at most S3_BOTTOM_M nodes is never walked
 // by the dataflow kernel; its subtree is aggregated on chip by one warp, twice (leaf->root sums for the parent, then
 // again for the way down), so its running sums never travel to HBM.  Flags written by forest.cu: k_subtree_flags.
-#define S3_BOTTOM_M 16
+#define S3_BOTTOM_M 32
 #define S3_NU_BOTTOM 0x200          // NodeUp.child_count: the node lies in a bottom subtree
 #define S3_NU_BOTCHILD_SHIFT 12     // bits 12..15: child j is the root of a bottom subtree (set on top nodes only)
 #define S3_NU_NEXTBOT_SHIFT 16      // bits 16..18: node v-16 / v-32 / v-256 of the same tree is a bottom node (the walk's next node)
@@ -165,7 +165,7 @@ struct s3dmst_ctx {
 };
 
 #define S3_MAX_ROUNDS 65536
-#define S3_CNT_NBOT (S3_MAX_ROUNDS - 48)   // View::counters slots (8-byte aligned pair): number of bottom subtrees, [+1] descriptors handed out
+#define S3_CNT_NBOT (S3_MAX_ROUNDS - 48)   // View::counters slots: number of bottom subtrees, [+1] descriptors handed out
 #define S3_FH_MAX_VIEWS 16        // views (2 per frame) one forest-kernel launch serves
 #define S3_FH_ROUNDS 8192         // round cap of the forest kernel (per-round counters)
 #define S3_FH_MAX_CTAS 256        // upper bound on the cooperative grid of the forest kernel
