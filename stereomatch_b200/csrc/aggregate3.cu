@@ -59,8 +59,7 @@ struct Agg3View {
     double* best;
     int32_t* pdisp;   // [slice][node] partial results otherwise
     double* pbest;
-    const int4* bottom_list;      // the view's bottom subtrees {root, first descriptor, nodes} (forest.cu: k_subtree_flags), *bottom_count of them
-    const int4* bottom_desc;      // their node descriptors (forest.cu: k_bottom_desc)
+    const uint32_t* bottom_list;  // roots of the view's bottom subtrees (forest.cu: k_subtree_flags), *bottom_count of them
     const int* bottom_count;
     // proposal mode with the plane cost (params.pms_cost_mode = 1): this view's and the other view's image and gradients
     const uint8_t* img_self;
@@ -255,7 +254,7 @@ template <> struct A3T<float> {
 // nodes closer than NEAR x CL.  Progress words and ring rows of other CTAs are read through distributed shared memory
 // (mapa + ld.acquire.cluster / ld.shared::cluster), published with st.release.cluster; the far path through L2 is the
 // same (the release is cluster scope, so global stores before it are visible to the other SMs of the cluster).
-template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS, int CL, bool BOT = false>
+template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS, int CL>
 __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3Args A) {
     static_assert(CL == 1 || BIG, "a cluster walks a tree with 32 warps per CTA");
     static_assert(CL == 1 || CL == 2 || CL == 4 || CL == 8, "portable cluster sizes");
@@ -276,8 +275,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     const int gw = w * CL + (int)crank;                             // this warp's position in the deal
 
     constexpr int NB_IDX = CL > 1 ? 2 : (BIG ? 1 : 0);              // which "the walk's next node is a bottom node" bit applies: 16 / 32 / 256 warps
-    constexpr bool bot = BOT;                                        // bottom subtrees are k_agg_bottom's: the walk passes over them
-    static_assert(!(BOT && PMS), "bottom subtrees are a dense-mode path");
+    const bool bot = !PMS && A.bottom;
     const int4 unit = A.units[A.unit0 + blockIdx.x / CL];
     const Agg3View V = A.views[unit.x];
     const int t = unit.y, slice = unit.w;
@@ -760,10 +758,9 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 // running sum (20 bytes), and no hand-over between warps at all.  Every sum is formed by the same operations in the same
 // order as in the walk (children in reverse BFS order, then the node's own cost; w * A[parent] + (1 - w^2) * A_up), so
 // the results are bit-identical.
-// The forest stage hands every subtree over as one contiguous run of node descriptors (forest.cu: k_bottom_desc: BFS
-// order, local indices of the children and of the parent, weights, pixel), and the cost rows of the whole subtree are
-// fetched at once with cp.async.  Lanes own label pairs, as in the walk: a lane only ever touches its own columns of the
-// shared rows, so the passes need no synchronisation inside the warp.
+// A subtree is found from its root alone: in BFS order its nodes at depth k are one index range (forest.cu:
+// k_subtree_size).  Lanes own label pairs, as in the walk: a lane only ever touches its own columns of the shared rows,
+// so the passes need no synchronisation inside the warp.
 template <int NH, bool FULL, bool DOWN, int WPB>
 __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -771,13 +768,17 @@ __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
     using TT = A3T<double>;
     constexpr uint32_t HB = 64 * sizeof(double), ROWB = NH * HB;
     constexpr uint32_t LUTB = ((2 * S3_NUM_W * sizeof(double) + 15) / 16) * 16;
-    constexpr uint32_t WB = M * ROWB + M * 32;   // the subtree's rows and descriptors
+    constexpr uint32_t WB = M * ROWB + M * 16 * 2 + M * 4 + (M + 2) * 4 * 2 + 16;   // rows, two records per node, node ids, level tables
     double* s_w = reinterpret_cast<double*>(s_raw);
     double* s_w2 = s_w + S3_NUM_W;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    unsigned char* wb = s_raw + LUTB + (size_t)w * WB;
+    unsigned char* wb = s_raw + LUTB + (size_t)w * ((WB + 15) / 16 * 16);
     const uint32_t rows_a = a3_smem(wb) + (uint32_t)sizeof(double2) * lane;   // this lane's column of the subtree's rows
-    int4* s_d = reinterpret_cast<int4*>(wb + M * ROWB);                       // [M][2] descriptors (forest.cu: k_bottom_desc)
+    int4* s_up = reinterpret_cast<int4*>(wb + M * ROWB);
+    int4* s_dn = s_up + M;
+    int* s_gid = reinterpret_cast<int*>(s_dn + M);
+    int* s_lo = s_gid + M;            // first node of the subtree's level k
+    int* s_off = s_lo + (M + 2);      // local index of that node
     for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
         s_w[i] = reinterpret_cast<const double*>(A.lut_w)[i];
         s_w2[i] = reinterpret_cast<const double*>(A.lut_w2)[i];
@@ -796,36 +797,63 @@ __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
 #pragma unroll
         for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;
         for (int it = gwarp; it < nb; it += nwarps) {
-            const int4 e = __ldg(V.bottom_list + it);   // {root, first descriptor, nodes}
-            const int n = e.z;
-            __syncwarp();  // the previous subtree is done with the descriptors
-            if (lane < n) {
-                const int4* dp = V.bottom_desc + 2 * ((size_t)e.y + lane);
-                s_d[2 * lane] = __ldg(dp);
-                s_d[2 * lane + 1] = __ldg(dp + 1);
+            const int r = (int)V.bottom_list[it];
+            // ---- the subtree: level ranges (every lane walks them; lane 0 keeps the table)
+            int lo = r, hi = r + 1, n = 1, L = 0;
+            __syncwarp();  // the previous subtree is done with the tables
+            if (lane == 0) { s_lo[0] = r; s_off[0] = 0; }
+            while (true) {
+                const int nlo = __ldg(&V.node_up[lo].child_begin);
+                const int4 last = __ldg(reinterpret_cast<const int4*>(V.node_up + hi - 1));
+                const int nhi = last.x + (last.y & 7);
+                if (nhi <= nlo) break;
+                L++;
+                if (lane == 0) { s_lo[L] = nlo; s_off[L] = n; }
+                n += nhi - nlo;
+                lo = nlo; hi = nhi;
+            }
+            if (lane == 0) s_off[L + 1] = n;
+            __syncwarp();
+            // ---- records of the nodes (lane i, i + 32, ...)
+            for (int i = lane; i < n; i += 32) {
+                int k = 0;
+                while (s_off[k + 1] <= i) k++;
+                const int g = s_lo[k] + i - s_off[k];
+                s_gid[i] = g;
+                s_up[i] = __ldg(reinterpret_cast<const int4*>(V.node_up + g));
+                s_dn[i] = __ldg(V.node_dn + g);
             }
             __syncwarp();
-            // ---- cost rows -> shared rows: every row of the subtree in flight at once (cp.async: no registers held)
-            for (int i = 0; i < n; i++) {
-                const char* cp = reinterpret_cast<const char*>(V.cost + (size_t)s_d[2 * i].x * Dp + l0 + 2 * lane);
+            // ---- cost rows -> shared rows (as doubles: the conversion is exact), four nodes in flight per lane
+            for (int i0 = 0; i0 < n; i0 += 4) {
+                float2 c[4][NH];
 #pragma unroll
-                for (int h = 0; h < NH; h++)
-                    if (act[h]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rows_a + (uint32_t)i * ROWB + h * HB), "l"(cp + h * 256) : "memory");
+                for (int u = 0; u < 4; u++)
+                    if (i0 + u < n) {
+                        const char* cp = reinterpret_cast<const char*>(V.cost + (size_t)s_gid[i0 + u] * Dp + l0 + 2 * lane);
+#pragma unroll
+                        for (int h = 0; h < NH; h++) c[u][h] = act[h] ? *reinterpret_cast<const float2*>(cp + h * 256) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i0 + u < n) {
+#pragma unroll
+                        for (int h = 0; h < NH; h++) TT::sts2(rows_a + (uint32_t)(i0 + u) * ROWB + h * HB, make_double2((double)c[u][h].x, (double)c[u][h].y));
+                    }
             }
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-            // ---- leaf -> root inside the subtree: (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost (Stereo3DMST.cpp:125-137);
-            // a cell holds the node's cost (fp32, as copied) until the node is reached, then its sum
-            for (int i = n - 1; i >= 0; i--) {
-                const int4 d0 = s_d[2 * i];
-                const int cc = d0.z & 7, cl0 = (d0.z >> 3) & 63;
-                const uint32_t cw23 = (uint32_t)s_d[2 * i + 1].x;
+            // ---- leaf -> root inside the subtree: (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost (Stereo3DMST.cpp:125-137)
+            for (int i = n - 1, k = L; i >= 0; i--) {
+                while (i < s_off[k]) k--;
+                const int4 nu = s_up[i];
+                const int cc = nu.y & 7;
                 double2 acc[NH];
 #pragma unroll
                 for (int h = 0; h < NH; h++) acc[h] = make_double2(0.0, 0.0);
+                const int cl0 = cc ? s_off[k + 1] + nu.x - s_lo[k + 1] : 0;   // local index of the first child
 #pragma unroll
                 for (int j = 3; j >= 0; j--)
                     if (cc > j) {
-                        const uint32_t iw = ((j & 2) ? cw23 : (uint32_t)d0.w) >> ((j & 1) * 16) & 0xFFFFu;
+                        const uint32_t iw = ((j & 2) ? (uint32_t)nu.w : (uint32_t)nu.z) >> ((j & 1) * 16) & 0xFFFFu;
                         const double wk = TT::ldsw(w_a + 8u * iw);
                         const uint32_t ra = rows_a + (uint32_t)(cl0 + j) * ROWB;
 #pragma unroll
@@ -838,20 +866,19 @@ __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
                 const uint32_t sa = rows_a + (uint32_t)i * ROWB;
 #pragma unroll
                 for (int h = 0; h < NH; h++) {
-                    float2 cf = make_float2(0.f, 0.f);
-                    if (act[h]) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf.x), "=f"(cf.y) : "r"(sa + h * HB) : "memory");
-                    acc[h].x = TT::add(acc[h].x, (double)cf.x);
-                    acc[h].y = TT::add(acc[h].y, (double)cf.y);
+                    const double2 cf = TT::lds2(sa + h * HB);
+                    acc[h].x = TT::add(acc[h].x, cf.x);
+                    acc[h].y = TT::add(acc[h].y, cf.y);
                     TT::sts2(sa + h * HB, acc[h]);
                 }
             }
+            double* const arow = V.aup + (size_t)r * Dp + l0 + 2 * lane;
             if constexpr (!DOWN) {  // the subtree root's row: read by its parent in the walk
-                const int r = e.x;
-                if (s_d[1].y != r) {
-                    char* arow = reinterpret_cast<char*>(V.aup + (size_t)r * Dp + l0 + 2 * lane);
+                const int4 nd0 = s_dn[0];
+                if (nd0.x != r) {
 #pragma unroll
                     for (int h = 0; h < NH; h++)
-                        if (act[h]) *reinterpret_cast<double2*>(arow + h * HB) = TT::lds2(rows_a + h * HB);
+                        if (act[h]) *reinterpret_cast<double2*>(reinterpret_cast<char*>(arow) + h * HB) = TT::lds2(rows_a + h * HB);
                 }
             } else {
                 // ---- root -> leaf: A[c] = w * A[parent] + (1 - w*w) * A_up[c] (Stereo3DMST.cpp:155), WTA per node
@@ -876,23 +903,23 @@ __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
                         }
                     }
                 };
-                for (int i = 0; i < n; i++) {
-                    const int4 d0 = s_d[2 * i];
-                    const int pg = s_d[2 * i + 1].y;   // parent node (global)
+                for (int i = 0, k = 0; i < n; i++) {
+                    while (i >= s_off[k + 1]) k++;
+                    const int4 nd = s_dn[i];
                     const uint32_t sa = rows_a + (uint32_t)i * ROWB;
                     double2 fin[NH];
 #pragma unroll
                     for (int h = 0; h < NH; h++) fin[h] = TT::lds2(sa + h * HB);
-                    if (pg != d0.x) {
-                        const uint32_t iw = ((uint32_t)d0.z >> 16) & 0x3FFu;
+                    if (nd.x != s_gid[i]) {
+                        const uint32_t iw = (uint32_t)nd.y & S3_NDY_W_MASK;
                         const double wp = TT::ldsw(w_a + 8u * iw), wq = TT::ldsw(w_a + 8u * (S3_NUM_W + iw));
                         double2 pv[NH];
                         if (i == 0) {  // the parent is a node of the walk: its final row is in HBM
-                            const char* gp = reinterpret_cast<const char*>(V.aup + (size_t)pg * Dp + l0 + 2 * lane);
+                            const char* gp = reinterpret_cast<const char*>(V.aup + (size_t)nd.x * Dp + l0 + 2 * lane);
 #pragma unroll
                             for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : make_double2(0.0, 0.0);
                         } else {
-                            const uint32_t pa = rows_a + (uint32_t)((d0.z >> 9) & 63) * ROWB;
+                            const uint32_t pa = rows_a + (uint32_t)(s_off[k - 1] + nd.x - s_lo[k - 1]) * ROWB;
 #pragma unroll
                             for (int h = 0; h < NH; h++) pv[h] = TT::lds2(pa + h * HB);
                         }
@@ -903,7 +930,7 @@ __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
                             TT::sts2(sa + h * HB, fin[h]);
                         }
                     }
-                    wta(fin, d0.x, d0.y);
+                    wta(fin, s_gid[i], nd.w);
                 }
             }
         }
@@ -912,7 +939,8 @@ __global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
 template <int NH, int WPB>
 static size_t agg_bottom_smem() {
     const size_t lut = ((2 * S3_NUM_W * sizeof(double) + 15) / 16) * 16;
-    return lut + (size_t)WPB * (S3_BOTTOM_M * NH * 512 + S3_BOTTOM_M * 32);
+    const size_t wb = (size_t)S3_BOTTOM_M * NH * 512 + S3_BOTTOM_M * 16 * 2 + S3_BOTTOM_M * 4 + (S3_BOTTOM_M + 2) * 4 * 2 + 16;
+    return lut + WPB * ((wb + 15) / 16 * 16);
 }
 
 static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
@@ -1051,7 +1079,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
             G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
             G.cost = V.cost; G.aup = V.aup;
             G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
-            G.bottom_list = V.bottom_list; G.bottom_desc = V.bottom_desc; G.bottom_count = V.counters + S3_CNT_NBOT;
+            G.bottom_list = V.bottom_list; G.bottom_count = V.counters + S3_CNT_NBOT;
         }
     }
     // bottom subtrees (k_agg_bottom): one work item per (view, slice); exact dense mode without the aggregated-volume dump
@@ -1119,16 +1147,15 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         }                                                                                                                        \
     } while (0)
     if (bottom) AB_LAUNCH(false);  // leaf->root sums of the bottom subtrees: their roots' rows feed the walk
-#define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, CL_, BOT_, GRID_, THREADS_)                                                \
+#define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                      \
     do {                                                                                                                       \
         const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(T_));                                                              \
-        S3_TRY(agg3_launch(ctx, k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false, CL_, BOT_>, GRID_, THREADS_, smem, CL_, launch_stream, A)); \
+        S3_TRY(agg3_launch(ctx, k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false, CL_>, GRID_, THREADS_, smem, CL_, launch_stream, A)); \
     } while (0)
 #define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                            \
     do {                                                                                                                       \
-        if (bottom) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, CL_, true, GRID_, THREADS_);                              \
-        else if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, CL_, false, GRID_, THREADS_);                         \
-        else A3_LAUNCH_T(float, NH_, FULL_, BIG_, (R_) * 2, NEAR_, CL_, false, GRID_, THREADS_);                               \
+        if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_);                                     \
+        else A3_LAUNCH_T(float, NH_, FULL_, BIG_, (R_) * 2, NEAR_, CL_, GRID_, THREADS_);                                      \
     } while (0)
     // ring geometry: rows R and hand-over distance NEAR (>= S3_AGG_NEAR, the distance the forest stage flags nodes by).
     // A warp may not run more than (R - NEAR) / W rounds ahead of the slowest one, so R - NEAR >= ~2 W.

@@ -80,7 +80,7 @@ static void free_view(View& V) {
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
     DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
-    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits); DFREE(V.bottom_list); DFREE(V.bottom_desc);
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits);
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
@@ -106,7 +106,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     S3_CUDA(dalloc(&V.tree_size, n)); S3_CUDA(dalloc(&V.tree_rootpix, n));
     S3_CUDA(dalloc(&V.tree_start, n + 1)); S3_CUDA(dalloc(&V.tree_depth, n)); S3_CUDA(dalloc(&V.unit_tree, n));
     S3_CUDA(dalloc(&V.node_pixel, n)); S3_CUDA(dalloc(&V.pixel_node, n)); S3_CUDA(dalloc(&V.parent, n));
-    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.leaf_bits, n / 32 + 2)); S3_CUDA(dalloc(&V.bottom_list, n)); S3_CUDA(dalloc(&V.bottom_desc, 2 * n));
+    S3_CUDA(dalloc(&V.level, n)); S3_CUDA(dalloc(&V.pw, n)); S3_CUDA(dalloc(&V.node_up, n)); S3_CUDA(dalloc(&V.node_dn, n)); S3_CUDA(dalloc(&V.leaf_bits, n / 32 + 2));
     S3_CUDA(dalloc(&V.lvl_start, 2 * n + 2));
     S3_CUDA(dalloc(&V.disp_i, n)); S3_CUDA(dalloc(&V.best, n)); S3_CUDA(dalloc(&V.abc, 3 * n)); S3_CUDA(dalloc(&V.min_cost, n));
     S3_CUDA(dalloc(&V.disp_f, n)); S3_CUDA(dalloc(&V.lr_mask, n));

@@ -774,16 +774,14 @@ __global__ void k_subtree_size(int N, const NodeUp* __restrict__ node_up, uint8_
     sub[v] = (uint8_t)min(cnt, S3_BOTTOM_M + 1);
 }
 __global__ void k_subtree_flags(int N, const uint8_t* __restrict__ sub, const int* __restrict__ tree_id, const int* __restrict__ tree_start,
-                                NodeUp* __restrict__ node_up, int4* __restrict__ node_dn, int4* __restrict__ list, int* __restrict__ count) {
+                                NodeUp* __restrict__ node_up, int4* __restrict__ node_dn, uint32_t* __restrict__ list, int* __restrict__ count) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     bool root = false;
-    int size = 0;
     if (v < N) {
         const int4 nd = node_dn[v];
         const int t = tree_id[nd.w];
         const int base = tree_start[t], end = tree_start[t + 1];
-        size = sub[v];
-        const bool bot = size <= S3_BOTTOM_M;
+        const bool bot = sub[v] <= S3_BOTTOM_M;
         root = bot && (nd.x == v || sub[nd.x] > S3_BOTTOM_M);
         NodeUp nu = node_up[v];
         const int cc = nu.child_count & 7;
@@ -804,63 +802,24 @@ __global__ void k_subtree_flags(int N, const uint8_t* __restrict__ sub, const in
         reinterpret_cast<int*>(node_up + v)[1] = (int)((unsigned)nu.child_count | fu);
         reinterpret_cast<int*>(node_dn + v)[1] = (int)((unsigned)nd.y | fd);
     }
-    // the roots take a list slot and a run of descriptors each: one pair of atomics per warp
     const unsigned bal = __ballot_sync(0xffffffffu, root);
     if (bal) {
         const int lane = threadIdx.x & 31;
-        int pre = root ? size : 0;  // inclusive scan of the sizes over the warp
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += u;
-        }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
-        int slot0 = 0, desc0 = 0;
-        if (lane == 0) { slot0 = atomicAdd(count, __popc(bal)); desc0 = atomicAdd(count + 1, total); }
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        desc0 = __shfl_sync(0xffffffffu, desc0, 0);
-        if (root) list[slot0 + __popc(bal & ((1u << lane) - 1))] = make_int4(v, desc0 + pre - size, size, 0);
-    }
-}
-// Descriptors of a bottom subtree: its nodes in BFS order (level ranges), each with everything the bottom kernels need,
-// so that they read ONE contiguous run per subtree instead of chasing records:
-//   d0 = {node, pixel, children | first child's local index << 3 | parent's local index << 9 | weight to the parent << 16, cw01}
-//   d1 = {cw23, parent node (global), 0, 0}
-__global__ void k_bottom_desc(const int* __restrict__ count, const int4* __restrict__ list, const NodeUp* __restrict__ node_up,
-                              const int4* __restrict__ node_dn, int4* __restrict__ desc) {
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= *count) return;
-    const int4 e = list[it];
-    int4* out = desc + 2 * (size_t)e.y;
-    int lo = e.x, hi = e.x + 1, off = 0, plo = e.x, poff = 0;   // this level's range and local offset, the parent level's
-    while (hi > lo) {
-        const int n_here = hi - lo;
-        int nlo = node_up[lo].child_begin, nhi = nlo;
-        for (int g = lo; g < hi; g++) {
-            const NodeUp nu = node_up[g];
-            const int4 nd = node_dn[g];
-            const int cc = nu.child_count & 7;
-            nhi = nu.child_begin + cc;
-            const int i = off + g - lo;
-            const int cl0 = cc ? off + n_here + nu.child_begin - nlo : 0;
-            const int pl = g == e.x ? 0 : poff + nd.x - plo;
-            out[2 * i] = make_int4(g, nd.w, cc | (cl0 << 3) | (pl << 9) | ((nd.y & S3_NDY_W_MASK) << 16), (int)nu.cw01);
-            out[2 * i + 1] = make_int4((int)nu.cw23, nd.x, 0, 0);
-        }
-        plo = lo; poff = off;
-        off += n_here;
-        lo = nlo; hi = nhi;
+        int off = 0;
+        if (lane == 0) off = atomicAdd(count, __popc(bal));
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (root) list[off + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v;
     }
 }
 
 int s3_forest_bottom(s3dmst_ctx* ctx, int view) {
     View& V = ctx->v[view];
     const int N = ctx->N, TB = 256;
-    S3_CUDA(cudaMemsetAsync(V.counters + S3_CNT_NBOT, 0, 2 * sizeof(int), ctx->stream));
+    V.bottom_list = V.bfs_front;
+    S3_CUDA(cudaMemsetAsync(V.counters + S3_CNT_NBOT, 0, sizeof(int), ctx->stream));
     k_subtree_size<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_up, V.e_flag);
     S3_LAUNCH_CHECK();
     k_subtree_flags<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.e_flag, V.tree_id, V.tree_start, V.node_up, V.node_dn, V.bottom_list, V.counters + S3_CNT_NBOT);
-    S3_LAUNCH_CHECK();
-    k_bottom_desc<<<(N + 127) / 128, 128, 0, ctx->stream>>>(V.counters + S3_CNT_NBOT, V.bottom_list, V.node_up, V.node_dn, V.bottom_desc);
     S3_LAUNCH_CHECK();
     return 0;
 }

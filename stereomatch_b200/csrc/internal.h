@@ -78,8 +78,7 @@ struct View {
     uint16_t* pw = nullptr;     // [N]
     NodeUp* node_up = nullptr;  // [N]
     int4* node_dn = nullptr;    // [N] {parent, parent weight, level | flags, pixel}: the root->leaf pass record
-    int4* bottom_list = nullptr;      // [N] one entry per bottom subtree: {root node, first descriptor, nodes, 0}; count at counters[S3_CNT_NBOT]
-    int4* bottom_desc = nullptr;      // [2N] two int4 per node of a bottom subtree, subtree after subtree, BFS order inside (forest.cu: k_bottom_desc)
+    uint32_t* bottom_list = nullptr;  // roots of the bottom subtrees (aliases bfs_front: free once the BFS is done); count at counters[CNT_NBOT]
     uint32_t* leaf_bits = nullptr;  // [N/32 + 1] bit v = node v is a leaf (prefetch target selection on the way down)
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
     // tree adjacency graph (Stereo3DMST.cpp:377-384) as a device CSR, built lazily (proposal generation, parity dumps)
@@ -165,7 +164,7 @@ struct s3dmst_ctx {
 };
 
 #define S3_MAX_ROUNDS 65536
-#define S3_CNT_NBOT (S3_MAX_ROUNDS - 48)   // View::counters slots: number of bottom subtrees, [+1] descriptors handed out
+#define S3_CNT_NBOT (S3_MAX_ROUNDS - 48)   // View::counters slot: number of bottom-subtree roots
 #define S3_FH_MAX_VIEWS 16        // views (2 per frame) one forest-kernel launch serves
 #define S3_FH_ROUNDS 8192         // round cap of the forest kernel (per-round counters)
 #define S3_FH_MAX_CTAS 256        // upper bound on the cooperative grid of the forest kernel
