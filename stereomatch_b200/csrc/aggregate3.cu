@@ -59,8 +59,6 @@ struct Agg3View {
     double* best;
     int32_t* pdisp;   // [slice][node] partial results otherwise
     double* pbest;
-    const uint32_t* bottom_list;  // roots of the view's bottom subtrees (forest.cu: k_subtree_flags), *bottom_count of them
-    const int* bottom_count;
     // proposal mode with the plane cost (params.pms_cost_mode = 1): this view's and the other view's image and gradients
     const uint8_t* img_self;
     const uint8_t* img_other;
@@ -86,12 +84,6 @@ struct Agg3Args {
     float oob;             // label cost outside [0, D)
     // proposal generation inside the kernel (s3dmst_pms_iterate): after a tree's listed proposals (its neighbours' labels),
     // the refinement ladder around a random pixel of the tree itself
-    // dense mode with bottom subtrees: the nodes flagged S3_NU_BOTTOM are aggregated on chip by k_agg_bottom (before and
-    // after this kernel); the walk passes over them, reads a bottom child's leaf->root row from HBM and leaves the final
-    // row of a node with bottom children there
-    int bottom;
-    const int4* bunits;    // k_agg_bottom: {view, first label, slice index, 0} per (view, slice) of the launch
-    int n_bunits;
     int cost_mode, view, img_h;            // proposal mode: 1 = plane cost from the images (hd_math.h: s3_plane_cost)
     float pm_alpha, pm_tau_c, pm_tau_g, pm_scale;
     int gen;
@@ -274,8 +266,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     const uint32_t crank = CL > 1 ? a3_crank() : 0u;
     const int gw = w * CL + (int)crank;                             // this warp's position in the deal
 
-    constexpr int NB_IDX = CL > 1 ? 2 : (BIG ? 1 : 0);              // which "the walk's next node is a bottom node" bit applies: 16 / 32 / 256 warps
-    const bool bot = !PMS && A.bottom;
     const int4 unit = A.units[A.unit0 + blockIdx.x / CL];
     const Agg3View V = A.views[unit.x];
     const int t = unit.y, slice = unit.w;
@@ -416,7 +406,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             nu = *reinterpret_cast<const int4*>(nup_p);
             if constexpr (CL > 1) par = V.node_dn[v].x;
             if constexpr (PMS) cf[0] = pms_cost(v);
-            else if (!(bot && (nu.y & S3_NU_BOTTOM))) {
+            else {
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p + h * 256);
@@ -447,24 +437,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             n_nodes++;
 #endif
             const int vn = v - WT;
-            if (bot && (nu.y & S3_NU_BOTTOM)) {  // a bottom node: k_agg_bottom's; only the progress word moves on
-                const bool nxt_bot = (nu.y >> (S3_NU_NEXTBOT_SHIFT + NB_IDX)) & 1;
-                if (lane == 0) publish(v);
-                if (vn >= base) {
-                    nu = *reinterpret_cast<const int4*>(nup_p - (long long)WT * 16);
-                    if constexpr (CL > 1) par = V.node_dn[vn].x;
-                    if (!nxt_bot) {
-#pragma unroll
-                        for (int h = 0; h < NH; h++)
-                            if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
-                    }
-                }
-                nup_p -= (long long)WT * 16;
-                cost_p -= strideC;
-                aup_p -= strideA;
-                v = vn;
-                continue;
-            }
             const int cc = nu.y & 7, cb = nu.x;
             if constexpr (CL > 1) guard_up();  // a round trip through the cluster: taken before the wait for the children, not after it
             T2 acc[NH];
@@ -478,13 +450,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         const uint32_t pa = prog_of(top - c);                                                                        \
         A3_CLK(q_pre);                                                                                               \
         T2 cv[NH];                                                                                              \
-        if (bot && ((nu.y >> (S3_NU_BOTCHILD_SHIFT + K)) & 1)) {                                                     \
-            /* the root of a bottom subtree: its leaf->root row was left in HBM by k_agg_bottom before this kernel */ \
-            const char* gp = aup_lane0 + (size_t)c * DA * sizeof(T);                                                 \
-            _Pragma("unroll") for (int h = 0; h < NH; h++)                                                           \
-                cv[h] = act[h] ? TT::ldcg2(gp + h * HB) : TT::zero2();                                               \
-            A3_CLK(q_poll);                                                                                          \
-        } else if (CL > 1 && c - v < NEAR_E) {                                                                       \
+        if (CL > 1 && c - v < NEAR_E) {                                                                              \
             /* another SM: the progress word and, right behind it, the row — ONE round trip through the cluster when */ \
             /* the child is done (requests of a warp to one CTA are serviced in order; a row fetched too early is    */ \
             /* simply fetched again) */                                                                              \
@@ -545,18 +511,17 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             // has in flight, and a load still on its way from HBM would put its latency on every level of the tree.
             const bool store_late = !far_parent;
             if (vn >= base) {  // next node of this warp: record and cost row
-                const bool nxt_bot = bot && ((nu.y >> (S3_NU_NEXTBOT_SHIFT + NB_IDX)) & 1);  // (its cost row is not this kernel's to read)
                 nu = *reinterpret_cast<const int4*>(nup_p - (long long)WT * 16);
                 if constexpr (CL > 1) par = V.node_dn[vn].x;
                 if constexpr (PMS) cf[0] = pms_cost(vn);
-                else if (!nxt_bot) {
+                else {
 #pragma unroll
                     for (int h = 0; h < NH; h++)
                         if (act[h]) cf[h] = *reinterpret_cast<const float2*>(cost_p - strideC + h * 256);
                 }
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
-            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base && !(PMS && A.cost_mode) && !bot)
+            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base && !(PMS && A.cost_mode))
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - (PMS ? 0 : 2 * lane * 4) - A3_PF * strideC + lane * 128));
             if (store_late) {  // read back on the way down
 #pragma unroll
@@ -592,11 +557,9 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         if (v < end) {
             nd = *reinterpret_cast<const int4*>(ndn_p);
             if constexpr (CL > 1) ch = *reinterpret_cast<const int2*>(V.node_up + v);
-            if (!(bot && (nd.y & S3_NDY_BOTTOM))) {
 #pragma unroll
-                for (int h = 0; h < NH; h++)  // (cluster: the row was written by another SM — read it from L2, never from this SM's L1)
-                    if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + h * HB) : *reinterpret_cast<const T2*>(aup_p + h * HB);
-            }
+            for (int h = 0; h < NH; h++)  // (cluster: the row was written by another SM — read it from L2, never from this SM's L1)
+                if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + h * HB) : *reinterpret_cast<const T2*>(aup_p + h * HB);
         } else if (lane == 0)
             publish(end);
         int guard_ok = base - 1;  // writing ring row v is known to be safe for every v <= guard_ok
@@ -645,30 +608,12 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         };
         while (v < end) {
             const int vn = v + WT;
-            if (bot && (nd.y & S3_NDY_BOTTOM)) {  // a bottom node: finished by k_agg_bottom after this kernel
-                const bool nxt_bot = (nd.y >> (S3_NDY_NEXTBOT_SHIFT + NB_IDX)) & 1;
-                if (lane == 0) publish(v);
-                if (vn < end) {
-                    nd = *reinterpret_cast<const int4*>(ndn_p + (long long)WT * 16);
-                    if constexpr (CL > 1) ch = *reinterpret_cast<const int2*>(V.node_up + vn);
-                    if (!nxt_bot) {
-#pragma unroll
-                        for (int h = 0; h < NH; h++)
-                            if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + strideA + h * HB) : *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
-                    }
-                }
-                ndn_p += (long long)WT * 16;
-                aup_p += strideA;
-                v = vn;
-                continue;
-            }
             const int p = nd.x;
             if constexpr (CL > 1) guard_dn();
             T2 fin[NH];
             if (p != v) {
                 // A[c] = w * A[parent] + (1 - w*w) * A_up[c]   (Stereo3DMST.cpp:155)
-                const uint32_t iw = (uint32_t)nd.y & S3_NDY_W_MASK;
-                const T wp = TT::ldsw(w_a + (uint32_t)sizeof(T) * iw), wq = TT::ldsw(w_a + (uint32_t)sizeof(T) * (S3_NUM_W + iw));
+                const T wp = TT::ldsw(w_a + (uint32_t)sizeof(T) * (uint32_t)nd.y), wq = TT::ldsw(w_a + (uint32_t)sizeof(T) * (uint32_t)(S3_NUM_W + nd.y));
 #pragma unroll
                 for (int h = 0; h < NH; h++) {  // the half that does not depend on the parent, before the wait
                     au[h].x = TT::mul(wq, au[h].x);
@@ -707,7 +652,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             }
             // children further than the rings reach read the final value from L2
             const bool far_child = CL > 1 ? ((ch.y & 7) > 0 && ch.x + (ch.y & 7) - 1 - v >= NEAR_E) : (bool)(nd.z & S3_ND_FAR);
-            if (far_child || (!PMS && A.keep) || (bot && (nd.y & S3_NDY_HASBOTTOM))) {  // (a bottom child's kernel reads the final row from HBM)
+            if (far_child || (!PMS && A.keep)) {
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (act[h]) *reinterpret_cast<T2*>(aup_p + h * HB) = fin[h];
@@ -724,16 +669,13 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             // next node's loads: after the publish (see the leaf->root pass), into the registers this node is done with
             const int pix = nd.w;
             if (vn < end) {
-                const bool nxt_bot = bot && ((nd.y >> (S3_NDY_NEXTBOT_SHIFT + NB_IDX)) & 1);
                 nd = *reinterpret_cast<const int4*>(ndn_p + (long long)WT * 16);
                 if constexpr (CL > 1) ch = *reinterpret_cast<const int2*>(V.node_up + vn);
-                if (!nxt_bot) {
 #pragma unroll
-                    for (int h = 0; h < NH; h++)
-                        if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + strideA + h * HB) : *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
-                }
+                for (int h = 0; h < NH; h++)
+                    if (act[h]) au[h] = CL > 1 ? TT::ldcg2(aup_p + strideA + h * HB) : *reinterpret_cast<const T2*>(aup_p + strideA + h * HB);
             }
-            if (lane < NH * (int)sizeof(T) / 2 && v + A3_PF * WT < end && !bot)
+            if (lane < NH * (int)sizeof(T) / 2 && v + A3_PF * WT < end)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(aup_p - 2 * lane * (int)sizeof(T) + A3_PF * strideA + lane * 128));
             // the WTA of this node runs while those loads are in flight and the next parent is still being computed
             wta(fin, v, pix);
@@ -745,202 +687,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     }  // passes
     // a CTA's shared memory must stay alive until no other CTA of the cluster can read it any more
     if constexpr (CL > 1) a3_cluster_sync();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Bottom subtrees.  A node whose whole subtree has at most S3_BOTTOM_M nodes (about four nodes in five on natural and
-// random-dot images alike) never enters the dataflow walk above: one warp aggregates its subtree on chip,
-//   DOWN = false (before the walk): leaf->root sums of the subtree in shared memory from the cost rows; only the subtree
-//                                   root's row goes to HBM, for its parent in the walk;
-//   DOWN = true  (after the walk):  the same sums again from the same cost rows, then root->leaf from the parent's final
-//                                   row (left in HBM by the walk) and the WTA;
-// so a bottom node costs two reads of its cost row (8 bytes per pixel-label) instead of cost + write + read of an fp64
-// running sum (20 bytes), and no hand-over between warps at all.  Every sum is formed by the same operations in the same
-// order as in the walk (children in reverse BFS order, then the node's own cost; w * A[parent] + (1 - w^2) * A_up), so
-// the results are bit-identical.
-// A subtree is found from its root alone: in BFS order its nodes at depth k are one index range (forest.cu:
-// k_subtree_size).  Lanes own label pairs, as in the walk: a lane only ever touches its own columns of the shared rows,
-// so the passes need no synchronisation inside the warp.
-template <int NH, bool FULL, bool DOWN, int WPB>
-__global__ void __launch_bounds__(32 * WPB, 1) k_agg_bottom(Agg3Args A) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    constexpr int M = S3_BOTTOM_M;
-    using TT = A3T<double>;
-    constexpr uint32_t HB = 64 * sizeof(double), ROWB = NH * HB;
-    constexpr uint32_t LUTB = ((2 * S3_NUM_W * sizeof(double) + 15) / 16) * 16;
-    constexpr uint32_t WB = M * ROWB + M * 16 * 2 + M * 4 + (M + 2) * 4 * 2 + 16;   // rows, two records per node, node ids, level tables
-    double* s_w = reinterpret_cast<double*>(s_raw);
-    double* s_w2 = s_w + S3_NUM_W;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    unsigned char* wb = s_raw + LUTB + (size_t)w * ((WB + 15) / 16 * 16);
-    const uint32_t rows_a = a3_smem(wb) + (uint32_t)sizeof(double2) * lane;   // this lane's column of the subtree's rows
-    int4* s_up = reinterpret_cast<int4*>(wb + M * ROWB);
-    int4* s_dn = s_up + M;
-    int* s_gid = reinterpret_cast<int*>(s_dn + M);
-    int* s_lo = s_gid + M;            // first node of the subtree's level k
-    int* s_off = s_lo + (M + 2);      // local index of that node
-    for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
-        s_w[i] = reinterpret_cast<const double*>(A.lut_w)[i];
-        s_w2[i] = reinterpret_cast<const double*>(A.lut_w2)[i];
-    }
-    __syncthreads();
-    const uint32_t w_a = a3_smem(s_w);
-    const int gwarp = blockIdx.x * WPB + w, nwarps = gridDim.x * WPB;
-    const size_t Dp = (size_t)A.Dp;
-
-    for (int bu = 0; bu < A.n_bunits; bu++) {
-        const int4 unit = A.bunits[bu];
-        const Agg3View V = A.views[unit.x];
-        const int l0 = unit.y, slice = unit.z;
-        const int nb = *V.bottom_count;
-        bool act[NH];
-#pragma unroll
-        for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;
-        for (int it = gwarp; it < nb; it += nwarps) {
-            const int r = (int)V.bottom_list[it];
-            // ---- the subtree: level ranges (every lane walks them; lane 0 keeps the table)
-            int lo = r, hi = r + 1, n = 1, L = 0;
-            __syncwarp();  // the previous subtree is done with the tables
-            if (lane == 0) { s_lo[0] = r; s_off[0] = 0; }
-            while (true) {
-                const int nlo = __ldg(&V.node_up[lo].child_begin);
-                const int4 last = __ldg(reinterpret_cast<const int4*>(V.node_up + hi - 1));
-                const int nhi = last.x + (last.y & 7);
-                if (nhi <= nlo) break;
-                L++;
-                if (lane == 0) { s_lo[L] = nlo; s_off[L] = n; }
-                n += nhi - nlo;
-                lo = nlo; hi = nhi;
-            }
-            if (lane == 0) s_off[L + 1] = n;
-            __syncwarp();
-            // ---- records of the nodes (lane i, i + 32, ...)
-            for (int i = lane; i < n; i += 32) {
-                int k = 0;
-                while (s_off[k + 1] <= i) k++;
-                const int g = s_lo[k] + i - s_off[k];
-                s_gid[i] = g;
-                s_up[i] = __ldg(reinterpret_cast<const int4*>(V.node_up + g));
-                s_dn[i] = __ldg(V.node_dn + g);
-            }
-            __syncwarp();
-            // ---- cost rows -> shared rows (as doubles: the conversion is exact), four nodes in flight per lane
-            for (int i0 = 0; i0 < n; i0 += 4) {
-                float2 c[4][NH];
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (i0 + u < n) {
-                        const char* cp = reinterpret_cast<const char*>(V.cost + (size_t)s_gid[i0 + u] * Dp + l0 + 2 * lane);
-#pragma unroll
-                        for (int h = 0; h < NH; h++) c[u][h] = act[h] ? *reinterpret_cast<const float2*>(cp + h * 256) : make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (i0 + u < n) {
-#pragma unroll
-                        for (int h = 0; h < NH; h++) TT::sts2(rows_a + (uint32_t)(i0 + u) * ROWB + h * HB, make_double2((double)c[u][h].x, (double)c[u][h].y));
-                    }
-            }
-            // ---- leaf -> root inside the subtree: (((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost (Stereo3DMST.cpp:125-137)
-            for (int i = n - 1, k = L; i >= 0; i--) {
-                while (i < s_off[k]) k--;
-                const int4 nu = s_up[i];
-                const int cc = nu.y & 7;
-                double2 acc[NH];
-#pragma unroll
-                for (int h = 0; h < NH; h++) acc[h] = make_double2(0.0, 0.0);
-                const int cl0 = cc ? s_off[k + 1] + nu.x - s_lo[k + 1] : 0;   // local index of the first child
-#pragma unroll
-                for (int j = 3; j >= 0; j--)
-                    if (cc > j) {
-                        const uint32_t iw = ((j & 2) ? (uint32_t)nu.w : (uint32_t)nu.z) >> ((j & 1) * 16) & 0xFFFFu;
-                        const double wk = TT::ldsw(w_a + 8u * iw);
-                        const uint32_t ra = rows_a + (uint32_t)(cl0 + j) * ROWB;
-#pragma unroll
-                        for (int h = 0; h < NH; h++) {
-                            const double2 cv = TT::lds2(ra + h * HB);
-                            acc[h].x = TT::add(acc[h].x, TT::mul(wk, cv.x));
-                            acc[h].y = TT::add(acc[h].y, TT::mul(wk, cv.y));
-                        }
-                    }
-                const uint32_t sa = rows_a + (uint32_t)i * ROWB;
-#pragma unroll
-                for (int h = 0; h < NH; h++) {
-                    const double2 cf = TT::lds2(sa + h * HB);
-                    acc[h].x = TT::add(acc[h].x, cf.x);
-                    acc[h].y = TT::add(acc[h].y, cf.y);
-                    TT::sts2(sa + h * HB, acc[h]);
-                }
-            }
-            double* const arow = V.aup + (size_t)r * Dp + l0 + 2 * lane;
-            if constexpr (!DOWN) {  // the subtree root's row: read by its parent in the walk
-                const int4 nd0 = s_dn[0];
-                if (nd0.x != r) {
-#pragma unroll
-                    for (int h = 0; h < NH; h++)
-                        if (act[h]) *reinterpret_cast<double2*>(reinterpret_cast<char*>(arow) + h * HB) = TT::lds2(rows_a + h * HB);
-                }
-            } else {
-                // ---- root -> leaf: A[c] = w * A[parent] + (1 - w*w) * A_up[c] (Stereo3DMST.cpp:155), WTA per node
-                auto wta = [&](const double2* f, int g, int pix) {
-                    double bc = DBL_MAX;
-                    int bd = 0x7fffffff;
-#pragma unroll
-                    for (int h = 0; h < NH; h++) {
-                        const int lab = l0 + h * 64 + 2 * lane;
-                        if ((FULL || lab < A.d1) && f[h].x < bc) { bc = f[h].x; bd = lab; }
-                        if ((FULL || lab + 1 < A.d1) && f[h].y < bc) { bc = f[h].y; bd = lab + 1; }
-                    }
-                    double mc;
-                    const unsigned md = TT::warp_argmin(bc, bd, mc);
-                    if (lane == 0) {
-                        if (A.n_slices == 1) {
-                            V.disp[pix] = (int)md;
-                            V.best[pix] = mc;
-                        } else {
-                            V.pdisp[(size_t)slice * A.N + g] = (int)md;
-                            V.pbest[(size_t)slice * A.N + g] = mc;
-                        }
-                    }
-                };
-                for (int i = 0, k = 0; i < n; i++) {
-                    while (i >= s_off[k + 1]) k++;
-                    const int4 nd = s_dn[i];
-                    const uint32_t sa = rows_a + (uint32_t)i * ROWB;
-                    double2 fin[NH];
-#pragma unroll
-                    for (int h = 0; h < NH; h++) fin[h] = TT::lds2(sa + h * HB);
-                    if (nd.x != s_gid[i]) {
-                        const uint32_t iw = (uint32_t)nd.y & S3_NDY_W_MASK;
-                        const double wp = TT::ldsw(w_a + 8u * iw), wq = TT::ldsw(w_a + 8u * (S3_NUM_W + iw));
-                        double2 pv[NH];
-                        if (i == 0) {  // the parent is a node of the walk: its final row is in HBM
-                            const char* gp = reinterpret_cast<const char*>(V.aup + (size_t)nd.x * Dp + l0 + 2 * lane);
-#pragma unroll
-                            for (int h = 0; h < NH; h++) pv[h] = act[h] ? TT::ldcg2(gp + h * HB) : make_double2(0.0, 0.0);
-                        } else {
-                            const uint32_t pa = rows_a + (uint32_t)(s_off[k - 1] + nd.x - s_lo[k - 1]) * ROWB;
-#pragma unroll
-                            for (int h = 0; h < NH; h++) pv[h] = TT::lds2(pa + h * HB);
-                        }
-#pragma unroll
-                        for (int h = 0; h < NH; h++) {
-                            fin[h].x = TT::add(TT::mul(wp, pv[h].x), TT::mul(wq, fin[h].x));
-                            fin[h].y = TT::add(TT::mul(wp, pv[h].y), TT::mul(wq, fin[h].y));
-                            TT::sts2(sa + h * HB, fin[h]);
-                        }
-                    }
-                    wta(fin, s_gid[i], nd.w);
-                }
-            }
-        }
-    }
-}
-template <int NH, int WPB>
-static size_t agg_bottom_smem() {
-    const size_t lut = ((2 * S3_NUM_W * sizeof(double) + 15) / 16) * 16;
-    const size_t wb = (size_t)S3_BOTTOM_M * NH * 512 + S3_BOTTOM_M * 16 * 2 + S3_BOTTOM_M * 4 + (S3_BOTTOM_M + 2) * 4 * 2 + 16;
-    return lut + WPB * ((wb + 15) / 16 * 16);
 }
 
 static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
@@ -1079,29 +825,18 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
             G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
             G.cost = V.cost; G.aup = V.aup;
             G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
-            G.bottom_list = V.bottom_list; G.bottom_count = V.counters + S3_CNT_NBOT;
         }
     }
-    // bottom subtrees (k_agg_bottom): one work item per (view, slice); exact dense mode without the aggregated-volume dump
-    static const int bottom_env = getenv("S3_AGG_BOTTOM") ? atoi(getenv("S3_AGG_BOTTOM")) : 0;
-    const bool bottom = ctx->P.exact != 0 && !ctx->P.keep_aggregated && (ctx->P.agg_bottom > 0 || (ctx->P.agg_bottom == 0 && bottom_env > 0));
-    std::vector<int4> bunits;
-    if (bottom)
-        for (int c = 0; c < nctx; c++)
-            for (int view = 0; view < 2; view++)
-                if (views_mask & (1 << view))
-                    for (int s = 0; s < n_slices; s++) bunits.push_back(make_int4(2 * c + view, d0 + s * SW, s, 0));
-    const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16, bbytes = bunits.size() * sizeof(int4);
-    if (ctx->units_cap < ubytes + tbytes + bbytes) {
+    const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16;
+    if (ctx->units_cap < ubytes + tbytes) {
         if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
         ctx->units_dev = nullptr; ctx->units_cap = 0;
-        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes + tbytes + bbytes));
-        ctx->units_cap = ubytes + tbytes + bbytes;
+        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes + tbytes));
+        ctx->units_cap = ubytes + tbytes;
     }
     char* ubase = reinterpret_cast<char*>(ctx->units_dev);
     S3_TRY(s3_h2d_staged(ctx, ubase, table.data(), table.size() * sizeof(Agg3View)));
     S3_TRY(s3_h2d_staged(ctx, ubase + tbytes, units.data(), ubytes));
-    if (bbytes) S3_TRY(s3_h2d_staged(ctx, ubase + tbytes + ubytes, bunits.data(), bbytes));
     // everything the other contexts have queued (their cost volumes) comes first
     for (int c = 1; c < nctx; c++) {
         S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
@@ -1117,9 +852,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.lut_w = exact ? (const void*)ctx->lut_w : (const void*)ctx->lut_wf;
     A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
-    A.bottom = bottom;
-    A.bunits = reinterpret_cast<const int4*>(ubase + tbytes + ubytes);
-    A.n_bunits = (int)bunits.size();
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env < 0 ? 0 : sleep_env ? sleep_env : 20;
 
@@ -1136,17 +868,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     const bool full = nl % SW == 0;  // every slice covers SW real labels
     S3_EV_BEGIN(S3DMST_T_AGG, first);
     cudaStream_t launch_stream = ctx->stream;
-#define AB_LAUNCH(DOWN_)                                                                                                          \
-    do {                                                                                                                         \
-        if (NH == 2) {                                                                                                           \
-            if (full) S3_TRY(agg3_launch(ctx, k_agg_bottom<2, true, DOWN_, 6>, ctx->num_sms, 32 * 6, agg_bottom_smem<2, 6>(), 1, ctx->stream, A));   \
-            else S3_TRY(agg3_launch(ctx, k_agg_bottom<2, false, DOWN_, 6>, ctx->num_sms, 32 * 6, agg_bottom_smem<2, 6>(), 1, ctx->stream, A));       \
-        } else {                                                                                                                 \
-            if (full) S3_TRY(agg3_launch(ctx, k_agg_bottom<1, true, DOWN_, 12>, ctx->num_sms, 32 * 12, agg_bottom_smem<1, 12>(), 1, ctx->stream, A)); \
-            else S3_TRY(agg3_launch(ctx, k_agg_bottom<1, false, DOWN_, 12>, ctx->num_sms, 32 * 12, agg_bottom_smem<1, 12>(), 1, ctx->stream, A));     \
-        }                                                                                                                        \
-    } while (0)
-    if (bottom) AB_LAUNCH(false);  // leaf->root sums of the bottom subtrees: their roots' rows feed the walk
 #define A3_LAUNCH_T(T_, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                      \
     do {                                                                                                                       \
         const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(T_));                                                              \
@@ -1185,8 +906,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         A3_DISPATCH(false, 128, 32, 1, n_small, 512);  // 64 KB ring: two trees per SM
     }
     if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    if (bottom) AB_LAUNCH(true);   // ... and their way down + WTA, from the final rows the walk left for them
-#undef AB_LAUNCH
 #undef A3_DISPATCH
 #undef A3_LAUNCH
 #undef A3_LAUNCH_T

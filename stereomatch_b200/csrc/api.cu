@@ -152,7 +152,6 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->fh_ctas = 0;
     p->fh_threads = 0;
     p->agg_cluster_nodes = 0;
-    p->agg_bottom = 0;
     p->fh_cluster = 0;
     p->pms_cost_mode = 0;
     p->pm_alpha = 0.9f;
@@ -434,10 +433,6 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
             if (P.child_count < 2) P.cw01 |= wv << (16 * P.child_count); else P.cw23 |= wv << (16 * (P.child_count - 2));
             P.child_count++;
         }
-        for (int g = a, next = a + 1; g < b; g++) {  // child_begin is a running position: defined for leaves too
-            if ((nu[g].child_count & 7) == 0) nu[g].child_begin = next;
-            next = nu[g].child_begin + (nu[g].child_count & 7);
-        }
         int* L = lvl.data() + a + t;
         int d = 0;
         L[0] = a;
@@ -476,7 +471,6 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int T, const int3
     H2D(V.unit_tree, order.data(), sizeof(int) * T);
     H2D(V.counters + (S3_MAX_ROUNDS - 64), &T, sizeof(int));  // forest.cu CNT_T: the device-side tree count
     H2D(V.tree_rootpix, rootpix.data(), sizeof(int) * T);
-    S3_TRY(s3_forest_bottom(ctx, view));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));
     V.T = T;
     V.h_tree_start.assign(tree_start, tree_start + T + 1);

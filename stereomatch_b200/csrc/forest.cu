@@ -755,75 +755,6 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     }
 }
 
-// ---- bottom subtrees.  In BFS order the descendants of a node at any depth form ONE contiguous index range
-// [child_begin(first), child_begin(last) + child_count(last)) of the range above (child_begin is a running position: it
-// is defined for leaves too), so a node finds the size of its subtree — capped at S3_BOTTOM_M + 1 — by walking a few
-// ranges, without any bottom-up pass over the tree.
-__global__ void k_subtree_size(int N, const NodeUp* __restrict__ node_up, uint8_t* __restrict__ sub) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    int lo = v, hi = v + 1, cnt = 1;
-    while (cnt <= S3_BOTTOM_M) {
-        const int nlo = node_up[lo].child_begin;
-        const NodeUp last = node_up[hi - 1];
-        const int nhi = last.child_begin + (last.child_count & 7);
-        if (nhi <= nlo) break;
-        cnt += nhi - nlo;
-        lo = nlo; hi = nhi;
-    }
-    sub[v] = (uint8_t)min(cnt, S3_BOTTOM_M + 1);
-}
-__global__ void k_subtree_flags(int N, const uint8_t* __restrict__ sub, const int* __restrict__ tree_id, const int* __restrict__ tree_start,
-                                NodeUp* __restrict__ node_up, int4* __restrict__ node_dn, uint32_t* __restrict__ list, int* __restrict__ count) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    bool root = false;
-    if (v < N) {
-        const int4 nd = node_dn[v];
-        const int t = tree_id[nd.w];
-        const int base = tree_start[t], end = tree_start[t + 1];
-        const bool bot = sub[v] <= S3_BOTTOM_M;
-        root = bot && (nd.x == v || sub[nd.x] > S3_BOTTOM_M);
-        NodeUp nu = node_up[v];
-        const int cc = nu.child_count & 7;
-        unsigned fu = bot ? S3_NU_BOTTOM : 0u, fd = bot ? S3_NDY_BOTTOM : 0u;
-        if (!bot) {
-            unsigned m = 0;
-            for (int j = 0; j < cc; j++)
-                if (sub[nu.child_begin + j] <= S3_BOTTOM_M) m |= 1u << j;
-            fu |= m << S3_NU_BOTCHILD_SHIFT;
-            if (m) fd |= S3_NDY_HASBOTTOM;
-        }
-        const int step[3] = {16, 32, 256};  // warps walking a tree: small CTA, big CTA, cluster
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            if (v - step[i] >= base && sub[v - step[i]] <= S3_BOTTOM_M) fu |= 1u << (S3_NU_NEXTBOT_SHIFT + i);
-            if (v + step[i] < end && sub[v + step[i]] <= S3_BOTTOM_M) fd |= 1u << (S3_NDY_NEXTBOT_SHIFT + i);
-        }
-        reinterpret_cast<int*>(node_up + v)[1] = (int)((unsigned)nu.child_count | fu);
-        reinterpret_cast<int*>(node_dn + v)[1] = (int)((unsigned)nd.y | fd);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, root);
-    if (bal) {
-        const int lane = threadIdx.x & 31;
-        int off = 0;
-        if (lane == 0) off = atomicAdd(count, __popc(bal));
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (root) list[off + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v;
-    }
-}
-
-int s3_forest_bottom(s3dmst_ctx* ctx, int view) {
-    View& V = ctx->v[view];
-    const int N = ctx->N, TB = 256;
-    V.bottom_list = V.bfs_front;
-    S3_CUDA(cudaMemsetAsync(V.counters + S3_CNT_NBOT, 0, sizeof(int), ctx->stream));
-    k_subtree_size<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_up, V.e_flag);
-    S3_LAUNCH_CHECK();
-    k_subtree_flags<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.e_flag, V.tree_id, V.tree_start, V.node_up, V.node_dn, V.bottom_list, V.counters + S3_CNT_NBOT);
-    S3_LAUNCH_CHECK();
-    return 0;
-}
-
 // node_dn -> the flat per-node arrays the other stages and the parity dumps read (off the BFS critical path)
 __global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __restrict__ node_pixel, int* __restrict__ parent,
                              int* __restrict__ level, uint16_t* __restrict__ pw, uint32_t* __restrict__ leaf_bits) {
@@ -833,7 +764,7 @@ __global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __res
     if ((threadIdx.x & 31) == 0 && h < N) leaf_bits[h >> 5] = lb;
     if (h >= N) return;
     parent[h] = nd.x;
-    pw[h] = (uint16_t)(nd.y & S3_NDY_W_MASK);
+    pw[h] = (uint16_t)nd.y;
     level[h] = nd.z & ~S3_ND_FLAGS;
     node_pixel[h] = nd.w;
 }
@@ -1030,7 +961,6 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
             View& V = ctx->v[view];
             k_bfs_unpack<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_dn, V.node_pixel, V.parent, V.level, V.pw, V.leaf_bits);
             S3_LAUNCH_CHECK();
-            S3_TRY(s3_forest_bottom(ctx, view));
             V.max_depth = -1;  // tree depths stay on the device until somebody asks (s3_forest_depths)
             V.adj_ready = false;
             V.forest_ready = true;   // the device side is complete in stream order; T and the sizes reach the host lazily

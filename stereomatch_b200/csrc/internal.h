@@ -16,17 +16,6 @@
 #define S3_ND_FAR (1 << 30)      // node_dn.z flag: the node has a child S3_AGG_NEAR or more nodes away
 #define S3_ND_LEAF (1 << 29)     // node_dn.z flag: no children (its leaf->root sum is its cost: never stored)
 #define S3_ND_FLAGS (S3_ND_FAR | S3_ND_LEAF)
-// Bottom subtrees (aggregate3.cu: k_agg_bottom): a node whose whole subtree has at most S3_BOTTOM_M nodes is never walked
-// by the dataflow kernel; its subtree is aggregated on chip by one warp, twice (leaf->root sums for the parent, then
-// again for the way down), so its running sums never travel to HBM.  Flags written by forest.cu: k_subtree_flags.
-#define S3_BOTTOM_M 32
-#define S3_NU_BOTTOM 0x200          // NodeUp.child_count: the node lies in a bottom subtree
-#define S3_NU_BOTCHILD_SHIFT 12     // bits 12..15: child j is the root of a bottom subtree (set on top nodes only)
-#define S3_NU_NEXTBOT_SHIFT 16      // bits 16..18: node v-16 / v-32 / v-256 of the same tree is a bottom node (the walk's next node)
-#define S3_NDY_W_MASK 0xFFFF        // node_dn.y: low 16 bits = parent weight
-#define S3_NDY_BOTTOM (1 << 16)     // node_dn.y: the node lies in a bottom subtree
-#define S3_NDY_HASBOTTOM (1 << 17)  // a top node with at least one bottom child: its final row has to reach HBM
-#define S3_NDY_NEXTBOT_SHIFT 18     // bits 18..20: node v+16 / v+32 / v+256 of the same tree is a bottom node
 
 // Per-node record read by the leaf->root pass: children are contiguous in BFS order.
 struct __align__(16) NodeUp {
@@ -78,7 +67,6 @@ struct View {
     uint16_t* pw = nullptr;     // [N]
     NodeUp* node_up = nullptr;  // [N]
     int4* node_dn = nullptr;    // [N] {parent, parent weight, level | flags, pixel}: the root->leaf pass record
-    uint32_t* bottom_list = nullptr;  // roots of the bottom subtrees (aliases bfs_front: free once the BFS is done); count at counters[CNT_NBOT]
     uint32_t* leaf_bits = nullptr;  // [N/32 + 1] bit v = node v is a leaf (prefetch target selection on the way down)
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
     // tree adjacency graph (Stereo3DMST.cpp:377-384) as a device CSR, built lazily (proposal generation, parity dumps)
@@ -164,7 +152,6 @@ struct s3dmst_ctx {
 };
 
 #define S3_MAX_ROUNDS 65536
-#define S3_CNT_NBOT (S3_MAX_ROUNDS - 48)   // View::counters slot: number of bottom-subtree roots
 #define S3_FH_MAX_VIEWS 16        // views (2 per frame) one forest-kernel launch serves
 #define S3_FH_ROUNDS 8192         // round cap of the forest kernel (per-round counters)
 #define S3_FH_MAX_CTAS 256        // upper bound on the cooperative grid of the forest kernel
@@ -207,7 +194,6 @@ int s3_forest_pre(s3dmst_ctx* ctx, int mask);                     // image stage
 int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (asynchronous)
 int s3_forest_finish_host(s3dmst_ctx* ctx);                       // tree count / sizes -> host (waits for the copy s3_forest_post queued)
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);
-int s3_forest_bottom(s3dmst_ctx* ctx, int view);                  // subtree sizes -> bottom-subtree flags and work list
 int s3_forest_depths(s3dmst_ctx* ctx, int view);                  // forest.cu: lazy D2H of the tree depths           // forest.cu: unit order, depths
 int s3_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const uint16_t* map_fxy, int W, int H);  // rectify.cu
 int s3_remap_raw_pair(s3dmst_ctx* ctx, const uint8_t* left_raw, const uint8_t* right_raw, int sw, int sh, int stride);

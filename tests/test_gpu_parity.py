@@ -969,55 +969,3 @@ def test_plane_cost_mode_matches_oracle(api, oracle, cluster):
     with pytest.raises(api.S3Error):
         e2.aggregate_dense(0, 0, D2)           # there is no volume to aggregate
     eng.close(); e2.close()
-
-
-@pytest.mark.parametrize("W,H,D,seed,c,ms,nat", CASES[:7] + [(120, 80, 200, 13, 900.0, 40, 0)])
-@pytest.mark.parametrize("own_forest,cluster", [(False, -1), (True, -1), (True, 48)])
-def test_bottom_subtrees_match_oracle(api, oracle, W, H, D, seed, c, ms, nat, own_forest, cluster):
-    """params.agg_bottom = 1: subtrees of at most 32 nodes are aggregated on chip by k_agg_bottom (their running sums never
-    reach HBM), the dataflow walk covers the rest: winners and minimum costs bit-identical to the oracle, for forests built
-    on the device and uploaded, one CTA per tree and a cluster per tree, one and several label slices."""
-    L, R, _ = make(W, H, min(D, 24), seed, nat)
-    F = oracle.forest(L, c=c, min_size=ms)
-    lv, _ = oracle.cost_adgrad(L, R, D)
-    disp_o, best_o, _ = oracle.aggregate_dense(F, lv)
-    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, agg_cluster_nodes=cluster, agg_bottom=1)
-    eng.set_images(L, R)
-    if own_forest:
-        eng.build_forest(0)
-    else:
-        eng.set_forest(0, W, H, F.tree_start, F.node_pixel, F.parent, F.pw)
-    eng.set_cost_volume(0, lv, ingest=False)
-    disp, best = eng.aggregate_dense(0)
-    assert np.array_equal(disp, disp_o)
-    assert np.array_equal(bits(best), bits(best_o))
-    if D >= 16:   # a label range (the sharded path) through the same kernels
-        d0, d1 = 4, D - 3
-        do, bo, _ = oracle.aggregate_dense(F, lv, d0, d1)
-        d2, b2 = eng.aggregate_dense(0, d0, d1)
-        assert np.array_equal(d2, do) and np.array_equal(bits(b2), bits(bo))
-    eng.close()
-
-
-def test_bottom_subtrees_pipeline_and_batch(api, oracle):
-    """The whole dense pipeline and a batch of frames with agg_bottom = 1 equal the runs without it."""
-    W, H, D = 256, 160, 48
-    frames = [make(W, H, D, 70 + i, i % 2) for i in range(3)]
-    ref = []
-    for Li, Ri, _ in frames:
-        e = api.Stereo3DMST()
-        e.set_images(Li, Ri)
-        ref.append(e.run_dense(D, fill=True))
-        e.close()
-    engs = []
-    for Li, Ri, _ in frames:
-        e = api.Stereo3DMST(fh_ctas=24, agg_bottom=1)
-        e.set_images(Li, Ri)
-        engs.append(e)
-    outs = api.run_dense_batch(engs, D, fill=True)
-    for (dl, dr), (rl, rr) in zip(outs, ref):
-        assert np.array_equal(bits(dl), bits(rl)) and np.array_equal(bits(dr), bits(rr))
-    dl, dr = engs[0].run_dense(D, fill=True)
-    assert np.array_equal(bits(dl), bits(ref[0][0])) and np.array_equal(bits(dr), bits(ref[0][1]))
-    for e in engs:
-        e.close()
