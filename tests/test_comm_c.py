@@ -21,7 +21,7 @@ def drv():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(ROOT, "tests", "models", "comm_driver.c")
     libdir = os.path.join(ROOT, "stereomatch_b200")
-    if not os.path.exists(SO) or max(os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "include", "s3dmst.h"))) > os.path.getmtime(SO):
+    if True:   # always rebuilt (a copied tree's mtimes prove nothing)
         subprocess.check_call(["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src,
                                "-L", libdir, "-ls3dmst", f"-Wl,-rpath,{libdir}", "-o", SO])
     return C.CDLL(SO)

@@ -20,8 +20,7 @@ def shim():
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(ROOT, "stereomatch_b200", "csrc", "stereo3dmst_shim.cpp"), os.path.join(ROOT, "tests", "models", "shim_driver.cpp")]
     libdir = os.path.join(ROOT, "stereomatch_b200")
-    deps = srcs + [os.path.join(ROOT, "include", "s3dmst.h"), os.path.join(ROOT, "oracle", "ref_shims", "opencv2", "core_shim.hpp")]
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in deps):   # (the parameter struct lives in the header)
+    if True:   # always rebuilt (2 s): the parameter struct lives in the header, and a copied tree's mtimes prove nothing
         subprocess.check_call(["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w", "-I", os.path.join(ROOT, "oracle", "ref_shims"),
                                "-I", os.path.join(ROOT, "include"), *srcs, "-L", libdir, "-ls3dmst", f"-Wl,-rpath,{libdir}", "-o", SO])
     return C.CDLL(SO)
