@@ -73,6 +73,20 @@ def test_forest_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat):
     eng.close()
 
 
+@pytest.mark.parametrize("cluster", [8, 16])
+def test_forest_cluster_barrier_variant(api, oracle, cluster):
+    """params.fh_cluster: every view's forest kernel runs in one thread-block cluster of 8 / 16 CTAs with the hardware
+    cluster barrier instead of the cooperative grid's software barrier — same forest, edge for edge."""
+    for (W, H, seed, nat, c, ms) in ((320, 200, 5, 0, 5000.0, 200), (317, 203, 6, 1, 1000.0, 50)):
+        L, R, _ = make(W, H, 16, seed, nat)
+        eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, fh_cluster=cluster)
+        eng.set_images(L, R)
+        eng.build_forest(0); eng.build_forest(1)
+        check_forest(oracle.forest(L, c=c, min_size=ms), eng.get_forest(0))
+        check_forest(oracle.forest(R, c=c, min_size=ms), eng.get_forest(1))
+        eng.close()
+
+
 def test_forest_without_median(api, oracle):
     L, R, _ = make(80, 60, 16, 4, 0)
     eng = api.Stereo3DMST(median=0, fh_c=800.0, min_cc_size=30)

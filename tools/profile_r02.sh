@@ -18,6 +18,7 @@ python tools/probe_pair.py c2 -1 > $O/r02_plain_c2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_agg_flow -s 2 -c 1 -f -o $O/r02_agg_flow_c2_single python tools/probe_pair.py c2 -1 > $O/r02_ncu_c2.log 2>&1
 echo "c2 full rc=$?"
 python tools/probe_pair.py flir 0 > $O/r02_plain_flir.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_agg_flow.*Li8EEv -s 2 -c 1 -f -o $O/r02_agg_flow_cluster_flir python tools/probe_pair.py flir 0 > $O/r02_ncu_flir.log 2>&1
+# (the cluster launch is the first k_agg_flow launch of every run_dense: launches 0, 3, 6, ... of the filter)
+ncu --set full --clock-control none --import-source on -k regex:k_agg_flow -s 6 -c 1 -f -o $O/r02_agg_flow_cluster_flir python tools/probe_pair.py flir 0 > $O/r02_ncu_flir.log 2>&1
 echo "flir cluster full rc=$?"
 ls -la $O | grep r02_
