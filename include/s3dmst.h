@@ -56,8 +56,8 @@ typedef struct s3dmst_params {
     int keep_aggregated;/* 1: s3dmst_aggregate_dense keeps the final aggregated volume for dumps    */
     int agg_threads;    /* 0 = auto; threads per CTA of the aggregation kernels (multiple of 32)    */
     int agg_cache_nodes;/* 0 = auto; nodes of a tree level cached in shared memory per CTA          */
-    int agg_ring_nodes; /* 0 = auto; node rows staged ahead per CTA by the bulk-copy (TMA) pipeline      */
-    int agg_kernel;     /* 0 = auto (dataflow kernel), 1 = simple level-synchronous kernel, 2 = TMA tile kernel */
+    int agg_ring_nodes; /* unused (kept so that the layout of round 1 callers stays valid)                 */
+    int agg_kernel;     /* 0 = auto (dataflow kernel), 1 = simple level-synchronous kernels (any even d0)        */
     int fh_ctas;        /* 0 = one CTA per SM (one pair alone on the GPU); > 0: CTAs of the cooperative forest kernel per
                            frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
                            frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
@@ -109,7 +109,8 @@ int s3dmst_get_image(s3dmst_ctx* ctx, int view, uint8_t* bgr);
 void s3dmst_remap_table(int16_t* tab);
 
 /* a3,a4,a5,a7 (Stereo3DMST.cpp:226-307, :342-384, :434-522; segment-graph.h:54-89): median, edge
- * weights, FH forest (level-synchronous Boruvka), min-size merge, tree ids, BFS re-indexing. */
+ * weights, FH forest (asynchronous exact rounds with a (weight, edge id) tie-break), min-size merge, tree ids, BFS
+ * re-indexing — all on the device; the call queues the work and returns (the tree count reaches the host lazily). */
 int s3dmst_build_forest(s3dmst_ctx* ctx, int view);
 int s3dmst_forest_info(s3dmst_ctx* ctx, int view, int* num_trees, int* max_depth, int* adj_size);
 /* Parity dump; any pointer may be NULL.  edge_weight/edge_mask are [2N] by canonical edge id
