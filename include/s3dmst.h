@@ -62,9 +62,6 @@ typedef struct s3dmst_params {
                            frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
                            frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
     int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel */
-    int agg_paths;      /* dense exact mode: 1 = path-parallel tree filter (a warp follows a heavy path with the running value in
-                           registers; every path of the launch is a work item of one GPU-wide queue); 0 = auto, -1 = the
-                           per-tree dataflow walk                                                                    */
     int fh_cluster;     /* 0: the forest kernel is a cooperative grid with a software barrier per view; 8 or 16: every view gets one
                            thread-block cluster of that many CTAs and the hardware cluster barrier                      */
     int pms_cost_mode;  /* data term of the 3D-label (PatchMatch) search: 0 = compute3DLabelCost on the cost volume (the

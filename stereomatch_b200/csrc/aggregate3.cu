@@ -59,13 +59,6 @@ struct Agg3View {
     double* best;
     int32_t* pdisp;   // [slice][node] partial results otherwise
     double* pbest;
-    // path-parallel aggregation (k_agg_paths): the view's heavy paths and the completion stamps of this launch
-    const int* path_nodes;
-    const int2* paths;
-    const int* path_count;
-    int* flags_up;    // [slices][N]: stamp of a path top = its leaf->root row is in HBM
-    int* flags_dn;    // [slices][N]: stamp of a node with light children = its final row is in HBM
-    int epoch;
     // proposal mode with the plane cost (params.pms_cost_mode = 1): this view's and the other view's image and gradients
     const uint8_t* img_self;
     const uint8_t* img_other;
@@ -91,11 +84,6 @@ struct Agg3Args {
     float oob;             // label cost outside [0, D)
     // proposal generation inside the kernel (s3dmst_pms_iterate): after a tree's listed proposals (its neighbours' labels),
     // the refinement ladder around a random pixel of the tree itself
-    // path-parallel aggregation: one work item per (view, slice) in punits {view, first label, slice, 0}; claim[0/1] = the
-    // up / down pass's work counters
-    const int4* punits;
-    int n_punits;
-    int* claim;
     int cost_mode, view, img_h;            // proposal mode: 1 = plane cost from the images (hd_math.h: s3_plane_cost)
     float pm_alpha, pm_tau_c, pm_tau_g, pm_scale;
     int gen;
@@ -701,218 +689,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     if constexpr (CL > 1) a3_cluster_sync();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Path-parallel tree filter (params.agg_paths = 1).  What bounds the dataflow walk above is the chain of dependent
-// instructions per tree level: a node's value travels warp -> shared memory -> another warp at every level.  Here a warp
-// follows a HEAVY PATH (a node's heavy child is its first child, forest.cu: s3_forest_paths) and keeps the running
-// value in registers: on the way up the heavy child's sum is exactly the operand of the node's LAST multiply-add
-// ((((0 + w3 A3) + w2 A2) + w1 A1) + w0 A0) + cost, Stereo3DMST.cpp:125-137 — children in reverse order, the first child
-// last), on the way down the parent's final value is the operand of the node's only one (:155).  A hand-over through
-// memory happens only where paths join: a light child's row is read from HBM/L2 once the stamp of its path's top says
-// it is there (up), a path's top reads its parent's final row (down).  Every path of every tree of the launch is one
-// work item; persistent warps claim them from ONE counter in an order in which a path's dependencies always precede
-// it (up: tops in descending node order — a light child's top has a larger index than its parent; down: ascending), so
-// a waiting warp only ever waits for a path that some running warp holds: no deadlock, no per-tree CTA, and a giant tree
-// spreads over the whole GPU.  Same operations in the same order as the walk: bit-identical.
-template <int NH, bool FULL, bool DOWN>
-__global__ void __launch_bounds__(256, 4) k_agg_paths(Agg3Args A) {
-    using TT = A3T<double>;
-    __shared__ double s_lut[2 * S3_NUM_W];
-    __shared__ int s_maxp;
-    constexpr uint32_t HB = 64 * sizeof(double);
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < S3_NUM_W; i += blockDim.x) {
-        s_lut[i] = reinterpret_cast<const double*>(A.lut_w)[i];
-        s_lut[S3_NUM_W + i] = reinterpret_cast<const double*>(A.lut_w2)[i];
-    }
-    if (tid == 0) {
-        int m = 0;
-        for (int b = 0; b < A.n_punits; b++) m = max(m, *A.views[A.punits[b].x].path_count);
-        s_maxp = m;
-    }
-    __syncthreads();
-    const uint32_t w_a = a3_smem(s_lut);
-    const int maxp = s_maxp, nbu = A.n_punits;
-    const size_t Dp = (size_t)A.Dp;
-    while (true) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(A.claim + (DOWN ? 1 : 0), 1);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        const int qi = g / nbu;
-        if (qi >= maxp) break;
-        const int4 unit = A.punits[g - qi * nbu];   // the views take turns: every view's paths are claimed in their own order
-        const Agg3View& V = A.views[unit.x];
-        const int P = __ldg(V.path_count);
-        if (qi >= P) continue;
-        const int l0 = unit.y, slice = unit.z;
-        const int2 pe = __ldg(V.paths + (DOWN ? qi : P - 1 - qi));
-        const int* nodes = V.path_nodes + pe.x;
-        const int len = pe.y, epoch = V.epoch;
-        bool act[NH];
-#pragma unroll
-        for (int h = 0; h < NH; h++) act[h] = FULL || l0 + h * 64 + 2 * lane < A.d1;
-        const size_t col = (size_t)l0 + 2 * lane;   // this lane's first label column
-        if constexpr (!DOWN) {
-            int* const fu = V.flags_up + (size_t)slice * A.N;
-            double2 heavy[NH];
-#pragma unroll
-            for (int h = 0; h < NH; h++) heavy[h] = make_double2(0.0, 0.0);
-            int v = 0;
-            for (int i0 = 0; i0 < len; i0 += 32) {
-                const int cnt = min(32, len - i0);
-                int v_l = 0;
-                int4 nu_l = make_int4(0, 0, 0, 0);
-                if (lane < cnt) {   // the chunk's node ids and records: two dependent loads for up to 32 nodes
-                    v_l = __ldg(nodes + i0 + lane);
-                    nu_l = __ldg(reinterpret_cast<const int4*>(V.node_up + v_l));
-                }
-                for (int j = 0; j < cnt; j++) {
-                    v = __shfl_sync(0xffffffffu, v_l, j);
-                    const int cb = __shfl_sync(0xffffffffu, nu_l.x, j), cy = __shfl_sync(0xffffffffu, nu_l.y, j);
-                    const uint32_t cw01 = (uint32_t)__shfl_sync(0xffffffffu, nu_l.z, j), cw23 = (uint32_t)__shfl_sync(0xffffffffu, nu_l.w, j);
-                    const int cc = cy & 7;
-                    float2 cf[NH];
-#pragma unroll
-                    for (int h = 0; h < NH; h++) cf[h] = act[h] ? *reinterpret_cast<const float2*>(V.cost + (size_t)v * Dp + col + h * 64) : make_float2(0.f, 0.f);
-                    double2 acc[NH];
-#pragma unroll
-                    for (int h = 0; h < NH; h++) acc[h] = make_double2(0.0, 0.0);
-                    // light children: their rows come from L2/HBM once the stamps of their paths are there.  The row loads
-                    // are issued only after the stamps were seen (control dependency) and go to L2 (ld.cg), where the writer
-                    // made the row visible before the stamp (__threadfence): no acquire fence needed.
-                    if (cc > 1) {
-                        while (true) {
-                            bool ok = true;
-#pragma unroll
-                            for (int k = 1; k <= 3; k++)
-                                if (cc > k) {
-                                    int f;
-                                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(fu + cb + k) : "memory");
-                                    ok &= f == epoch;
-                                }
-                            if (ok) break;
-                            __nanosleep(100);
-                        }
-                    }
-                    double2 cvk[3][NH];
-#pragma unroll
-                    for (int k = 1; k <= 3; k++)
-#pragma unroll
-                        for (int h = 0; h < NH; h++)
-                            cvk[k - 1][h] = (cc > k && act[h]) ? TT::ldcg2(reinterpret_cast<const char*>(V.aup + (size_t)(cb + k) * Dp + col) + h * HB) : make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int k = 3; k >= 1; k--)
-                        if (cc > k) {
-                            const double wk = TT::ldsw(w_a + 8u * (((k & 2) ? cw23 : cw01) >> ((k & 1) * 16) & 0xFFFFu));
-                            const double2* cv = cvk[k - 1];
-#pragma unroll
-                            for (int h = 0; h < NH; h++) {
-                                acc[h].x = TT::add(acc[h].x, TT::mul(wk, cv[h].x));
-                                acc[h].y = TT::add(acc[h].y, TT::mul(wk, cv[h].y));
-                            }
-                        }
-                    if (cc > 0) {   // the heavy child: the previous node of this path, still in registers
-                        const double w0 = TT::ldsw(w_a + 8u * (cw01 & 0xFFFFu));
-#pragma unroll
-                        for (int h = 0; h < NH; h++) {
-                            acc[h].x = TT::add(acc[h].x, TT::mul(w0, heavy[h].x));
-                            acc[h].y = TT::add(acc[h].y, TT::mul(w0, heavy[h].y));
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < NH; h++) {
-                        acc[h].x = TT::add(acc[h].x, (double)cf[h].x);
-                        acc[h].y = TT::add(acc[h].y, (double)cf[h].y);
-                        heavy[h] = acc[h];
-                        if (act[h]) *reinterpret_cast<double2*>(reinterpret_cast<char*>(V.aup + (size_t)v * Dp + col) + h * HB) = acc[h];   // read back on the way down
-                    }
-                }
-            }
-            // the top's row is out: stamp it for the parent's path (every lane fences its own stores first)
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(fu + v), "r"(epoch) : "memory");
-        } else {
-            int* const fd = V.flags_dn + (size_t)slice * A.N;
-            double2 fp[NH];   // the final value of the node above
-#pragma unroll
-            for (int h = 0; h < NH; h++) fp[h] = make_double2(0.0, 0.0);
-            const int top = __ldg(nodes + len - 1);
-            const int ptop = __ldg(&V.node_dn[top].x);
-            if (ptop != top) {   // the top's parent lies on another path: its final row, once stamped
-                const char* gp = reinterpret_cast<const char*>(V.aup + (size_t)ptop * Dp + col);
-                while (true) {   // stamp first, row after it (see the up pass)
-                    int f;
-                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(fd + ptop) : "memory");
-                    if (f == epoch) break;
-                    __nanosleep(100);
-                }
-#pragma unroll
-                for (int h = 0; h < NH; h++) fp[h] = act[h] ? TT::ldcg2(gp + h * HB) : make_double2(0.0, 0.0);
-            }
-            for (int i1 = len; i1 > 0; i1 -= 32) {   // chunks from the top downwards
-                const int cnt = min(32, i1);
-                int v_l = 0, cc_l = 0;
-                int4 nd_l = make_int4(0, 0, 0, 0);
-                if (lane < cnt) {
-                    v_l = __ldg(nodes + i1 - 1 - lane);
-                    nd_l = __ldg(V.node_dn + v_l);
-                    cc_l = __ldg(&V.node_up[v_l].child_count) & 7;
-                }
-                for (int j = 0; j < cnt; j++) {
-                    const int v = __shfl_sync(0xffffffffu, v_l, j);
-                    const int p = __shfl_sync(0xffffffffu, nd_l.x, j), iw = __shfl_sync(0xffffffffu, nd_l.y, j), pix = __shfl_sync(0xffffffffu, nd_l.w, j);
-                    const int cc = __shfl_sync(0xffffffffu, cc_l, j);
-                    char* const ap = reinterpret_cast<char*>(V.aup + (size_t)v * Dp + col);
-                    double2 fin[NH];
-#pragma unroll
-                    for (int h = 0; h < NH; h++) fin[h] = act[h] ? *reinterpret_cast<const double2*>(ap + h * HB) : make_double2(0.0, 0.0);
-                    if (p != v) {   // A[c] = w * A[parent] + (1 - w*w) * A_up[c]   (Stereo3DMST.cpp:155)
-                        const double wp = TT::ldsw(w_a + 8u * (uint32_t)iw), wq = TT::ldsw(w_a + 8u * (uint32_t)(S3_NUM_W + iw));
-#pragma unroll
-                        for (int h = 0; h < NH; h++) {
-                            fin[h].x = TT::add(TT::mul(wp, fp[h].x), TT::mul(wq, fin[h].x));
-                            fin[h].y = TT::add(TT::mul(wp, fp[h].y), TT::mul(wq, fin[h].y));
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < NH; h++) fp[h] = fin[h];
-                    if (cc > 1 || A.keep) {   // light children's paths (and the volume dump) read the final row from memory
-#pragma unroll
-                        for (int h = 0; h < NH; h++)
-                            if (act[h]) *reinterpret_cast<double2*>(ap + h * HB) = fin[h];
-                        if (cc > 1) {
-                            __threadfence();
-                            __syncwarp();
-                            if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(fd + v), "r"(epoch) : "memory");
-                        }
-                    }
-                    // WTA over the node's labels held by this warp: strict '<', lowest label wins ties
-                    double bc = DBL_MAX;
-                    int bd = 0x7fffffff;
-#pragma unroll
-                    for (int h = 0; h < NH; h++) {
-                        const int lab = l0 + h * 64 + 2 * lane;
-                        if ((FULL || lab < A.d1) && fin[h].x < bc) { bc = fin[h].x; bd = lab; }
-                        if ((FULL || lab + 1 < A.d1) && fin[h].y < bc) { bc = fin[h].y; bd = lab + 1; }
-                    }
-                    double mc;
-                    const unsigned md = TT::warp_argmin(bc, bd, mc);
-                    if (lane == 0) {
-                        if (A.n_slices == 1) {
-                            V.disp[pix] = (int)md;
-                            V.best[pix] = mc;
-                        } else {
-                            V.pdisp[(size_t)slice * A.N + v] = (int)md;
-                            V.pbest[(size_t)slice * A.N + v] = mc;
-                        }
-                    }
-                }
-            }
-        }
-    }
-}
-
 static size_t agg3_smem_bytes(int NH, int R, size_t tsz) { return (2 * S3_NUM_W * tsz + 15) / 16 * 16 + (size_t)R * NH * 32 * 2 * tsz + 32 * sizeof(int); }
 
 __global__ void k_wta_finish3(int N, int n_slices, const int4* __restrict__ node_dn, const int32_t* __restrict__ pdisp,
@@ -1022,9 +798,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     std::vector<int4> units(u.size());
     for (size_t i = 0; i < u.size(); i++) units[i] = u[i].second;
 
-    // path-parallel aggregation instead of the per-tree walk (exact dense mode)
-    static const int paths_env = getenv("S3_AGG_PATHS") ? atoi(getenv("S3_AGG_PATHS")) : 0;
-    const bool paths_mode = ctx->P.exact != 0 && (ctx->P.agg_paths > 0 || (ctx->P.agg_paths == 0 && paths_env > 0));
     // per-view tables and (for several slices) partial WTA results
     std::vector<Agg3View> table(2 * (size_t)nctx);
     memset(table.data(), 0, table.size() * sizeof(Agg3View));
@@ -1052,50 +825,18 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
             G.tree_start = V.tree_start; G.node_up = V.node_up; G.node_dn = V.node_dn; G.node_pixel = V.node_pixel;
             G.cost = V.cost; G.aup = V.aup;
             G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
-            if (paths_mode && (views_mask & (1 << view))) {
-                // heavy paths (built once per forest, on the frame's own stream) and this launch's completion stamps
-                const int r = [&]() -> int {
-                    s3dmst_ctx* ctx = cx;   // the error macros report into this frame's context
-                    S3_TRY(s3_forest_paths(ctx, view));
-                    const size_t need = 2 * (size_t)n_slices * ctx->N;
-                    if (V.path_flags_cap < need) {
-                        if (V.path_flags) S3_CUDA(cudaFree(V.path_flags));
-                        V.path_flags = nullptr; V.path_flags_cap = 0;
-                        S3_CUDA(cudaMalloc(&V.path_flags, sizeof(int) * need));
-                        S3_CUDA(cudaMemsetAsync(V.path_flags, 0, sizeof(int) * need, ctx->stream));
-                        V.path_flags_cap = need;
-                        V.path_epoch = 0;
-                    }
-                    return 0;
-                }();
-                if (r) return c == 0 ? r : s3_fail(ctx, r, "aggregate_dense: frame %d: %s", c, cx->err.c_str());
-                V.path_epoch++;
-                G.path_nodes = V.path_nodes; G.paths = V.paths; G.path_count = V.counters + S3_CNT_NPATH;
-                G.flags_up = V.path_flags; G.flags_dn = V.path_flags + (size_t)n_slices * cx->N; G.epoch = V.path_epoch;
-            }
         }
     }
-    std::vector<int4> punits;   // k_agg_paths: one work item per (view, slice)
-    if (paths_mode)
-        for (int c = 0; c < nctx; c++)
-            for (int view = 0; view < 2; view++)
-                if (views_mask & (1 << view))
-                    for (int s = 0; s < n_slices; s++) punits.push_back(make_int4(2 * c + view, d0 + s * SW, s, 0));
-    const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16, pbytes = punits.size() * sizeof(int4) + 16;
-    if (ctx->units_cap < ubytes + tbytes + pbytes) {
+    const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16;
+    if (ctx->units_cap < ubytes + tbytes) {
         if (ctx->units_dev) S3_CUDA(cudaFree(ctx->units_dev));
         ctx->units_dev = nullptr; ctx->units_cap = 0;
-        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes + tbytes + pbytes));
-        ctx->units_cap = ubytes + tbytes + pbytes;
+        S3_CUDA(cudaMalloc(&ctx->units_dev, ubytes + tbytes));
+        ctx->units_cap = ubytes + tbytes;
     }
     char* ubase = reinterpret_cast<char*>(ctx->units_dev);
     S3_TRY(s3_h2d_staged(ctx, ubase, table.data(), table.size() * sizeof(Agg3View)));
     S3_TRY(s3_h2d_staged(ctx, ubase + tbytes, units.data(), ubytes));
-    if (paths_mode) {
-        const int zero[4] = {0, 0, 0, 0};   // the two work counters
-        S3_TRY(s3_h2d_staged(ctx, ubase + tbytes + ubytes, zero, sizeof zero));
-        S3_TRY(s3_h2d_staged(ctx, ubase + tbytes + ubytes + 16, punits.data(), punits.size() * sizeof(int4)));
-    }
     // everything the other contexts have queued (their cost volumes) comes first
     for (int c = 1; c < nctx; c++) {
         S3_CUDA(cudaEventRecord(ctxs[c]->ev_xctx, ctxs[c]->stream));
@@ -1111,9 +852,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.lut_w = exact ? (const void*)ctx->lut_w : (const void*)ctx->lut_wf;
     A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
-    A.claim = reinterpret_cast<int*>(ubase + tbytes + ubytes);
-    A.punits = reinterpret_cast<const int4*>(ubase + tbytes + ubytes + 16);
-    A.n_punits = (int)punits.size();
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env < 0 ? 0 : sleep_env ? sleep_env : 20;
 
@@ -1150,22 +888,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
             if (full) A3_LAUNCH(1, true, BIG_, RB_, NEARB_, CL_, GRID_, THREADS_); else A3_LAUNCH(1, false, BIG_, RB_, NEARB_, CL_, GRID_, THREADS_); \
         }                                                                                              \
     } while (0)
-    if (paths_mode) {
-        // two persistent launches (leaf->root, root->leaf + WTA) over every path of every tree of the launch
-#define AP_LAUNCH(NH_, FULL_)                                                                                                   \
-    do {                                                                                                                       \
-        int per_sm = 0;                                                                                                        \
-        S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agg_paths<NH_, FULL_, false>, 256, 0));               \
-        const int grid = ctx->num_sms * std::max(1, per_sm);                                                                   \
-        k_agg_paths<NH_, FULL_, false><<<grid, 256, 0, ctx->stream>>>(A);                                                      \
-        S3_LAUNCH_CHECK();                                                                                                     \
-        k_agg_paths<NH_, FULL_, true><<<grid, 256, 0, ctx->stream>>>(A);                                                       \
-        S3_LAUNCH_CHECK();                                                                                                     \
-    } while (0)
-        if (NH == 2) { if (full) AP_LAUNCH(2, true); else AP_LAUNCH(2, false); }
-        else { if (full) AP_LAUNCH(1, true); else AP_LAUNCH(1, false); }
-#undef AP_LAUNCH
-    } else {
     if (n_cl) {
         S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         S3_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
@@ -1184,7 +906,6 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         A3_DISPATCH(false, 128, 32, 1, n_small, 512);  // 64 KB ring: two trees per SM
     }
     if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    }
 #undef A3_DISPATCH
 #undef A3_LAUNCH
 #undef A3_LAUNCH_T

@@ -80,7 +80,7 @@ static void free_view(View& V) {
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
     DFREE(V.tree_start); DFREE(V.tree_depth); DFREE(V.unit_tree);
-    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits); DFREE(V.path_nodes); DFREE(V.paths); DFREE(V.path_scratch); DFREE(V.path_flags); V.path_flags_cap = 0; V.paths_ready = false;
+    DFREE(V.node_pixel); DFREE(V.pixel_node); DFREE(V.parent); DFREE(V.level); DFREE(V.pw); DFREE(V.node_up); DFREE(V.node_dn); DFREE(V.leaf_bits);
     DFREE(V.lvl_start);
     DFREE(V.cost); DFREE(V.aup); V.cost_cap = V.aup_cap = 0;
     DFREE(V.disp_i); DFREE(V.best); DFREE(V.abc); DFREE(V.min_cost); DFREE(V.disp_f); DFREE(V.lr_mask);
@@ -152,7 +152,6 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->fh_ctas = 0;
     p->fh_threads = 0;
     p->agg_cluster_nodes = 0;
-    p->agg_paths = 0;
     p->fh_cluster = 0;
     p->pms_cost_mode = 0;
     p->pm_alpha = 0.9f;

@@ -755,41 +755,6 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     }
 }
 
-// ---- heavy-path decomposition (aggregate3.cu: k_agg_paths).  The heavy child of a node is its FIRST child — the one the
-// reference adds last (children are summed in reverse BFS order, Stereo3DMST.cpp:125-137), so a warp that walks a path
-// upwards holds exactly the operand of the last multiply-add of every node in registers.  top(v) and the distance to it
-// by pointer jumping over the "heavy parent" links (ceil(log2 N) rounds); the paths are laid out in the
-// order of their tops, every path leaf first.
-__global__ void k_path_init(int N, const NodeUp* __restrict__ node_up, const int* __restrict__ parent, int2* __restrict__ hd, int* __restrict__ is_top,
-                            int* __restrict__ len_at) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int p = parent[v];
-    const bool heavy = p != v && node_up[p].child_begin == v;
-    hd[v] = heavy ? make_int2(p, 1) : make_int2(v, 0);
-    is_top[v] = !heavy;
-    len_at[v] = 0;
-}
-__global__ void k_path_jump(int N, const int2* __restrict__ in, int2* __restrict__ out) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int2 a = in[v];
-    const int2 b = in[a.x];
-    out[v] = make_int2(b.x, a.y + b.y);
-}
-__global__ void k_path_len(int N, const NodeUp* __restrict__ node_up, const int2* __restrict__ hd, int* __restrict__ len_at) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < N && (node_up[v].child_count & 7) == 0) len_at[hd[v].x] = hd[v].y + 1;  // a path ends in exactly one leaf
-}
-__global__ void k_path_scatter(int N, const int2* __restrict__ hd, const int* __restrict__ is_top, const int* __restrict__ len_at, const int* __restrict__ off,
-                               const int* __restrict__ rank, int* __restrict__ path_nodes, int2* __restrict__ paths) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int2 h = hd[v];
-    path_nodes[off[h.x] + len_at[h.x] - 1 - h.y] = v;
-    if (is_top[v]) paths[rank[v]] = make_int2(off[v], len_at[v]);
-}
-
 // node_dn -> the flat per-node arrays the other stages and the parity dumps read (off the BFS critical path)
 __global__ void k_bfs_unpack(int N, const int4* __restrict__ node_dn, int* __restrict__ node_pixel, int* __restrict__ parent,
                              int* __restrict__ level, uint16_t* __restrict__ pw, uint32_t* __restrict__ leaf_bits) {
@@ -998,7 +963,6 @@ int s3_forest_post(s3dmst_ctx* ctx, int mask) {
             S3_LAUNCH_CHECK();
             V.max_depth = -1;  // tree depths stay on the device until somebody asks (s3_forest_depths)
             V.adj_ready = false;
-            V.paths_ready = false;
             V.forest_ready = true;   // the device side is complete in stream order; T and the sizes reach the host lazily
             V.cost_ready = false;
             V.agg_ready = false;
@@ -1034,40 +998,6 @@ int s3_forest_finish_host(s3dmst_ctx* ctx) {
     return 0;
 }
 
-int s3_forest_paths(s3dmst_ctx* ctx, int view) {
-    View& V = ctx->v[view];
-    if (!V.forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "forest paths: no forest");
-    if (V.paths_ready) return 0;
-    const int N = ctx->N, TB = 256;
-    if (!V.path_nodes) S3_CUDA(cudaMalloc(&V.path_nodes, sizeof(int) * (size_t)N));
-    if (!V.paths) S3_CUDA(cudaMalloc(&V.paths, sizeof(int2) * (size_t)N));
-    if (!V.path_scratch) S3_CUDA(cudaMalloc(&V.path_scratch, sizeof(int) * (3 * (size_t)N + 8192)));
-    int2* hd0 = reinterpret_cast<int2*>(V.e_ra);      // forest-kernel scratch, idle once the forest is built: [N] int2 each
-    int2* hd1 = reinterpret_cast<int2*>(V.e_rb);
-    int* is_top = V.scan_tmp;                          // [N]
-    int* len_at = V.minpix;                            // [N] (the labelling is done with it)
-    int* rank = V.path_scratch;                        // [N + 1]
-    int* off = V.path_scratch + N + 8;                 // [N + 1]
-    int* bsum = V.path_scratch + 2 * (N + 8);          // block totals of the scans
-    k_path_init<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_up, V.parent, hd0, is_top, len_at);
-    S3_LAUNCH_CHECK();
-    int rounds = 1;
-    while ((1 << rounds) < N) rounds++;   // a path can be as long as its tree is deep
-    for (int r = 0; r < rounds; r++) {
-        k_path_jump<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, hd0, hd1);
-        S3_LAUNCH_CHECK();
-        std::swap(hd0, hd1);
-    }
-    k_path_len<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, V.node_up, hd0, len_at);
-    S3_LAUNCH_CHECK();
-    S3_TRY(scan_exclusive(ctx, N, nullptr, N, is_top, rank, bsum, V.counters + S3_CNT_NPATH));
-    S3_TRY(scan_exclusive(ctx, N, nullptr, N, len_at, off, bsum, nullptr));
-    k_path_scatter<<<(N + TB - 1) / TB, TB, 0, ctx->stream>>>(N, hd0, is_top, len_at, off, rank, V.path_nodes, V.paths);
-    S3_LAUNCH_CHECK();
-    V.paths_ready = true;
-    return 0;
-}
-
 int s3_forest_stage_mask(s3dmst_ctx* ctx, int mask) {
     S3_TRY(s3_forest_pre(ctx, mask));
     S3_TRY(s3_fh_launch(ctx, mask));
@@ -1095,7 +1025,6 @@ int s3_forest_finalize_host(s3dmst_ctx* ctx, int view) {
     ctx->forest_pending &= ~(1 << view);
     V.max_depth = -1;
     V.adj_ready = false;
-    V.paths_ready = false;
     V.forest_ready = true;
     V.cost_ready = false;
     V.agg_ready = false;

@@ -67,15 +67,6 @@ struct View {
     uint16_t* pw = nullptr;     // [N]
     NodeUp* node_up = nullptr;  // [N]
     int4* node_dn = nullptr;    // [N] {parent, parent weight, level | flags, pixel}: the root->leaf pass record
-    // heavy-path decomposition of the forest (forest.cu: s3_forest_paths, built lazily for the path-parallel aggregation):
-    // a node's heavy child is its first child; a path is a maximal chain of heavy links, named by its top node
-    int* path_nodes = nullptr;    // [N] the nodes of every path, leaf first, top last; paths in the order of their tops
-    int2* paths = nullptr;        // [P] {first entry in path_nodes, length}; P at counters[S3_CNT_NPATH]
-    int* path_scratch = nullptr;  // [3N + 8192] scans
-    int* path_flags = nullptr;    // [2][slices][N] completion stamps of the path walks (up: path tops, down: nodes with light children)
-    size_t path_flags_cap = 0;
-    int path_epoch = 0;           // stamp of the current launch (the arrays are never cleared)
-    bool paths_ready = false;
     uint32_t* leaf_bits = nullptr;  // [N/32 + 1] bit v = node v is a leaf (prefetch target selection on the way down)
     int* lvl_start = nullptr;   // [N + T + 1]; tree t's level offsets start at tree_start[t] + t
     // tree adjacency graph (Stereo3DMST.cpp:377-384) as a device CSR, built lazily (proposal generation, parity dumps)
@@ -161,7 +152,6 @@ struct s3dmst_ctx {
 };
 
 #define S3_MAX_ROUNDS 65536
-#define S3_CNT_NPATH (S3_MAX_ROUNDS - 44)  // View::counters slot: number of heavy paths
 #define S3_FH_MAX_VIEWS 16        // views (2 per frame) one forest-kernel launch serves
 #define S3_FH_ROUNDS 8192         // round cap of the forest kernel (per-round counters)
 #define S3_FH_MAX_CTAS 256        // upper bound on the cooperative grid of the forest kernel
@@ -204,7 +194,6 @@ int s3_forest_pre(s3dmst_ctx* ctx, int mask);                     // image stage
 int s3_forest_post(s3dmst_ctx* ctx, int mask);                    // labelling + BFS (asynchronous)
 int s3_forest_finish_host(s3dmst_ctx* ctx);                       // tree count / sizes -> host (waits for the copy s3_forest_post queued)
 int s3_forest_finalize_host(s3dmst_ctx* ctx, int view);
-int s3_forest_paths(s3dmst_ctx* ctx, int view);                   // heavy-path decomposition (lazy, asynchronous)
 int s3_forest_depths(s3dmst_ctx* ctx, int view);                  // forest.cu: lazy D2H of the tree depths           // forest.cu: unit order, depths
 int s3_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const uint16_t* map_fxy, int W, int H);  // rectify.cu
 int s3_remap_raw_pair(s3dmst_ctx* ctx, const uint8_t* left_raw, const uint8_t* right_raw, int sw, int sh, int stride);

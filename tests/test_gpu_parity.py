@@ -123,15 +123,14 @@ def test_cost_volume_matches_oracle(api, oracle, W, H, D, seed):
 
 
 @pytest.mark.parametrize("W,H,D,seed,c,ms,nat", CASES[:7])
-@pytest.mark.parametrize("own_forest,cluster,paths", [(False, -1, -1), (True, -1, -1), (True, 48, -1), (True, -1, 1), (False, -1, 1)])
-def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat, own_forest, cluster, paths):
-    """cluster = 48: every tree of >= 48 nodes is walked by a thread-block cluster of 8 CTAs (the giant-tree kernel);
-    paths = 1: the path-parallel kernel (k_agg_paths) instead of the per-tree walk."""
+@pytest.mark.parametrize("own_forest,cluster", [(False, -1), (True, -1), (True, 48)])
+def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat, own_forest, cluster):
+    """cluster = 48: every tree of >= 48 nodes is walked by a thread-block cluster of 8 CTAs (the giant-tree kernel)."""
     L, R, _ = make(W, H, D, seed, nat)
     F = oracle.forest(L, c=c, min_size=ms)
     lv, _ = oracle.cost_adgrad(L, R, D)
     disp_o, best_o, agg_o = oracle.aggregate_dense(F, lv, want_agg=True)
-    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, keep_aggregated=1, agg_cluster_nodes=cluster, agg_paths=paths)
+    eng = api.Stereo3DMST(fh_c=c, min_cc_size=ms, keep_aggregated=1, agg_cluster_nodes=cluster)
     eng.set_images(L, R)
     if own_forest:
         eng.build_forest(0)
@@ -144,9 +143,6 @@ def test_dense_aggregation_matches_oracle(api, oracle, W, H, D, seed, c, ms, nat
     assert np.array_equal(disp, disp_o)                     # integer WTA disparities: bit-exact
     assert np.array_equal(bits(best), bits(best_o))
     np.testing.assert_allclose(agg, agg_o, rtol=1e-4)       # the tolerance north_star states, for the record
-    if paths > 0:                                           # a second launch on the same context: new stamps epoch
-        d2, b2 = eng.aggregate_dense(0)
-        assert np.array_equal(d2, disp_o) and np.array_equal(bits(b2), bits(best_o))
     eng.close()
 
 
@@ -171,13 +167,13 @@ def test_dense_aggregation_config_independent(api, oracle, threads, cap):
     eng.close()
 
 
-@pytest.mark.parametrize("cluster,paths", [(-1, -1), (100, -1), (-1, 1)])
-def test_dense_label_slices_and_ranges(api, oracle, cluster, paths):
+@pytest.mark.parametrize("cluster", [-1, 100])
+def test_dense_label_slices_and_ranges(api, oracle, cluster):
     W, H, D = 120, 80, 200   # > 128 labels: several (tree, slice) units + the combine kernel
     L, R, _ = make(W, H, 24, 13, 0)
     F = oracle.forest(L, c=900.0, min_size=40)
     lv, _ = oracle.cost_adgrad(L, R, D)
-    eng = api.Stereo3DMST(fh_c=900.0, min_cc_size=40, agg_cluster_nodes=cluster, agg_paths=paths)
+    eng = api.Stereo3DMST(fh_c=900.0, min_cc_size=40, agg_cluster_nodes=cluster)
     eng.set_images(L, R)
     eng.build_forest(0)
     eng.set_cost_volume(0, lv, ingest=False)
@@ -458,14 +454,6 @@ def test_batch_mixed_c4_shapes(api, oracle):
             engs.append(e)
         outs = api.run_dense_batch(engs, D, fill=True)
         Hh, Ww = frames[0][0].shape[:2]
-        pe = [api.Stereo3DMST(fh_ctas=36, agg_paths=1) for _ in frames]   # the same batch through the path-parallel kernel
-        for e, (Li, Ri) in zip(pe, frames):
-            e.set_images(Li, Ri)
-        pouts = api.run_dense_batch(pe, D, fill=True)
-        for (dl, dr), (pl, pr) in zip(outs, pouts):
-            assert np.array_equal(bits(dl), bits(pl)) and np.array_equal(bits(dr), bits(pr))
-        for e in pe:
-            e.close()
         for (Li, Ri), (dl, dr), e in zip(frames, outs, engs):
             single = api.Stereo3DMST()
             single.set_images(Li, Ri)
