@@ -93,7 +93,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
     const size_t n = N;
     S3_CUDA(dalloc(&V.bgr, 3 * n)); S3_CUDA(dalloc(&V.raw4, n)); S3_CUDA(dalloc(&V.med, n)); S3_CUDA(dalloc(&V.gray, n));
     S3_CUDA(dalloc(&V.ew, 2 * n));
-    { unsigned char* b = nullptr; S3_CUDA(dalloc(&b, 32 * n)); V.uf_comp = b; }
+    { unsigned char* b = nullptr; S3_CUDA(dalloc(&b, 16 * n)); V.uf_comp = b; }
     S3_CUDA(dalloc(&V.uf_parent, n));
     S3_CUDA(dalloc(&V.adjw, n)); S3_CUDA(dalloc(&V.bfs_front, n));
     S3_CUDA(dalloc(&V.uf_resv, n));

@@ -38,18 +38,20 @@
 #define CNT_ACT (S3_MAX_ROUNDS - 20)  // [2] live-list lengths of the FH rounds
 #define ROUND_CAP (S3_FH_ROUNDS - 32)
 
-// Component record: everything a round reads about a component (a root) sits in ONE 32-byte sector (the forest kernel
-// is bound by random sector traffic: L2 for one pair, DRAM for a batch).  The union-find parents stay in a compact int
-// array: the find chains walk ordinary pixels, whose neighbours share sectors (packing them too was measured 2x slower).  The kernels address the fields
-// through strided pointers: int fields stride FHC_I ints, 64-bit fields stride FHC_L.
-struct __align__(32) FHComp {
-    unsigned long long pick[2];  // minimum live edge key of the component, by round parity
-    int size;                    // pixels of the component (valid at the root)
-    int lastw;                   // weight of the last accepted edge (valid at the root)
-    int pad[2];
+// Component record: everything a round reads about a component (a root) is ONE 16-byte load (the forest kernel is
+// bound by random sector requests: L2 for one pair, DRAM for a batch).  The pick word cleans itself: a posted key carries
+// (S3_FH_ROUNDS - round) above the weight, so a value left by an earlier round is larger than anything the current
+// round posts and simply loses the atomicMin — no second buffer, no clearing stores.  The union-find parents stay in a
+// compact int array: the find chains walk ordinary pixels, whose neighbours share sectors (packing them too was measured
+// 2x slower).  The kernels address the fields through strided pointers: int fields stride FHC_I ints, 64-bit fields FHC_L.
+struct __align__(16) FHComp {
+    unsigned long long pick;  // minimum live edge key of the component in the round named by its prefix
+    int size;                 // pixels of the component (valid at the root)
+    int lastw;                // weight of the last accepted edge (valid at the root)
 };
-#define FHC_I 8
-#define FHC_L 4
+#define FHC_I 4
+#define FHC_L 2
+#define FH_RSHIFT 42          // pick = (S3_FH_ROUNDS - round) << 42 | w << 32 | edge id   (w < 1024)
 
 struct __align__(16) FHEntry {
     unsigned long long key;  // (w << 32) | edge id; bit 63 = accepted last round (ra = the root that hooked), bit 62 = rejected
@@ -70,7 +72,7 @@ struct FHArgs {
     int* parent;
     int* size;
     int* lastw;
-    unsigned long long* pick[2];  // [N] minimum live key per component, double-buffered by round parity
+    unsigned long long* pick;     // [N] minimum live key per component (round-prefixed, see FHComp)
     FHEntry* ent[2];              // [2N] live-edge lists, ping-pong
     unsigned long long* resv;
     uint8_t* mask;
@@ -119,8 +121,8 @@ __device__ __forceinline__ void uf_find2(int* parent, int& x, int& y) {
 }
 
 // segment-graph.h:27,80 — THRESHOLD(size,c) is a float division (Q2), added to a double w
-__device__ __forceinline__ bool uf_open(const FHArgs& A, int r, int w) {
-    const double thr = (double)__ldcg(A.lastw + FHC_I * r) + (double)__fdiv_rn(A.c, (float)__ldcg(A.size + FHC_I * r));
+__device__ __forceinline__ bool uf_open(float c, int size, int lastw, int w) {
+    const double thr = (double)lastw + (double)__fdiv_rn(c, (float)size);
     return (double)w <= thr;
 }
 
@@ -220,8 +222,8 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
             }
             const FHEntry* src = A.ent[par] + seg;
             FHEntry* dst = A.ent[par ^ 1] + seg;
-            unsigned long long* pick = A.pick[par];
-            unsigned long long* pick_prev = A.pick[par ^ 1];
+            unsigned long long* pick = A.pick;
+            const unsigned long long rtag = (unsigned long long)(S3_FH_ROUNDS - round) << FH_RSHIFT;
             // ---- phase 1: settle last round's decisions, re-root the survivors, post keys, compact
             const int n_new = band_pos - band_lo_vi;
             const int share = (n_new + nblk - 1) / nblk;
@@ -236,8 +238,6 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
                 en.key = FH_NOKEY; en.ra = 0; en.rb = 0;
                 if (pos < my_src) {
                     en = src[pos];
-                    __stcg(pick_prev + FHC_L * en.ra, FH_NOKEY);  // clean the buffer the previous round posted into
-                    __stcg(pick_prev + FHC_L * en.rb, FH_NOKEY);
                     if (en.key & FH_HOOKED) {
                         // accepted last round, en.ra hooked: its size flows to the root it ended under
                         const int R = uf_find(A.parent, en.ra);
@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
                     live = en.ra != en.rb;
                 }
                 if (live) {
-                    atomicMin(pick + FHC_L * en.ra, en.key);
-                    atomicMin(pick + FHC_L * en.rb, en.key);
+                    atomicMin(pick + FHC_L * en.ra, rtag | en.key);
+                    atomicMin(pick + FHC_L * en.rb, rtag | en.key);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, live);
                 if (bal) {
@@ -275,9 +275,11 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
             // ---- phase 2: decide every edge that is the minimum of one of its components
             for (int pos = threadIdx.x; pos < my_cnt; pos += blockDim.x) {
                 FHEntry en = dst[pos];
-                const unsigned long long ka = __ldcg(pick + FHC_L * en.ra), kb = __ldcg(pick + FHC_L * en.rb);
+                // one 16-byte load per endpoint: {pick, size, lastw}
+                const int4 ca = __ldcg(reinterpret_cast<const int4*>(pick + FHC_L * en.ra)), cb = __ldcg(reinterpret_cast<const int4*>(pick + FHC_L * en.rb));
+                const unsigned long long ka = ((unsigned long long)(unsigned)ca.y << 32 | (unsigned)ca.x) ^ rtag, kb = ((unsigned long long)(unsigned)cb.y << 32 | (unsigned)cb.x) ^ rtag;
                 const int wa = (int)(ka >> 32), wb = (int)(kb >> 32), w = (int)(en.key >> 32);
-                if (!uf_open(A, en.ra, wa) || !uf_open(A, en.rb, wb)) {  // (1): a dead endpoint
+                if (!uf_open(A.c, ca.z, ca.w, wa) || !uf_open(A.c, cb.z, cb.w, wb)) {  // (1): a dead endpoint
                     dst[pos].key = en.key | FH_REJECT;
                     continue;
                 }
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(1024, 2) k_fh_merge(FHArgs2 AA) {
                     A.mask[(uint32_t)en.key] = 1;
                     int frm, to;
                     if (pa && pb) {  // only one side of a mutual pick hooks: the smaller component goes under the larger (shorter paths)
-                        const int sa = __ldcg(A.size + FHC_I * en.ra), sb = __ldcg(A.size + FHC_I * en.rb);
+                        const int sa = ca.z, sb = cb.z;
                         const bool a_hooks = sa < sb || (sa == sb && en.ra > en.rb);
                         frm = a_hooks ? en.ra : en.rb; to = a_hooks ? en.rb : en.ra;
                     }
@@ -393,11 +395,9 @@ __global__ void k_uf_init(int N, FHComp* comp, int* parent, unsigned long long* 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     FHComp c;
-    c.pick[0] = FH_NOKEY;
-    c.pick[1] = FH_NOKEY;
+    c.pick = FH_NOKEY;
     c.size = 1;
     c.lastw = 0;
-    c.pad[0] = c.pad[1] = 0;
     comp[i] = c;
     parent[i] = i;
     resv[i] = ~0ull;
@@ -775,7 +775,7 @@ static void fill_fh_args(s3dmst_ctx* ctx, View& V, FHArgs& A) {
     A.ew = V.ew; A.elist = V.elist; A.lvl_off = V.lvl_off;
     FHComp* comp = reinterpret_cast<FHComp*>(V.uf_comp);
     A.parent = V.uf_parent; A.size = &comp->size; A.lastw = &comp->lastw; A.resv = V.uf_resv;
-    A.pick[0] = &comp->pick[0]; A.pick[1] = &comp->pick[1];
+    A.pick = &comp->pick;
     A.ent[0] = reinterpret_cast<FHEntry*>(V.fh_ent[0]); A.ent[1] = reinterpret_cast<FHEntry*>(V.fh_ent[1]);
     // Live-list band.  A wide band means fewer rounds (latency: one pair alone on the GPU, 16384/65536), a narrow one
     // fewer futile re-visits of edges whose turn has not come (throughput: contexts set up for batching share the GPU and

@@ -34,7 +34,7 @@ struct View {
     bool plane_ready = false;
     uint16_t* ew = nullptr;    // [2N] edge weights by canonical id
     // ---- union-find / forest construction
-    void* uf_comp = nullptr;   // [N] x 32 B component records (forest.cu: FHComp)
+    void* uf_comp = nullptr;   // [N] x 16 B component records (forest.cu: FHComp)
     int* uf_parent = nullptr;  // [N] union-find parents
     void* fh_ent[2] = {nullptr, nullptr};                 // [2N] x 16 B live-edge lists of the FH rounds (ping-pong)
     unsigned long long* uf_resv = nullptr;  // [N] merge reservation key
