@@ -747,6 +747,19 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
     // Front: forest + cost volume of every frame, queued on the frames' own streams by this one host thread.  Nothing
     // here waits for the device: the tree counts and sizes travel to the host behind the forest kernels, and the joint
     // aggregation below is the first thing that needs them.
+    static const int joint_env = getenv("S3_FH_JOINT") ? atoi(getenv("S3_FH_JOINT")) : 0;   // development: one forest launch for the batch
+    if ((phases & 1) && joint_env && n > 1 && 2 * n <= S3_FH_MAX_VIEWS) {
+        for (int c = 0; c < n; c++) {
+            memset(ctxs[c]->ev_set, 0, sizeof ctxs[c]->ev_set);
+            S3_TRY(s3_forest_pre(ctxs[c], 3));
+        }
+        S3_TRY(s3_fh_launch_multi(ctxs, n, 3));
+        for (int c = 0; c < n; c++) {
+            S3_TRY(s3_forest_post(ctxs[c], 3));
+            S3_TRY(s3_cost_adgrad(ctxs[c], D, 0));
+        }
+        phases &= ~1;
+    }
     for (int c = 0; (phases & 1) && c < n; c++) {
         s3dmst_ctx* cx = ctxs[c];
         const int r = [&]() -> int {

@@ -102,6 +102,10 @@ __device__ __forceinline__ void uf_find2(int* parent, int& x, int& y) {
         int px = x, py = y;
         if (!dx) px = __ldcg(parent + x);
         if (!dy) py = __ldcg(parent + y);
+        if (px == py) {  // the chains have met: one component, whatever its root is (most edges by the time their level comes)
+            x = y = px;
+            break;
+        }
         if (!dx) {
             if (px == x) dx = true;
             else { dx4 = cx; cx = bx; bx = ax; ax = x; x = px; }
