@@ -62,6 +62,10 @@ typedef struct s3dmst_params {
                            frame, for contexts that run beside others in a batch (measured best at C2: 36 for 8
                            frames; also selects the narrower live-edge band, forest.cu fill_fh_args)           */
     int fh_threads;     /* 0 = 1024; threads per CTA of the forest kernel */
+    int fuse_cost;      /* dense runs (run_dense, run_dense_batch, aggregate_dense_sharded) on the library's AD+gradient cost:
+                           0 / 1 = the aggregation kernel computes the matching cost itself and no volume is built
+                           (s3dmst_get_cost_volume / s3dmst_aggregate_dense build it on demand afterwards); -1 = build the
+                           volume first.  Results are bit-identical either way.                                      */
     int fh_cluster;     /* 0: the forest kernel is a cooperative grid with a software barrier per view; 8 or 16: every view gets one
                            thread-block cluster of that many CTAs and the hardware cluster barrier                      */
     int pms_cost_mode;  /* data term of the 3D-label (PatchMatch) search: 0 = compute3DLabelCost on the cost volume (the

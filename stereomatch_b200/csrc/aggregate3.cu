@@ -64,6 +64,9 @@ struct Agg3View {
     const uint8_t* img_other;
     const float* grad_self;
     const float* grad_other;
+    // dense mode with the matching cost computed in the kernel (FUSE): {packed BGR, gray} of this view's and the other view's image
+    const uint2* m_self;
+    const uint2* m_other;
 };
 
 struct Agg3Args {
@@ -92,6 +95,24 @@ struct Agg3Args {
 };
 
 __device__ __forceinline__ uint32_t a3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Truncated colour + gradient matching cost of one (pixel, label) — the expression of k_cost_adgrad (cost.cu;
+// PatchMatchStereoGPU.cu:1482-1550), operation for operation, so that a dense run that never materialises the volume
+// aggregates bit-identical numbers.  ct = the 22-entry colour-term table (L1 distance saturates at 21).
+__device__ __forceinline__ float a3_adgrad(const float* ct, int view, uint32_t me, float me_g, float me_gn, uint32_t o, float og, float ogn) {
+    const int l1 = (int)__dp4a(__vabsdiffu4(o, me), 0x00010101u, 0u);
+    const float ctv = ct[min(l1, 21)];
+    const float g = view == 0 ? S3_FADD(S3_FSUB(me_g, og), S3_FSUB(ogn, me_gn)) : S3_FADD(S3_FSUB(og, me_g), S3_FSUB(me_gn, ogn));
+    const float ag = fabsf(g);
+    const float gterm = ag < 2.0f ? ag : 2.0f;
+    return S3_FADD(ctv, S3_FMUL(0.89f, gterm));
+}
+__global__ void k_pack_match(int N, const uchar4* __restrict__ raw4, const float* __restrict__ gray, uint2* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const uchar4 o = raw4[p];
+    out[p] = make_uint2((uint32_t)o.x | ((uint32_t)o.y << 8) | ((uint32_t)o.z << 16), __float_as_uint(gray[p]));
+}
 __device__ __forceinline__ int a3_ld_acquire(uint32_t a) {
     int v;
     asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -246,9 +267,10 @@ template <> struct A3T<float> {
 // nodes closer than NEAR x CL.  Progress words and ring rows of other CTAs are read through distributed shared memory
 // (mapa + ld.acquire.cluster / ld.shared::cluster), published with st.release.cluster; the far path through L2 is the
 // same (the release is cluster scope, so global stores before it are visible to the other SMs of the cluster).
-template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS, int CL>
+template <typename T, int NH, bool FULL, bool BIG, int A3_R, int A3_NEAR, bool PMS, int CL, bool FUSE = false>
 __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3Args A) {
     static_assert(CL == 1 || BIG, "a cluster walks a tree with 32 warps per CTA");
+    static_assert(!(FUSE && PMS), "the fused matching cost belongs to the dense mode");
     static_assert(CL == 1 || CL == 2 || CL == 4 || CL == 8, "portable cluster sizes");
     constexpr int LOGCL = CL == 1 ? 0 : CL == 2 ? 1 : CL == 4 ? 2 : 3;
     constexpr int NEAR_E = A3_NEAR * CL;   // hand-over distance and ring rows of the whole cluster
@@ -274,6 +296,14 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     const size_t DA = PMS ? (size_t)64 : Dp;        // running-sum row length (proposal mode: a [node][64] scratch)
     __shared__ float s_lab[PMS ? 64 * 3 : 1];
     __shared__ int s_nlad;
+    __shared__ float s_ct[FUSE ? 22 : 1];  // colour term of L1 = i: 0.11f * min((float)((double)i * 0.33333333333), 7.0f)
+    if constexpr (FUSE) {
+        if (tid < 22) {
+            float ctv = (float)S3_DMUL((double)(float)tid, 0.33333333333);
+            ctv = ctv < 7.0f ? ctv : 7.0f;
+            s_ct[tid] = S3_FMUL(0.11f, ctv);
+        }
+    }
     const int p_lo = PMS ? A.prop_off[t] : 0, p_hi = PMS ? A.prop_off[t + 1] : 1;
     // passes over the tree: dense mode one; proposal mode one per batch of 64 listed proposals, then (A.gen) one for the
     // refinement ladder this kernel generates itself from the label the tree holds after those (MST_PMS, :584-625)
@@ -392,6 +422,43 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
     {
         int v = top - gw;
         const char* nup_p = reinterpret_cast<const char*>(V.node_up + v);
+        // FUSE: the matching cost of this lane's labels at node vv, straight from the two images (cost.cu: k_cost_adgrad; the
+        // left volume reads the right image at x - d, the right volume the left image at x + d; labels without a
+        // counterpart cost 3.0, row padding 0).  Issued where the cost row would be loaded: after the publish, in the
+        // shadow of the wait for the next node's children.
+        auto fused_cost = [&](int vv, float2* cf) {
+            const int pix = __ldg(V.node_pixel + vv);
+            const int x = pix - (pix / A.img_w) * A.img_w;
+            const int view = unit.x & 1;
+            const uint2 me = __ldg(V.m_self + pix);
+            const bool has_next = x + 1 < A.img_w;
+            const float me_g = __uint_as_float(me.y);
+            const float me_gn = has_next ? __uint_as_float(__ldg(V.m_self + pix + 1).y) : 0.0f;
+            const int dvalid = view == 0 ? (has_next ? x + 1 : 0) : A.img_w - 1 - x;
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                cf[h] = make_float2(0.f, 0.f);
+                if (!act[h]) continue;
+                const int dA = l0 + h * 64 + 2 * lane;
+                const bool vA = dA < A.D && dA < dvalid, vB = dA + 1 < A.D && dA + 1 < dvalid;
+                float cA = 3.0f, cB = 3.0f;  // bad_cost
+                if (vA) {
+                    // three consecutive pixels of the other view cover both labels and their right neighbours
+                    const uint2* q = V.m_other + (view == 0 ? pix - dA - 1 : pix + dA);
+                    const uint2 q1 = __ldg(q + 1);
+                    uint2 q0 = make_uint2(0u, 0u), q2 = make_uint2(0u, 0u);
+                    if (view == 0 ? vB : true) q0 = __ldg(q);
+                    if (view == 0 ? true : vB) q2 = __ldg(q + 2);
+                    const uint2 a = view == 0 ? q1 : q0, b = view == 0 ? q0 : q1;
+                    const float an = __uint_as_float(view == 0 ? q2.y : q1.y), bn = __uint_as_float(view == 0 ? q1.y : q2.y);
+                    cA = a3_adgrad(s_ct, view, me.x, me_g, me_gn, a.x, __uint_as_float(a.y), an);
+                    if (vB) cB = a3_adgrad(s_ct, view, me.x, me_g, me_gn, b.x, __uint_as_float(b.y), bn);
+                }
+                if (dA >= A.D) cA = 0.0f;
+                if (dA + 1 >= A.D) cB = 0.0f;
+                cf[h] = make_float2(cA, cB);
+            }
+        };
         const char* cost_p = reinterpret_cast<const char*>(V.cost + (size_t)v * Dp + (PMS ? 0 : l0 + 2 * lane));
         char* aup_p = reinterpret_cast<char*>(aupT + (size_t)v * DA + aoff + 2 * lane);
         const char* aup_lane0 = reinterpret_cast<const char*>(aupT + aoff + 2 * lane);  // + c * DA * sizeof(T) for a far child
@@ -406,6 +473,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
             nu = *reinterpret_cast<const int4*>(nup_p);
             if constexpr (CL > 1) par = V.node_dn[v].x;
             if constexpr (PMS) cf[0] = pms_cost(v);
+            else if constexpr (FUSE) fused_cost(v, cf);
             else {
 #pragma unroll
                 for (int h = 0; h < NH; h++)
@@ -514,6 +582,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 nu = *reinterpret_cast<const int4*>(nup_p - (long long)WT * 16);
                 if constexpr (CL > 1) par = V.node_dn[vn].x;
                 if constexpr (PMS) cf[0] = pms_cost(vn);
+                else if constexpr (FUSE) fused_cost(vn, cf);
                 else {
 #pragma unroll
                     for (int h = 0; h < NH; h++)
@@ -521,7 +590,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
                 }
             }
             // pull this warp's row of A3_PF rounds from now into L2 (one 128-byte line per lane)
-            if (lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base && !(PMS && A.cost_mode))
+            if (!FUSE && lane < (PMS ? (int)((Dp * 4 + 127) / 128) : NH * 2) && v - A3_PF * WT >= base && !(PMS && A.cost_mode))
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(cost_p - (PMS ? 0 : 2 * lane * 4) - A3_PF * strideC + lane * 128));
             if (store_late) {  // read back on the way down
 #pragma unroll
@@ -753,8 +822,11 @@ static int agg3_launch(s3dmst_ctx* ctx, K kernel, int grid, int threads, size_t 
 // independent trees instead of waiting on the deepest tree of a single pair.  Runs on ctxs[0]'s stream; the other
 // contexts' streams are ordered before and after it with events.
 // Returns 1 (and does nothing) if this kernel cannot serve the request, so the caller falls back to the simple one.
-int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1) {
+// fuse != 0: the matching cost is computed inside the up pass from the images (no cost volume is read; the views need
+// images, forests and V.D / V.aup from s3_ensure_volume).
+int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1, int fuse) {
     s3dmst_ctx* ctx = ctxs[0];
+    if (fuse && !ctx->P.exact) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: the fused matching cost needs the exact mode");
     int first = -1;
     for (int view = 0; view < 2 && first < 0; view++)
         if (views_mask & (1 << view)) first = view;
@@ -770,7 +842,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         for (int view = 0; view < 2; view++) {
             if (!(views_mask & (1 << view))) continue;
             View& V = ctxs[c]->v[view];
-            if (!V.forest_ready || !V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense: forest and cost volume required");
+            if (!V.forest_ready || !(fuse ? V.aup != nullptr && V.D > 0 : V.cost_ready)) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense: forest and cost volume required");
             if (V.D != Dv) return s3_fail(ctx, S3DMST_E_ARG, "aggregate_dense: views hold different D");
         }
     }
@@ -826,6 +898,18 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
             G.cost = V.cost; G.aup = V.aup;
             G.disp = V.disp_i; G.best = V.best; G.pdisp = pdisp[2 * c + view]; G.pbest = pbest[2 * c + view];
         }
+        if (fuse) {  // {BGR, gray} of both images, 8 bytes per pixel (on the frame's own stream, before the hand-over below)
+            for (int view = 0; view < 2; view++) {
+                View& V = cx->v[view];
+                if (!V.match8) S3_CUDA(cudaMalloc(&V.match8, sizeof(uint2) * ((size_t)cx->N + 2)));
+                k_pack_match<<<(cx->N + 255) / 256, 256, 0, cx->stream>>>(cx->N, V.raw4, V.gray, V.match8);
+                S3_LAUNCH_CHECK();
+            }
+            for (int view = 0; view < 2; view++) {
+                table[2 * c + view].m_self = cx->v[view].match8;
+                table[2 * c + view].m_other = cx->v[view ^ 1].match8;
+            }
+        }
     }
     const size_t ubytes = units.size() * sizeof(int4), tbytes = (table.size() * sizeof(Agg3View) + 15) / 16 * 16;
     if (ctx->units_cap < ubytes + tbytes) {
@@ -852,6 +936,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.lut_w = exact ? (const void*)ctx->lut_w : (const void*)ctx->lut_wf;
     A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
+    A.img_w = ctx->W; A.D = Dv;
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env < 0 ? 0 : sleep_env ? sleep_env : 20;
 
@@ -873,9 +958,15 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(T_));                                                              \
         S3_TRY(agg3_launch(ctx, k_agg_flow<T_, NH_, FULL_, BIG_, R_, NEAR_, false, CL_>, GRID_, THREADS_, smem, CL_, launch_stream, A)); \
     } while (0)
+#define A3_LAUNCH_F(NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                          \
+    do {                                                                                                                       \
+        const size_t smem = agg3_smem_bytes(NH_, R_, sizeof(double));                                                          \
+        S3_TRY(agg3_launch(ctx, k_agg_flow<double, NH_, FULL_, BIG_, R_, NEAR_, false, CL_, true>, GRID_, THREADS_, smem, CL_, launch_stream, A)); \
+    } while (0)
 #define A3_LAUNCH(NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_)                                                            \
     do {                                                                                                                       \
-        if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_);                                     \
+        if (fuse) A3_LAUNCH_F(NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_);                                              \
+        else if (exact) A3_LAUNCH_T(double, NH_, FULL_, BIG_, R_, NEAR_, CL_, GRID_, THREADS_);                                \
         else A3_LAUNCH_T(float, NH_, FULL_, BIG_, (R_) * 2, NEAR_, CL_, GRID_, THREADS_);                                      \
     } while (0)
     // ring geometry: rows R and hand-over distance NEAR (>= S3_AGG_NEAR, the distance the forest stage flags nodes by).
@@ -908,6 +999,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
 #undef A3_DISPATCH
 #undef A3_LAUNCH
+#undef A3_LAUNCH_F
 #undef A3_LAUNCH_T
     if (n_slices > 1) {
         for (int c = 0; c < nctx; c++)
@@ -936,7 +1028,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     return 0;
 }
 
-int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1) { return s3_aggregate_flow_multi(&ctx, 1, views_mask, d0, d1); }
+int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1, int fuse) { return s3_aggregate_flow_multi(&ctx, 1, views_mask, d0, d1, fuse); }
 
 // Proposal mode of the dataflow kernel.  Plan: the unit list (trees with work, longest first) and the view table, uploaded
 // once; launch: one evaluation of a tree-grouped proposal list (labels_dev [n][3] grouped by tree, order inside a tree

@@ -75,7 +75,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 
 static void free_view(View& V) {
     DFREE(V.bgr); DFREE(V.raw4); DFREE(V.med); DFREE(V.gray); DFREE(V.ew); DFREE(V.pgrad); V.plane_ready = false;
-    DFREE(V.uf_comp); DFREE(V.uf_parent); DFREE(V.adjw); DFREE(V.bfs_front); DFREE(V.fh_ent[0]); DFREE(V.fh_ent[1]); DFREE(V.uf_resv);
+    DFREE(V.match8); DFREE(V.uf_comp); DFREE(V.uf_parent); DFREE(V.adjw); DFREE(V.bfs_front); DFREE(V.fh_ent[0]); DFREE(V.fh_ent[1]); DFREE(V.uf_resv);
     DFREE(V.mask); DFREE(V.elist); DFREE(V.e_ra); DFREE(V.e_rb); DFREE(V.e_flag);
     DFREE(V.hist); DFREE(V.lvl_off); DFREE(V.lvl_cursor); DFREE(V.counters);
     DFREE(V.minpix); DFREE(V.scan_tmp); DFREE(V.tree_id); DFREE(V.tree_size); DFREE(V.tree_rootpix);
@@ -152,6 +152,7 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->fh_ctas = 0;
     p->fh_threads = 0;
     p->agg_cluster_nodes = 0;
+    p->fuse_cost = 0;
     p->fh_cluster = 0;
     p->pms_cost_mode = 0;
     p->pm_alpha = 0.9f;
@@ -283,6 +284,7 @@ static int set_images_impl(s3dmst_ctx* ctx, const uint8_t* left_bgr, const uint8
         ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = ctx->v[i].plane_ready = false;
     }
     ctx->forest_pending = 0;
+    ctx->fused_D = 0;
     if (sync) S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
     return 0;
 }
@@ -302,6 +304,7 @@ int s3dmst_set_raw_images(s3dmst_ctx* ctx, const uint8_t* left_raw_bgr, const ui
     S3_CUDA(cudaSetDevice(ctx->device));
     S3_TRY(set_size(ctx, ctx->map_w[0], ctx->map_h[0]));
     for (int i = 0; i < 2; i++) ctx->v[i].forest_ready = ctx->v[i].cost_ready = ctx->v[i].agg_ready = false;
+    ctx->fused_D = 0;
     S3_TRY(s3_remap_raw_pair(ctx, left_raw_bgr, right_raw_bgr, src_w, src_h, stride));
     S3_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffers may be pageable / reused
     return 0;
@@ -485,6 +488,7 @@ int s3dmst_build_cost_volume(s3dmst_ctx* ctx, int D, int apply_ingest) {
 int s3dmst_set_cost_volume(s3dmst_ctx* ctx, int view, const float* vol, int D, int apply_ingest) {
     if (view < 0 || view > 1 || !vol) return s3_fail(ctx, S3DMST_E_ARG, "set_cost_volume: bad arguments");
     S3_CUDA(cudaSetDevice(ctx->device));
+    ctx->fused_D = 0;
     float* stage = nullptr;
     const size_t bytes = (size_t)ctx->N * D * sizeof(float);
     S3_CUDA(cudaMalloc(&stage, bytes));
@@ -499,6 +503,7 @@ int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol) {
     S3_CUDA(cudaSetDevice(ctx->device));
     if (view < 0 || view > 1 || !vol) return s3_fail(ctx, S3DMST_E_ARG, "get_cost_volume: bad arguments");
     View& V = ctx->v[view];
+    S3_TRY(s3_materialize_cost(ctx));  // a dense run that computed its cost on the fly left none
     if (!V.cost_ready) return s3_fail(ctx, S3DMST_E_STATE, "get_cost_volume: no volume");
     float* stage = nullptr;
     const size_t bytes = (size_t)ctx->N * V.D * sizeof(float);
@@ -516,6 +521,7 @@ int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol) {
 int s3dmst_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1, int32_t* disp, double* best_cost) {
     if (view < 0 || view > 1) return s3_fail(ctx, S3DMST_E_ARG, "bad view");
     S3_CUDA(cudaSetDevice(ctx->device));
+    S3_TRY(s3_materialize_cost(ctx));
     {
         int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 1 << view, d0, d1);
         if (rc == 1) rc = s3_aggregate_dense(ctx, view, d0, d1);  // simple kernel: any even d0, any depth
@@ -690,9 +696,11 @@ int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* 
     S3_EV_BEGIN(S3DMST_T_FOREST, 0);
     S3_TRY(s3_forest_stage_mask(ctx, 3));  // both views share every launch of the forest stage
     S3_EV_END(S3DMST_T_FOREST, 0);
-    S3_TRY(s3_cost_adgrad(ctx, D, 0));
+    const bool fuse = s3_want_fused_cost(ctx);
+    if (fuse) S3_TRY(s3_fused_prepare(ctx, D));
+    else S3_TRY(s3_cost_adgrad(ctx, D, 0));
     {
-        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 3, 0, D);  // both views' trees in one launch
+        int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 3, 0, D, fuse);  // both views' trees in one launch
         if (rc == 1) {
             rc = 0;
             for (int view = 0; view < 2 && !rc; view++) rc = s3_aggregate_dense(ctx, view, 0, D);
@@ -744,6 +752,7 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
         if (!ctxs[c] || ctxs[c]->device != ctx->device || ctxs[c]->N != ctx->N || ctxs[c]->N == 0)
             return s3_fail(ctx, S3DMST_E_ARG, "run_dense_batch: contexts must share the device and hold images of one size");
     S3_CUDA(cudaSetDevice(ctx->device));
+    const bool fuse = s3_want_fused_cost(ctx);  // a batch_back after a batch_front decides the same way (same parameters)
     // Front: forest + cost volume of every frame, queued on the frames' own streams by this one host thread.  Nothing
     // here waits for the device: the tree counts and sizes travel to the host behind the forest kernels, and the joint
     // aggregation below is the first thing that needs them.
@@ -756,7 +765,8 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
         S3_TRY(s3_fh_launch_multi(ctxs, n, 3));
         for (int c = 0; c < n; c++) {
             S3_TRY(s3_forest_post(ctxs[c], 3));
-            S3_TRY(s3_cost_adgrad(ctxs[c], D, 0));
+            if (fuse) S3_TRY(s3_fused_prepare(ctxs[c], D));
+            else S3_TRY(s3_cost_adgrad(ctxs[c], D, 0));
         }
         phases &= ~1;
     }
@@ -768,13 +778,13 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
             S3_EV_BEGIN(S3DMST_T_FOREST, 0);
             S3_TRY(s3_forest_stage_mask(ctx, 3));
             S3_EV_END(S3DMST_T_FOREST, 0);
-            return s3_cost_adgrad(ctx, D, 0);
+            return fuse ? s3_fused_prepare(ctx, D) : s3_cost_adgrad(ctx, D, 0);
         }();
         if (r) return c == 0 ? r : s3_fail(ctx, r, "run_dense_batch: frame %d: %s", c, cx->err.c_str());
     }
     if (!(phases & 2)) return 0;
     {
-        int r = ctx->P.agg_kernel == 0 ? s3_aggregate_flow_multi(ctxs, n, 3, 0, D) : 1;
+        int r = ctx->P.agg_kernel == 0 ? s3_aggregate_flow_multi(ctxs, n, 3, 0, D, fuse) : 1;
         if (r == 1) {
             r = 0;
             for (int c = 0; c < n && !r; c++)

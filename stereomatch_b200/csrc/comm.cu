@@ -180,11 +180,16 @@ int s3dmst_aggregate_dense_sharded(s3dmst_ctx* ctx, int D) {
     S3_CUDA(cudaSetDevice(ctx->device));
     int d0, d1;
     label_range(D, ctx->comm_nranks, ctx->comm_rank, &d0, &d1);
+    // Without a volume of D labels on both views the matching cost is computed inside the aggregation kernel: a rank then
+    // holds no cost volume at all, only the running sums of the labels it aggregates... (rows keep their full pitch).
+    const bool have_vol = ctx->v[0].cost_ready && ctx->v[1].cost_ready && ctx->v[0].D == D && ctx->v[1].D == D;
+    const bool fuse = !have_vol && s3_want_fused_cost(ctx);
+    if (fuse) S3_TRY(s3_fused_prepare(ctx, D));
     for (int view = 0; view < 2; view++) {
         View& V = ctx->v[view];
-        if (!V.forest_ready || !V.cost_ready || V.D != D) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense_sharded: forests and a cost volume of D labels required");
+        if (!V.forest_ready || !(fuse || have_vol)) return s3_fail(ctx, S3DMST_E_STATE, "aggregate_dense_sharded: forests and a cost volume of D labels required");
         if (d1 > d0) {
-            int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 1 << view, d0, d1);
+            int rc = ctx->P.agg_kernel == 1 ? 1 : s3_aggregate_flow(ctx, 1 << view, d0, d1, fuse);
             if (rc == 1) rc = s3_aggregate_dense(ctx, view, d0, d1);
             if (rc) return rc;
         } else {  // more ranks than label blocks: contribute the identity of MIN-LOC

@@ -164,12 +164,12 @@ __global__ void __launch_bounds__(256) k_to_dmajor(const float* __restrict__ in,
     }
 }
 
-int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D) {
+int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D, bool need_cost) {
     View& V = ctx->v[view];
     if (D < 1 || D > 4096) return s3_fail(ctx, S3DMST_E_ARG, "D=%d out of range", D);
     const int Dp = (D + 3) / 4 * 4;
     const size_t need = (size_t)ctx->N * Dp;
-    if (V.cost_cap < need) {
+    if (need_cost && V.cost_cap < need) {
         if (V.cost) S3_CUDA(cudaFree(V.cost));
         V.cost = nullptr; V.cost_cap = 0;
         S3_CUDA(cudaMalloc(&V.cost, need * sizeof(float)));
@@ -184,6 +184,30 @@ int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D) {
     V.D = D;
     V.Dp = Dp;
     return 0;
+}
+
+// Dense runs (s3dmst_run_dense / _batch / aggregate_dense_sharded) on the library's own AD+gradient cost do not need the
+// volume at all: the dataflow kernel computes a node's matching cost where it would have read the row (aggregate3.cu:
+// FUSE) — 8 of the 24.75 bytes per pixel·label of a step (4 written here, 4 read there) and the whole kernel below
+// disappear.  params.fuse_cost = -1 (or S3_FUSE=0 in the environment) keeps the volume.
+bool s3_want_fused_cost(const s3dmst_ctx* ctx) {
+    static const int env = getenv("S3_FUSE") ? atoi(getenv("S3_FUSE")) : 1;
+    return env != 0 && ctx->P.fuse_cost >= 0 && ctx->P.exact != 0 && ctx->P.agg_kernel == 0;
+}
+int s3_fused_prepare(s3dmst_ctx* ctx, int D) {
+    for (int view = 0; view < 2; view++) {
+        if (!ctx->v[view].forest_ready) return s3_fail(ctx, S3DMST_E_STATE, "dense run: both forests required");
+        S3_TRY(s3_ensure_volume(ctx, view, D, false));
+        ctx->v[view].cost_ready = false;  // whatever volume the view held belongs to other images or another D
+    }
+    ctx->fused_D = D;
+    return 0;
+}
+int s3_materialize_cost(s3dmst_ctx* ctx) {
+    if (ctx->fused_D <= 0 || (ctx->v[0].cost_ready && ctx->v[1].cost_ready)) return 0;
+    const int D = ctx->fused_D;
+    ctx->fused_D = 0;
+    return s3_cost_adgrad(ctx, D, 0);
 }
 
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest) {

@@ -30,6 +30,7 @@ struct View {
     uchar4* raw4 = nullptr;    // [N] raw (b,g,r,0)
     uchar4* med = nullptr;     // [N] median-filtered (b,g,r,0)
     float* gray = nullptr;     // [N] s3_gray of the RAW image (cost kernel)
+    uint2* match8 = nullptr;   // [N] {packed BGR, gray}: what the fused matching cost of the aggregation kernel reads
     float* pgrad = nullptr;    // [N][2] Sobel/8 gradients of the BGR2GRAY image (pms_cost_mode 1, pm.cpp:70-88), lazily allocated
     bool plane_ready = false;
     uint16_t* ew = nullptr;    // [2N] edge weights by canonical id
@@ -114,6 +115,7 @@ struct s3dmst_ctx {
     cudaEvent_t ev[S3DMST_T_COUNT][2][2];  // [stage][view][begin/end]
     bool ev_set[S3DMST_T_COUNT][2];
     long long launches = 0;
+    int fused_D = 0;           // > 0: the last dense run computed its matching cost in the aggregation kernel for this D (no volume yet)
     std::string err;
     // scratch for PMS
     cudaEvent_t ev_xctx = nullptr;  // orders this context's stream against another context's in batched launches
@@ -203,7 +205,7 @@ int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
 int s3_aggregate_dense(s3dmst_ctx* ctx, int view, int d0, int d1); // aggregate.cu (v1, reference kernel)
-int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1);    // aggregate3.cu (dataflow, default)
+int s3_aggregate_flow(s3dmst_ctx* ctx, int views_mask, int d0, int d1, int fuse = 0);    // aggregate3.cu (dataflow, default)
 struct PmsFlowPlan {   // aggregate3.cu: unit list of a proposal-mode launch, uploaded once and reused by every round
     int n_cl, n_big, n_small;
     const void* views_dev;
@@ -215,7 +217,7 @@ int s3_pms_flow_launch(s3dmst_ctx* ctx, int view, const PmsFlowPlan* plan, const
 // source may die as soon as the call returns.
 int s3_h2d_staged(s3dmst_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int s3_tree_adjacency(s3dmst_ctx* ctx, int view);   // pms.cu: device CSR of the tree adjacency graph (lazy)
-int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1);  // one launch over several frames
+int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0, int d1, int fuse = 0);  // one launch over several frames
 int s3_pms_apply(s3dmst_ctx* ctx, int view, const int32_t* h_tree_ids, const float* h_labels, size_t n);
 int s3_init_labels(s3dmst_ctx* ctx, int view, int Dmax);          // pms.cu: the reference's random plane initialisation
 int s3_pms_iterate(s3dmst_ctx* ctx, int view, int n_iter, unsigned seed);
@@ -224,7 +226,10 @@ int s3_dense_to_disp(s3dmst_ctx* ctx, int view);
 int s3_lr_check(s3dmst_ctx* ctx, int fill);
 int s3_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
 int s3_reproject(s3dmst_ctx* ctx, const double* Q16, float disp_floor, int handle_missing, float* h_xyz, uint32_t* h_rgb);
-int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D);
+int s3_ensure_volume(s3dmst_ctx* ctx, int view, int D, bool need_cost = true);   // need_cost = false: only the running sums (fused cost)
+bool s3_want_fused_cost(const s3dmst_ctx* ctx);                 // dense runs compute the matching cost inside the aggregation kernel
+int s3_fused_prepare(s3dmst_ctx* ctx, int D);                   // ... what such a run needs instead of s3_cost_adgrad
+int s3_materialize_cost(s3dmst_ctx* ctx);                       // build the volume a fused run skipped, if somebody asks for it
 int s3_prepare_plane_cost(s3dmst_ctx* ctx, int Dmax);              // pms.cu
 int s3_weighted_median(s3dmst_ctx* ctx, int view, int radius, float gamma, const uint8_t* h_mask);  // postfilter.cu
 int s3_norm_factor(s3dmst_ctx* ctx, int view, double* h_out);

@@ -540,10 +540,45 @@ def test_lr_check_matches_oracle(api, oracle, fill):
         eng.close()
 
 
-def test_run_dense_end_to_end(api, oracle):
+@pytest.mark.parametrize("W,H,D,seed,nat,cluster", [(96, 64, 16, 3, 0, -1), (130, 70, 23, 5, 1, -1), (200, 120, 70, 9, 1, 64),
+                                                     (120, 80, 200, 13, 0, -1), (333, 97, 130, 17, 0, 100), (64, 48, 100, 19, 1, -1)])
+def test_fused_matching_cost_equals_the_volume_path(api, oracle, W, H, D, seed, nat, cluster):
+    """params.fuse_cost (the default): a dense run computes the AD+gradient cost inside the aggregation kernel and builds no
+    volume.  The aggregated costs (all of them, keep_aggregated), winners and maps are bit-identical to the run that builds
+    the volume first and to the oracle — including labels without a counterpart in the other image (D > W: cost 3.0), the
+    image borders, partly filled label slices, several slices per tree and the cluster kernel.  The volume a fused run
+    skipped is built on demand and is the oracle's."""
+    L, R, _ = make(W, H, min(D, 24), seed, nat)
+    lv, rv = oracle.cost_adgrad(L, R, D)
+    res = {}
+    for fuse in (0, -1):
+        eng = api.Stereo3DMST(fuse_cost=fuse, keep_aggregated=1, agg_cluster_nodes=cluster)
+        eng.set_images(L, R)
+        dl, dr = eng.run_dense(D, fill=True)
+        res[fuse] = (dl, dr, eng.get_aggregated(0), eng.get_aggregated(1), eng.get_dense_result(0), eng.get_dense_result(1))
+        if fuse == 0:
+            n_fused = eng.launch_count()
+            assert np.array_equal(bits(eng.get_cost_volume(0)), bits(lv)) and np.array_equal(bits(eng.get_cost_volume(1)), bits(rv))
+        else:
+            assert eng.launch_count() > n_fused   # the volume path launched the cost kernels on top
+        eng.close()
+    for a, b in zip(res[0], res[-1]):
+        if isinstance(a, tuple):
+            assert all(np.array_equal(bits(x), bits(y)) for x, y in zip(a, b))
+        else:
+            assert np.array_equal(bits(a), bits(b))
+    for view, (img, vol) in enumerate(((L, lv), (R, rv))):
+        F = oracle.forest(img)
+        disp_o, best_o, agg_o = oracle.aggregate_dense(F, vol, want_agg=True)
+        assert np.array_equal(bits(res[0][2 + view]), bits(agg_o))
+        assert np.array_equal(res[0][4 + view][0], disp_o) and np.array_equal(bits(res[0][4 + view][1]), bits(best_o))
+
+
+@pytest.mark.parametrize("fuse", [0, -1])
+def test_run_dense_end_to_end(api, oracle, fuse):
     W, H, D = 256, 160, 48
     L, R, gt = make(W, H, D, 77, 0)
-    eng = api.Stereo3DMST()
+    eng = api.Stereo3DMST(fuse_cost=fuse)
     eng.set_images(L, R)
     dl, dr = eng.run_dense(D, fill=True)
     n0 = eng.launch_count()
