@@ -37,6 +37,18 @@ WORKLOAD = ("C4 frames: synthetic random-dot slanted-plane pairs 1920x1080, D=25
             "(forest+cost+tree-filter+WTA+LR/fill, both views)")
 METRIC = "Mpix*disparities/s"
 ALG_BYTES_PER_PXLABEL = 12.0  # read cost 4 + write A_up 4 + read A_up 4 (fp32 model; exact mode moves 20)
+ALG_BYTES_COST_BUILD = 4.0    # the cost-volume build writes 4 B per pixel*label per view
+FUSE = True                   # --no-fuse: build the cost volume first (params.fuse_cost = -1)
+
+
+def alg_bytes_per_pxlabel():
+    """Algorithmic bytes of the dominant kernel.  With the matching cost computed inside k_agg_flow (the default) that
+    kernel does the work of the cost-volume build and of the aggregation: 4 + 12 B per pixel*label of SURVEY §8d."""
+    return ALG_BYTES_PER_PXLABEL + (ALG_BYTES_COST_BUILD if FUSE else 0.0)
+
+
+def eng_kw():
+    return {} if FUSE else {"fuse_cost": -1}
 FLIR_TAGS = ("000020", "000040", "000060", "000061", "000080")
 FLIR_D = 100                   # src/stereo_Yin.cpp:207
 CPU_LABEL_PARTS = 4            # CPU arm: label shards per view of a frame (each shard rebuilds its view's forest, like a rank of the GPU's C5 path)
@@ -55,9 +67,10 @@ def read_peaks():
 def read_traffic():
     """DRAM bytes per pixel*label of the batched aggregation launch, from this round's committed ncu capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
+    key = "k_agg_flow_fused_c4" if FUSE else "k_agg_flow_c4"
     try:
         tj = json.load(open(p))
-        return float(tj["k_agg_flow_c4_bytes_per_pxlabel"]), tj.get("k_agg_flow_c4_source", "profiles/traffic.json")
+        return float(tj[key + "_bytes_per_pxlabel"]), tj.get(key + "_source", "profiles/traffic.json")
     except Exception:
         return None, None
 
@@ -174,8 +187,8 @@ def gpu_config(world, B):
     """The `config` object of the JSON line — the same for both arms (the reference arm runs a bounded sample of it)."""
     return {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": f"frame-sharded x{world}, no collective",
             "batching": "frames of a step run on their own contexts/streams; one tree-aggregation launch covers the whole batch",
-            "l2": f"working set per step ({12.7 * B:.0f} GB of cost + running sums) exceeds the 126 MB L2; no explicit flush",
-            "mode": "exact (fp64, reference association order)"}
+            "l2": f"working set per step ({(8.5 if FUSE else 12.7) * B:.0f} GB of {'' if FUSE else 'cost + '}running sums) exceeds the 126 MB L2; no explicit flush",
+            "mode": "exact (fp64, reference association order)" + ("; matching cost computed inside the aggregation kernel (no cost volume)" if FUSE else "")}
 
 
 def run_reference(args):
@@ -244,9 +257,9 @@ def bench_flir(api, local, peak):
     if not pairs:
         return {"unavailable": "tests/golden/flir_*.jpg missing"}
     fh, fw = pairs[0][0].shape[:2]
-    alg = ALG_BYTES_PER_PXLABEL * fw * fh * FLIR_D * 2
+    alg = alg_bytes_per_pxlabel() * fw * fh * FLIR_D * 2
     per = []
-    eng = api.Stereo3DMST(device=local)
+    eng = api.Stereo3DMST(device=local, **eng_kw())
     for (l, r) in pairs:
         eng.set_images(l, r)
         for _ in range(2):
@@ -261,7 +274,7 @@ def bench_flir(api, local, peak):
     eng.close()
     ms = float(np.mean([p[0] for p in per])); st = np.mean([p[1] for p in per], axis=0)
     # the five pairs as one batch (one aggregation launch over every pair's trees)
-    engs = [api.Stereo3DMST(device=local, fh_ctas=28) for _ in pairs]
+    engs = [api.Stereo3DMST(device=local, fh_ctas=28, **eng_kw()) for _ in pairs]
     for e, (l, r) in zip(engs, pairs):
         e.set_images(l, r)
     for _ in range(2):
@@ -292,7 +305,7 @@ def bench_flir(api, local, peak):
 def bench_c2(api, synth, local, peak, B, fh_ctas, steps):
     """Round 1's headline workload, kept for continuity: C2 (1280x720, D = 128) in batches of 8."""
     w2, h2, d2 = 1280, 720, 128
-    engs = [api.Stereo3DMST(device=local, fh_ctas=fh_ctas) for _ in range(B)]
+    engs = [api.Stereo3DMST(device=local, fh_ctas=fh_ctas, **eng_kw()) for _ in range(B)]
     for i, e in enumerate(engs):
         l, r, _ = synth.make_pair(w2, h2, d2, seed=synth.BASE_SEED + i)
         e.set_images(l, r)
@@ -310,7 +323,7 @@ def bench_c2(api, synth, local, peak, B, fh_ctas, steps):
     ms = (time.perf_counter() - t0) / steps * 1e3
     for e in engs:
         e.close()
-    ach = ALG_BYTES_PER_PXLABEL * w2 * h2 * d2 * 2 * B / (agg / steps * 1e-3) / 1e9
+    ach = alg_bytes_per_pxlabel() * w2 * h2 * d2 * 2 * B / (agg / steps * 1e-3) / 1e9
     return {"workload": f"C2 synthetic pair {w2}x{h2}, D={d2}, batches of {B}", "value": B * w2 * h2 * d2 / ms / 1e3, "unit": METRIC,
             "ms_per_step": ms, "ms_per_frame": ms / B, "aggregate_ms": agg / steps, "roofline_frac": ach / peak}
 
@@ -328,7 +341,7 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    eng = api.Stereo3DMST(device=local)
+    eng = api.Stereo3DMST(device=local, **eng_kw())
     parallel.comm_init_from_torch(eng)
     out = {"ranks": world, "collective": "2 x ncclAllReduce(MIN) + mask kernel per view, on the library's communicator (csrc/comm.cu)"}
     # ---- (a) small pair, bit-exact against the CPU oracle's full-range result, on every rank
@@ -336,8 +349,9 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
     L, R, _ = synth.make_pair(cw, ch, cd, seed=synth.BASE_SEED + 100)
     eng.set_images(L, R)
     eng.build_forest(0); eng.build_forest(1)
-    eng.build_cost_volume(cd)
-    eng.aggregate_dense_sharded(cd)
+    if not FUSE:
+        eng.build_cost_volume(cd)
+    eng.aggregate_dense_sharded(cd)   # (default: no cost volume anywhere — the aggregation kernel computes the matching cost)
     eng.sync()
     from oracle.pyoracle import Oracle
     O = Oracle(fast=True)
@@ -355,8 +369,28 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
     eng.set_images(L, R)
     d0, d1 = eng.comm_label_range(d5)
     eng.build_forest(0); eng.build_forest(1)
-    eng.build_cost_volume(d5)
-    # merge property: reduced result == tie-rule merge of the ranks' partial results (gathered to every rank over torch's NCCL)
+    if not FUSE:
+        eng.build_cost_volume(d5)
+
+    def timed_sharded():
+        for _ in range(2):
+            eng.aggregate_dense_sharded(d5)
+        eng.sync()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mm = 0.0
+        for _ in range(steps):
+            eng.aggregate_dense_sharded(d5)
+            eng.sync()
+            mm += eng.comm_minloc_ms()
+        dist.barrier(); torch.cuda.synchronize()
+        return maxms((time.perf_counter() - t0) * 1e3 / steps), maxms(mm / steps)
+
+    # timing: aggregation of this rank's labels (default: matching cost included, no volume exists) + the reductions, both views
+    ms, mlms = timed_sharded()
+    reduced = [eng.get_dense_result(view) for view in (0, 1)]
+    # merge property: reduced result == tie-rule merge of the ranks' partial results (gathered to every rank over torch's NCCL).
+    # The partial results come from s3dmst_aggregate_dense on a cost volume (built on demand here): the other code path.
     merged_ok = True
     partial = []
     for view in (0, 1):
@@ -366,8 +400,6 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
         else:
             pd = np.full(eng.N, 2**31 - 1, np.int32); pb = np.full(eng.N, np.finfo(np.float64).max)
         partial.append((pd, pb))
-    eng.aggregate_dense_sharded(d5)
-    eng.sync()
     for view in (0, 1):
         pd, pb = partial[view]
         tb = torch.from_numpy(pb).cuda(); td = torch.from_numpy(pd).cuda()
@@ -377,27 +409,19 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
         for r in range(1, world):          # ranks hold ascending label ranges: strict '<' keeps the lowest d on ties
             take = gb[r] < mb
             mb = torch.where(take, gb[r], mb); md = torch.where(take, gd[r], md)
-        disp, best = eng.get_dense_result(view)
+        disp, best = reduced[view]
         merged_ok &= bool(np.array_equal(md.cpu().numpy(), disp) and np.array_equal(mb.cpu().numpy().view(np.uint64), best.view(np.uint64)))
         del gb, gd, tb, td, mb, md
     out["c5_merge_check"] = allmin_flag(merged_ok)
-    # timing: aggregation of this rank's labels + the reductions, both views
-    for _ in range(2):
-        eng.aggregate_dense_sharded(d5)
-    eng.sync()
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    mm = 0.0
-    for _ in range(steps):
-        eng.aggregate_dense_sharded(d5)
-        eng.sync()
-        mm += eng.comm_minloc_ms()
-    dist.barrier(); torch.cuda.synchronize()
-    ms = maxms((time.perf_counter() - t0) * 1e3 / steps)
-    out.update({"c5_case": f"{w5}x{h5} D={d5}, {d1 - d0} labels on rank 0", "ms_per_pair": ms, "minloc_ms": maxms(mm / steps),
+    out.update({"c5_case": f"{w5}x{h5} D={d5}, {d1 - d0} labels on rank 0", "ms_per_pair": ms, "minloc_ms": mlms,
                 "bytes": 2 * w5 * h5 * 12, "Mpix_disp_per_s": w5 * h5 * d5 / ms / 1e3,
-                "note": "ms_per_pair = aggregation of the rank's label range + MIN-LOC, both views, max over ranks; minloc_ms = device time of the "
-                        "reductions alone (the left view's overlaps the right view's aggregation); bytes = (8 + 4) B x pixels x 2 views all-reduced"})
+                "note": "ms_per_pair = " + ("matching cost + " if FUSE else "") + "aggregation of the rank's label range + MIN-LOC, both views, max over ranks"
+                        + (" (no cost volume exists on any rank)" if FUSE else " (the full cost volume was built on every rank beforehand, not timed)")
+                        + "; minloc_ms = device time of the reductions alone (the left view's overlaps the right view's aggregation); "
+                          "bytes = (8 + 4) B x pixels x 2 views all-reduced"})
+    if FUSE:  # for the record: the same call once a volume exists (built by the merge check above): aggregation only
+        ms_v, _ = timed_sharded()
+        out["ms_per_pair_from_prebuilt_volume"] = ms_v
     eng.close()
     return out
 
@@ -417,7 +441,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = max(1, args.batch)
     # one context (and stream) per frame of the batch; in a batch the cooperative forest kernel takes a share of the SMs
-    engs = [api.Stereo3DMST(device=local, fh_ctas=(args.fh_ctas if B > 1 else 0), fh_threads=(args.fh_threads if B > 1 else 0), fh_cluster=args.fh_cluster) for _ in range(B)]
+    engs = [api.Stereo3DMST(device=local, fh_ctas=(args.fh_ctas if B > 1 else 0), fh_threads=(args.fh_threads if B > 1 else 0), fh_cluster=args.fh_cluster, **eng_kw()) for _ in range(B)]
     frames = [synth.make_pair(W, H, D, seed=synth.BASE_SEED + 10 + rank * B + i) for i in range(B)]   # different frames per rank (C4: seed+10 ...)
     # pinned host staging for the e2e leg
     pin = [(torch.from_numpy(L.copy()).pin_memory(), torch.from_numpy(R.copy()).pin_memory()) for L, R, _ in frames]
@@ -496,7 +520,7 @@ def run_gpu(args):
     del engs
 
     # ---- single-frame latency (one C4 pair alone on the GPU, forest kernel on every SM)
-    lat = api.Stereo3DMST(device=local)
+    lat = api.Stereo3DMST(device=local, **eng_kw())
     lat.set_images(pin[0][0].numpy(), pin[0][1].numpy())
     for _ in range(3):
         lat.run_dense(D, fill=True, fetch=False)
@@ -523,7 +547,7 @@ def run_gpu(args):
     if rank == 0:
         per_launch_ms = agg_ms / args.steps                # one aggregation launch set per step covers every frame's trees
         pxl = float(W) * H * D * 2 * B                     # pixel*labels of one launch: both views of B frames
-        alg_bytes = ALG_BYTES_PER_PXLABEL * pxl
+        alg_bytes = alg_bytes_per_pxlabel() * pxl
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         tpp, tsrc = read_traffic()
         cpu = cpu_baseline_serial() if world == 1 and not args.no_cpu else None
@@ -537,7 +561,11 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "k_agg_flow", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": (tpp * pxl if tpp else None), "traffic_source": tsrc, "peak_source": peak_src,
                          "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp64_traffic_model_gbs": 20.0 * pxl / (per_launch_ms * 1e-3) / 1e9},
+                         "algorithmic_bytes_per_pxlabel": alg_bytes_per_pxlabel(),
+                         "algorithmic_model": ("k_agg_flow computes the matching cost itself: 4 B (cost-volume build) + 12 B (aggregation) per pixel*label of SURVEY 8d"
+                                               if FUSE else "12 B per pixel*label (aggregation, SURVEY 8d); the cost volume is built by k_cost_adgrad"),
+                         "frac_12B_aggregation_only": ALG_BYTES_PER_PXLABEL * pxl / (per_launch_ms * 1e-3) / 1e9 / peak,
+                         "fp64_traffic_model_gbs": (16.0 if FUSE else 20.0) * pxl / (per_launch_ms * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": METRIC, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * W * H * 3 * B, "d2h_bytes_per_step": 2 * W * H * 4 * B},
             "gpu_launches": int(launches),
@@ -573,8 +601,11 @@ def main():
     ap.add_argument("--fh-cluster", type=int, default=0, help="CTAs of the thread-block cluster a view's forest kernel runs in (0: cooperative grid)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the c1_flir / c2 objects")
+    ap.add_argument("--no-fuse", action="store_true", help="build the cost volume with k_cost_adgrad first (params.fuse_cost = -1)")
     ap.add_argument("--no-label-sharded", action="store_true", help="skip the C5 leg at N >= 2")
     args = ap.parse_args()
+    global FUSE
+    FUSE = not args.no_fuse
     if args.impl == "reference":
         run_reference(args)
     else:

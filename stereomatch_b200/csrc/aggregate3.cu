@@ -84,6 +84,7 @@ struct Agg3Args {
     double* min_cost;      // [N] pixel order
     float* abc;            // [N][3] pixel order
     int img_w, D;          // image width, labels of the cost rows
+    unsigned long long w_magic;  // ceil(2^40 / img_w): pix / img_w == (pix * w_magic) >> 40 for pix < 2^28 (FUSE)
     float oob;             // label cost outside [0, D)
     // proposal generation inside the kernel (s3dmst_pms_iterate): after a tree's listed proposals (its neighbours' labels),
     // the refinement ladder around a random pixel of the tree itself
@@ -428,13 +429,28 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
         // shadow of the wait for the next node's children.
         auto fused_cost = [&](int vv, float2* cf) {
             const int pix = __ldg(V.node_pixel + vv);
-            const int x = pix - (pix / A.img_w) * A.img_w;
+            const int x = pix - (int)(((unsigned long long)(unsigned)pix * A.w_magic) >> 40) * A.img_w;
             const int view = unit.x & 1;
             const uint2 me = __ldg(V.m_self + pix);
             const bool has_next = x + 1 < A.img_w;
             const float me_g = __uint_as_float(me.y);
             const float me_gn = has_next ? __uint_as_float(__ldg(V.m_self + pix + 1).y) : 0.0f;
             const int dvalid = view == 0 ? (has_next ? x + 1 : 0) : A.img_w - 1 - x;
+            // nodes whose whole label slice has a counterpart in the other image (all but the columns next to one border):
+            // no per-label validity
+            if (FULL && (view == 0 ? (has_next && x >= l0 + 64 * NH - 1) : (x + l0 + 64 * NH < A.img_w))) {
+#pragma unroll
+                for (int h = 0; h < NH; h++) {
+                    const int dA = l0 + h * 64 + 2 * lane;
+                    const uint2* q = V.m_other + (view == 0 ? pix - dA - 1 : pix + dA);
+                    const uint2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                    const uint2 a = view == 0 ? q1 : q0, b = view == 0 ? q0 : q1;
+                    const float an = __uint_as_float(view == 0 ? q2.y : q1.y), bn = __uint_as_float(view == 0 ? q1.y : q2.y);
+                    cf[h].x = a3_adgrad(s_ct, view, me.x, me_g, me_gn, a.x, __uint_as_float(a.y), an);
+                    cf[h].y = a3_adgrad(s_ct, view, me.x, me_g, me_gn, b.x, __uint_as_float(b.y), bn);
+                }
+                return;
+            }
 #pragma unroll
             for (int h = 0; h < NH; h++) {
                 cf[h] = make_float2(0.f, 0.f);
@@ -937,6 +953,7 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     A.lut_w2 = exact ? (const void*)ctx->lut_w2 : (const void*)ctx->lut_w2f;
     A.keep = ctx->P.keep_aggregated;
     A.img_w = ctx->W; A.D = Dv;
+    A.w_magic = ((1ull << 40) + (unsigned long long)ctx->W - 1) / (unsigned long long)ctx->W;
     static const int sleep_env = getenv("S3_AGG_SLEEP") ? atoi(getenv("S3_AGG_SLEEP")) : 0;
     A.sleep_ns = sleep_env < 0 ? 0 : sleep_env ? sleep_env : 20;
 
