@@ -442,8 +442,15 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512, BIG ? 1 : 2) k_agg_flow(Agg3
 #pragma unroll
                 for (int h = 0; h < NH; h++) {
                     const int dA = l0 + h * 64 + 2 * lane;
-                    const uint2* q = V.m_other + (view == 0 ? pix - dA - 1 : pix + dA);
-                    const uint2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                    // the three pixels q0 q1 q2 from two aligned 16-byte loads (lanes 16 bytes apart: dense wavefronts; the
+                    // parity of the first pixel is the same for every lane of the node)
+                    const int lo = view == 0 ? pix - dA - 1 : pix + dA;
+                    const uint4* qq = reinterpret_cast<const uint4*>(V.m_other + (lo & ~1));
+                    const uint4 u0 = __ldg(qq), u1 = __ldg(qq + 1);
+                    const bool odd = lo & 1;
+                    const uint2 q0 = odd ? make_uint2(u0.z, u0.w) : make_uint2(u0.x, u0.y);
+                    const uint2 q1 = odd ? make_uint2(u1.x, u1.y) : make_uint2(u0.z, u0.w);
+                    const uint2 q2 = odd ? make_uint2(u1.z, u1.w) : make_uint2(u1.x, u1.y);
                     const uint2 a = view == 0 ? q1 : q0, b = view == 0 ? q0 : q1;
                     const float an = __uint_as_float(view == 0 ? q2.y : q1.y), bn = __uint_as_float(view == 0 ? q1.y : q2.y);
                     cf[h].x = a3_adgrad(s_ct, view, me.x, me_g, me_gn, a.x, __uint_as_float(a.y), an);
