@@ -54,6 +54,26 @@ FLIR_D = 100                   # src/stereo_Yin.cpp:207
 CPU_LABEL_PARTS = 4            # CPU arm: label shards per view of a frame (each shard rebuilds its view's forest, like a rank of the GPU's C5 path)
 
 
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """The ONE JSON line is the only thing that may reach stdout: libraries loaded into this process (NCCL prints its
+    version banner there at WARN level) get stderr instead."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(s):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(s + "\n")
+    out.flush()
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -228,7 +248,7 @@ def run_reference(args):
     sample = (f"{frames} whole C4 frame(s) per step ({W}x{H}, all {D} labels, full dense pipeline both views), each frame as {2 * P} shards "
               f"(view x label quarter: forest of the view + its cost labels + tree filter/WTA) on {2 * P} cores, MIN-LOC merge + LR check/fill in the "
               f"parent; {busy} of {cores} cores busy; the {args.warmup} warm-up steps run on 480x270 crops")
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -578,7 +598,7 @@ def run_gpu(args):
                 rc = 3
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         t = torch.tensor([rc], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -606,6 +626,7 @@ def main():
     args = ap.parse_args()
     global FUSE
     FUSE = not args.no_fuse
+    guard_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
