@@ -135,6 +135,8 @@ int s3dmst_set_forest(s3dmst_ctx* ctx, int view, int W, int H, int num_trees, co
 int s3dmst_build_cost_volume(s3dmst_ctx* ctx, int D, int apply_ingest);
 /* a2: external volume in the mc-cnn file layout float[D][H][W] (left.bin / right.bin), ingested. */
 int s3dmst_set_cost_volume(s3dmst_ctx* ctx, int view, const float* vol_dmajor, int D, int apply_ingest);
+/* (After a dense run that computed its matching cost inside the aggregation kernel — params.fuse_cost — the volume of
+ * that run is built here on demand.) */
 int s3dmst_get_cost_volume(s3dmst_ctx* ctx, int view, float* vol_dmajor);
 
 /* a9,a10 + WTA, dense-label mode: labels [d0,d1), two-pass tree filter, strict '<'
@@ -161,6 +163,9 @@ int s3dmst_minloc_mask(s3dmst_ctx* ctx, int view, const double* global_min_dev);
  *   s3dmst_aggregate_dense_sharded  both views: this rank's labels, then the reduction; the left view's reduction runs
  *                          on the context's communication stream while the right view is aggregated.  Afterwards every
  *                          rank holds the global result (s3dmst_dense_to_disparity / s3dmst_lr_check as usual).
+ *                          Needs images and forests; a cost volume of D labels on both views is used if there is one,
+ *                          otherwise (params.fuse_cost >= 0) the AD+gradient cost of the rank's labels is computed
+ *                          inside the aggregation kernel and no rank ever holds a volume.
  *   s3dmst_comm_minloc_ms  device time of the two views' reductions of the last sharded call (CUDA events), ms */
 int s3dmst_comm_unique_id(void* id128);
 int s3dmst_comm_init(s3dmst_ctx* ctx, const void* id128, int rank, int nranks);
@@ -231,8 +236,9 @@ int s3dmst_norm_factor(s3dmst_ctx* ctx, int view, double* norm_factor);
  * (r << 16 | g << 8 | b of the left image).  xyz float[H*W][3], rgb uint32[H*W]; either may be NULL. */
 int s3dmst_reproject_to_3d(s3dmst_ctx* ctx, const double* Q, float disp_floor, int handle_missing, float* xyz, uint32_t* rgb);
 
-/* Whole dense pipeline on the current images: forests, cost volume, aggregation + WTA for both views,
- * LR check (+fill).  Outputs float[H][W] (NULL = leave on device). */
+/* Whole dense pipeline on the current images: forests, AD+gradient matching cost, aggregation + WTA for both views,
+ * LR check (+fill).  Outputs float[H][W] (NULL = leave on device).  By default (params.fuse_cost) the matching cost is
+ * computed inside the aggregation kernel and no cost volume is built; the results are bit-identical either way. */
 int s3dmst_run_dense(s3dmst_ctx* ctx, int D, int fill, float* left_disp, float* right_disp);
 
 /* a1: the reference's own pipeline (stereo3dmst, Stereo3DMST.cpp:805-904) on the current images: forests (built if
