@@ -311,6 +311,15 @@ def bench_flir(api, local, peak):
     bms = (time.perf_counter() - t0) / reps * 1e3
     for e in engs:
         e.close()
+    # the reference's OWN pipeline on the bundled pair (BASELINE config C1: plane init, 100 x MST_PMS per view, LabelToDisp,
+    # LR check = s3dmst_run, what the drop-in stereo3dmst() symbol runs): ~500 s on one CPU core
+    eng = api.Stereo3DMST(device=local, cost_scale=1 / 6.0)
+    eng.set_images(*pairs[0])
+    eng.run(FLIR_D, seed=1, fetch=False); eng.sync()
+    t0 = time.perf_counter()
+    eng.run(FLIR_D, seed=2)
+    ref_mode_ms = (time.perf_counter() - t0) * 1e3
+    eng.close()
     ach1 = alg / (st[2] * 1e-3) / 1e9
     achb = alg * len(pairs) / (agg / reps * 1e-3) / 1e9
     return {"workload": f"the 5 bundled FLIR pairs (rectified as src/stereo_Yin.cpp:135-147), {fw}x{fh}, D={FLIR_D} (stereo_Yin.cpp:207)",
@@ -319,7 +328,10 @@ def bench_flir(api, local, peak):
             "Mpix_disp_per_s": fw * fh * FLIR_D / ms / 1e3,
             "roofline": {"bound": "hbm", "kernel": "k_agg_flow (cluster walk for the giant trees)", "achieved": ach1, "peak": peak, "unit": "GB/s",
                          "frac": ach1 / peak, "launch_ms": float(st[2]), "algorithmic_bytes_per_launch": alg},
-            "batch_of_5": {"ms_per_pair": bms / len(pairs), "aggregate_ms": agg / reps, "roofline_frac": achb / peak}}
+            "batch_of_5": {"ms_per_pair": bms / len(pairs), "aggregate_ms": agg / reps, "roofline_frac": achb / peak},
+            "reference_mode": {"ms_per_pair": ref_mode_ms, "ms_per_round_per_view": ref_mode_ms / 200.0,
+                               "what": "s3dmst_run on pair 000020: random plane init, 100 rounds of MST_PMS per view with the library's device-side "
+                                       "proposal generator, LabelToDisp, left-right check; host buffers in, both maps out"}}
 
 
 def bench_c2(api, synth, local, peak, B, fh_ctas, steps):
