@@ -810,9 +810,20 @@ static int s3_agg_cluster_nodes(const s3dmst_ctx* ctx) {
     const int p = ctx->P.agg_cluster_nodes;
     return p < 0 ? 0 : p > 0 ? p : env ? env : 32768;
 }
-static int s3_agg_big_nodes() {
-    static const int v = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 256;
-    return v;
+// Trees of at least this many nodes get a CTA of 32 warps and an SM of their own; the others 16 warps, two trees per SM.
+// Two small CTAs per SM hide each other's hand-over latencies — measured better whenever the launch has enough trees to
+// fill the GPU (C4 batch of 8: 40.4 -> 36.5 ms with every tree on 16 warps) — but a tree that would be the launch's critical
+// path on 16 warps needs the 32 (one C2 pair, whose 19 k-node tree is 1401 levels deep: 1.83 vs 2.93 ms; the FLIR pair: 6.7
+// vs 8.1).  So: the big CTA for trees whose nodes exceed alpha x what one of the 2 x SMs small-CTA slots would get if the
+// launch were spread perfectly.  alpha = 0.25 measured (0.25 / 0.5 / 1: C2 pair 1.85 / 1.88 / 2.02 ms, FLIR pair 6.66 / 7.55 /
+// 8.17, C4 pair 5.02 / 5.79 / 4.64, C4 batch 36.8 / 36.5 / 36.5); development overrides: S3_AGG_BIG_ALPHA, S3_AGG_BIG (the
+// threshold itself).  The three size classes are launched on three streams and run side by side.
+static int s3_agg_big_nodes(const s3dmst_ctx* ctx, double unit_nodes_total) {
+    static const int v = getenv("S3_AGG_BIG") ? atoi(getenv("S3_AGG_BIG")) : 0;
+    static const double alpha = getenv("S3_AGG_BIG_ALPHA") ? atof(getenv("S3_AGG_BIG_ALPHA")) : 0.25;
+    if (v > 0) return v;
+    const double per_slot = unit_nodes_total / (2.0 * ctx->num_sms);
+    return (int)std::max(256.0, std::min(1.0e9, alpha * per_slot));
 }
 
 template <typename K>
@@ -967,7 +978,9 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
     // The giant trees get a thread-block cluster (A3_CLUSTER CTAs = 256 warps on one tree), on the context's second
     // stream so that they run beside the rest; all but the smallest of the others get 32 warps and an SM of their own;
     // the rest 16 warps, two trees per SM.
-    const int cl_nodes = s3_agg_cluster_nodes(ctx), big_nodes = s3_agg_big_nodes();
+    double unit_nodes_total = 0.0;
+    for (const auto& e : u) unit_nodes_total += e.first;
+    const int cl_nodes = s3_agg_cluster_nodes(ctx), big_nodes = s3_agg_big_nodes(ctx, unit_nodes_total);
     int n_cl = 0;
     while (cl_nodes > 0 && n_cl < (int)u.size() && u[n_cl].first >= cl_nodes) n_cl++;
     int n_big = n_cl;
@@ -1012,15 +1025,27 @@ int s3_aggregate_flow_multi(s3dmst_ctx** ctxs, int nctx, int views_mask, int d0,
         S3_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
         launch_stream = ctx->stream;
     }
+    // the three size classes run side by side (streams in one launch order would make the small trees wait for the last
+    // big one while most SMs idle)
+    if (n_big && n_small) {
+        if (!n_cl) S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        S3_CUDA(cudaStreamWaitEvent(ctx->stream_big, ctx->ev_fork, 0));
+        launch_stream = ctx->stream_big;
+    }
     if (n_big) {
         A.unit0 = n_cl;
         A3_DISPATCH(true, 256, 64, 1, n_big, 1024);   // 128 KB ring, one tree per SM
+    }
+    if (n_big && n_small) {
+        S3_CUDA(cudaEventRecord(ctx->ev_join_big, ctx->stream_big));
+        launch_stream = ctx->stream;
     }
     if (n_small) {
         A.unit0 = n_cl + n_big;
         A3_DISPATCH(false, 128, 32, 1, n_small, 512);  // 64 KB ring: two trees per SM
     }
     if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (n_big && n_small) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_big, 0));
 #undef A3_DISPATCH
 #undef A3_LAUNCH
 #undef A3_LAUNCH_F
@@ -1086,7 +1111,9 @@ int s3_pms_flow_plan(s3dmst_ctx* ctx, int view, const int* h_prop_off, double* s
     char* ubase = reinterpret_cast<char*>(ctx->units_dev);
     S3_TRY(s3_h2d_staged(ctx, ubase, &G, sizeof G));
     S3_TRY(s3_h2d_staged(ctx, ubase + tbytes, units.data(), ubytes));
-    const int cl_nodes = s3_agg_cluster_nodes(ctx), big_nodes = s3_agg_big_nodes();
+    double unit_nodes_total = 0.0;
+    for (const auto& e : u) unit_nodes_total += e.first;
+    const int cl_nodes = s3_agg_cluster_nodes(ctx), big_nodes = s3_agg_big_nodes(ctx, unit_nodes_total);
     int n_cl = 0;
     while (cl_nodes > 0 && n_cl < (int)u.size() && u[n_cl].first >= cl_nodes) n_cl++;
     int n_big = n_cl;
@@ -1121,15 +1148,22 @@ int s3_pms_flow_launch(s3dmst_ctx* ctx, int view, const PmsFlowPlan* plan, const
         S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, A3_CL_NEAR, true, A3_CLUSTER>, n_cl * A3_CLUSTER, 1024, agg3_smem_bytes(1, 256, sizeof(double)), A3_CLUSTER, ctx->stream_aux, A));
         S3_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
     }
+    const bool split = n_big && n_small;  // the size classes run side by side (see s3_aggregate_flow_multi)
+    if (split) {
+        if (!n_cl) S3_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        S3_CUDA(cudaStreamWaitEvent(ctx->stream_big, ctx->ev_fork, 0));
+    }
     if (n_big) {
         A.unit0 = n_cl;
-        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, 64, true, 1>, n_big, 1024, agg3_smem_bytes(1, 256, sizeof(double)), 1, ctx->stream, A));
+        S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, true, 256, 64, true, 1>, n_big, 1024, agg3_smem_bytes(1, 256, sizeof(double)), 1, split ? ctx->stream_big : ctx->stream, A));
+        if (split) S3_CUDA(cudaEventRecord(ctx->ev_join_big, ctx->stream_big));
     }
     if (n_small) {
         A.unit0 = n_cl + n_big;
         S3_TRY(agg3_launch(ctx, k_agg_flow<double, 1, false, false, 128, 32, true, 1>, n_small, 512, agg3_smem_bytes(1, 128, sizeof(double)), 1, ctx->stream, A));
     }
     if (n_cl) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (split) S3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_big, 0));
     S3_EV_END(S3DMST_T_PMS, view);
     return 0;
 }

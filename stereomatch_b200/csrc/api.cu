@@ -187,6 +187,8 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
     for (int i = 0; ok && i < S3DMST_T_COUNT * 4; i++) ok = cudaEventCreate(&ctx->ev[i / 4][(i / 2) & 1][i & 1]) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_xctx, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_big, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_join_big, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
@@ -234,6 +236,8 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream_aux) { cudaStreamSynchronize(ctx->stream_aux); cudaStreamDestroy(ctx->stream_aux); }
+    if (ctx->stream_big) { cudaStreamSynchronize(ctx->stream_big); cudaStreamDestroy(ctx->stream_big); }
+    if (ctx->ev_join_big) cudaEventDestroy(ctx->ev_join_big);
     if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stage) cudaFreeHost(ctx->stage);

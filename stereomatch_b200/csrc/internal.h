@@ -103,6 +103,8 @@ struct s3dmst_ctx {
     s3dmst_params P;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream_big = nullptr;   // third stream: the 32-warp CTAs of the large trees beside the small trees' launch
+    cudaEvent_t ev_join_big = nullptr;
     cudaStream_t stream_aux = nullptr;   // second stream: the cluster launch of the giant trees runs beside the other trees' launches
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int W = 0, H = 0, N = 0;
