@@ -256,6 +256,11 @@ int s3dmst_run(s3dmst_ctx* ctx, int Dmax, unsigned seed, int fill, float* left_d
  * batch fill the GPU where a single pair waits on its deepest tree), then LR check/fill per frame.
  * left_disp[i] / right_disp[i]: float[H][W] per frame (the arrays or any entry may be NULL). */
 int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp);
+/* The same for a stream of batches: returns once the copies into left_disp / right_disp (pinned host memory for a truly
+ * asynchronous copy) are QUEUED on the frames' streams; they are complete after s3dmst_sync on the frame's context (or
+ * any later synchronising call on it).  The next batch on the same contexts (s3dmst_set_images_async + this call) can be
+ * queued at once: a frame's upload and forest start while the other frames' results are still on their way out. */
+int s3dmst_run_dense_batch_async(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp);
 /* The two halves of s3dmst_run_dense_batch, for software pipelining over consecutive batches (two sets of contexts,
  * two host threads): front = forests + cost volumes of every frame (latency-bound, many small kernels), back = the
  * joint aggregation launch (HBM-bound), LR check/fill and the copies.  front(k+1) may run while back(k) does. */

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_run_dense_batch_async", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_launch_count",
     "s3dmst_comm_unique_id", "s3dmst_comm_init", "s3dmst_comm_destroy", "s3dmst_comm_label_range", "s3dmst_reduce_minloc", "s3dmst_aggregate_dense_sharded",
     "s3dmst_comm_minloc_ms", "s3dmst_get_lr_mask", "s3dmst_weighted_median", "s3dmst_wmf_table", "s3dmst_norm_factor",
     "s3dmst_prepare_plane_cost", "s3dmst_get_plane_gradients",
@@ -117,6 +117,7 @@ def load_library():
     L.s3dmst_run.argtypes = [c_p, C.c_int, C.c_uint, C.c_int, c_p, c_p]
     L.s3dmst_reproject_to_3d.argtypes = [c_p, c_p, C.c_float, C.c_int, c_p, c_p]
     L.s3dmst_run_dense_batch.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
+    L.s3dmst_run_dense_batch_async.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_batch_front.argtypes = [C.POINTER(c_p), C.c_int, C.c_int]
     L.s3dmst_batch_back.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_stage_ms.argtypes = [c_p, C.c_int]
@@ -488,10 +489,12 @@ class Stereo3DMST:
         return self.L.s3dmst_launch_count(self.h)
 
 
-def run_dense_batch(engines, D, fill=False, fetch=True, out=None):
+def run_dense_batch(engines, D, fill=False, fetch=True, out=None, wait=True):
     """s3dmst_run_dense_batch over a list of Stereo3DMST handles (one frame each, images already set): forest and cost
     stages of the frames overlap, one aggregation launch covers every frame's trees.  Returns [(left, right), ...]
-    (float32 [N]) when fetch, else None.  `out` = optional [(left, right), ...] of preallocated (e.g. pinned) buffers."""
+    (float32 [N]) when fetch, else None.  `out` = optional [(left, right), ...] of preallocated (e.g. pinned) buffers.
+    wait=False (s3dmst_run_dense_batch_async): the copies into `out` are only queued; they are complete after
+    `sync()` on the frame's handle."""
     n = len(engines)
     L = engines[0].L
     hs = (c_p * n)(*[e.h for e in engines])
@@ -502,7 +505,7 @@ def run_dense_batch(engines, D, fill=False, fetch=True, out=None):
         pr = (c_p * n)(*[c_p(_addr(o[1])) for o in out])
     else:
         pl = pr = None
-    rc = L.s3dmst_run_dense_batch(hs, n, int(D), int(fill), pl, pr)
+    rc = (L.s3dmst_run_dense_batch if wait else L.s3dmst_run_dense_batch_async)(hs, n, int(D), int(fill), pl, pr)
     if rc != 0:
         raise S3Error(f"s3dmst error {rc}: {L.s3dmst_last_error(engines[0].h).decode()}")
     for e in engines:

@@ -749,6 +749,7 @@ int s3dmst_run(s3dmst_ctx* ctx, int Dmax, unsigned seed, int fill, float* left_d
 }
 
 // phases: bit 0 = front (forests + cost volumes of every frame), bit 1 = back (joint aggregation, LR check, copies)
+// phases: 1 = front, 2 = back, 4 = do not wait for the copies into left_disp / right_disp
 static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp, int phases) {
     if (!ctxs || n < 1) return S3DMST_E_ARG;
     s3dmst_ctx* ctx = ctxs[0];
@@ -808,13 +809,16 @@ static int run_dense_batch_impl(s3dmst_ctx** ctxs, int n, int D, int fill, float
         if (left_disp && left_disp[c]) S3_CUDA(cudaMemcpyAsync(left_disp[c], cx->v[0].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
         if (right_disp && right_disp[c]) S3_CUDA(cudaMemcpyAsync(right_disp[c], cx->v[1].disp_f, sizeof(float) * cx->N, cudaMemcpyDeviceToHost, cx->stream));
     }
-    if (left_disp || right_disp)
+    if ((left_disp || right_disp) && !(phases & 4))
         for (int c = 0; c < n; c++) S3_CUDA(cudaStreamSynchronize(ctxs[c]->stream));
     return 0;
 }
 
 int s3dmst_run_dense_batch(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {
     return run_dense_batch_impl(ctxs, n, D, fill, left_disp, right_disp, 3);
+}
+int s3dmst_run_dense_batch_async(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {
+    return run_dense_batch_impl(ctxs, n, D, fill, left_disp, right_disp, 3 | 4);
 }
 int s3dmst_batch_front(s3dmst_ctx** ctxs, int n, int D) { return run_dense_batch_impl(ctxs, n, D, 0, nullptr, nullptr, 1); }
 int s3dmst_batch_back(s3dmst_ctx** ctxs, int n, int D, int fill, float** left_disp, float** right_disp) {

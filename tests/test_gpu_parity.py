@@ -613,6 +613,21 @@ def test_run_dense_batch_matches_single_frames(api, oracle):
         dro = oracle.aggregate_dense(oracle.forest(R), rv)[0].astype(np.float32)
         want, _ = oracle.lr_check(dlo, dro, W, H, D, True)
         assert np.array_equal(bits(dl), bits(want)) and np.array_equal(bits(dr), bits(dro))
+    # the asynchronous variant: two batches queued back to back into two sets of host buffers, read after sync()
+    import torch
+    bufs = [[(torch.empty(W * H, dtype=torch.float32).pin_memory().numpy(), torch.empty(W * H, dtype=torch.float32).pin_memory().numpy())
+             for _ in engs] for _ in range(2)]
+    for k in range(2):
+        for e, (L, R, _) in zip(engs, frames if k == 0 else frames[::-1]):
+            e.set_images(L, R)
+        api.run_dense_batch(engs, D, fill=True, out=bufs[k], wait=False)
+    for e in engs:
+        e.sync()
+    for k in range(2):
+        for (dl, dr), (bl, br) in zip(outs if k == 0 else outs[::-1], bufs[k]):
+            assert np.array_equal(bits(dl), bits(bl)) and np.array_equal(bits(dr), bits(br))
+    for e, (L, R, _) in zip(engs, frames):
+        e.set_images(L, R)
     # a second batch on the same contexts (state reuse) with D not a multiple of the slice width
     outs = api.run_dense_batch(engs[:2], 36, fill=False)
     for (L, R, _), (dl, dr) in zip(frames[:2], outs):
