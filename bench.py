@@ -506,22 +506,27 @@ def run_gpu(args):
         sampler.start()
     launches0 = sum(e.launch_count() for e in engs)
     stage_tot = np.zeros(4)
+    for e in engs:       # the library accumulates its per-stage CUDA-event times over the calls of the timed region
+        for st in (api.T_FOREST, api.T_COST, api.T_AGG, api.T_POST):
+            e.stage_total_ms(st, reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        step()
-        for e in engs:
-            e.sync()
-        # aggregation: ONE launch set per step (engine 0's stream); forest/cost: mean over the frames' own streams (they overlap)
-        stage_tot[api.T_AGG] += engs[0].stage_ms(api.T_AGG)
-        stage_tot[api.T_FOREST] += float(np.mean([e.stage_ms(api.T_FOREST) for e in engs]))
-        stage_tot[api.T_COST] += float(np.mean([e.stage_ms(api.T_COST) for e in engs]))
-        stage_tot[api.T_POST] += float(np.mean([e.stage_ms(api.T_POST) for e in engs]))
+        step()           # queued back to back: no host synchronisation between the steps
+    for e in engs:
+        e.sync()
     ev1.record()
     barrier()
     t_wall = (time.perf_counter() - t_wall) * 1e3
+    # aggregation: ONE launch set per step (engine 0's stream); forest/cost/post: mean over the frames' own streams (they overlap)
+    agg_total, agg_samples = engs[0].stage_total_ms(api.T_AGG)
+    if agg_samples != args.steps:
+        raise SystemExit(f"bench.py: {agg_samples} aggregation timings for {args.steps} steps")
+    stage_tot[api.T_AGG] = agg_total
+    for st in (api.T_FOREST, api.T_COST, api.T_POST):
+        stage_tot[st] = float(np.mean([e.stage_total_ms(st)[0] for e in engs]))
     # the frames run on their own streams: the default-stream events bracket host-synchronised steps, so take the larger
     ms_max = maxms(max(ev0.elapsed_time(ev1), t_wall))
     launches = sum(e.launch_count() for e in engs) - launches0

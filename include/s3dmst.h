@@ -272,6 +272,10 @@ enum {
     S3DMST_T_FOREST = 0, S3DMST_T_COST = 1, S3DMST_T_AGG = 2, S3DMST_T_POST = 3, S3DMST_T_PMS = 4, S3DMST_T_COUNT = 5
 };
 double s3dmst_stage_ms(s3dmst_ctx* ctx, int stage);
+/* The same accumulated over every call since the last reset (a caller that queues call after call without synchronising
+ * still gets every sample: up to 4 per stage and view may be in flight).  Waits for the samples still running.
+ * *samples = number of timed intervals in the total (may be NULL); reset != 0 clears the accumulator afterwards. */
+double s3dmst_stage_total_ms(s3dmst_ctx* ctx, int stage, int* samples, int reset);
 /* Number of kernels this library has launched on the context since creation. */
 long long s3dmst_launch_count(const s3dmst_ctx* ctx);
 

@@ -174,6 +174,11 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
     if (params) ctx->P = *params; else s3dmst_default_params(&ctx->P);
     memset(ctx->ev, 0, sizeof ctx->ev);
     memset(ctx->ev_set, 0, sizeof ctx->ev_set);
+    memset(ctx->ev_slot, 0, sizeof ctx->ev_slot);
+    memset(ctx->ev_state, 0, sizeof ctx->ev_state);
+    memset(ctx->ev_acc_ms, 0, sizeof ctx->ev_acc_ms);
+    memset(ctx->ev_acc_n, 0, sizeof ctx->ev_acc_n);
+    memset(ctx->ev_lost, 0, sizeof ctx->ev_lost);
     bool ok = cudaSetDevice(device) == cudaSuccess;
     cudaDeviceProp prop;
     ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
@@ -184,7 +189,10 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
         ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
         ctx->own_stream = ok;
     }
-    for (int i = 0; ok && i < S3DMST_T_COUNT * 4; i++) ok = cudaEventCreate(&ctx->ev[i / 4][(i / 2) & 1][i & 1]) == cudaSuccess;
+    {
+        cudaEvent_t* evs = &ctx->ev[0][0][0][0];
+        for (int i = 0; ok && i < S3DMST_T_COUNT * 2 * S3_EV_SLOTS * 2; i++) ok = cudaEventCreate(&evs[i]) == cudaSuccess;
+    }
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_xctx, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_big, cudaStreamNonBlocking) == cudaSuccess;
@@ -230,8 +238,11 @@ void s3dmst_destroy(s3dmst_ctx* ctx) {
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
     s3_rectify_free(ctx);
     DFREE(ctx->lut_w); DFREE(ctx->lut_w2); DFREE(ctx->lut_wf); DFREE(ctx->lut_w2f); DFREE(ctx->pms_scratch); DFREE(ctx->units_dev); DFREE(ctx->fh_sync); DFREE(ctx->abc_init);
-    for (int i = 0; i < S3DMST_T_COUNT * 4; i++)
-        if (ctx->ev[i / 4][(i / 2) & 1][i & 1]) cudaEventDestroy(ctx->ev[i / 4][(i / 2) & 1][i & 1]);
+    {
+        cudaEvent_t* evs = &ctx->ev[0][0][0][0];
+        for (int i = 0; i < S3DMST_T_COUNT * 2 * S3_EV_SLOTS * 2; i++)
+            if (evs[i]) cudaEventDestroy(evs[i]);
+    }
     if (ctx->ev_xctx) cudaEventDestroy(ctx->ev_xctx);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -262,11 +273,36 @@ double s3dmst_stage_ms(s3dmst_ctx* ctx, int stage) {
     double total = 0.0;
     for (int view = 0; view < 2; view++) {
         if (!ctx->ev_set[stage][view]) continue;
+        cudaEvent_t* p = ctx->ev[stage][view][ctx->ev_slot[stage][view]];
         float ms = 0.f;
-        if (cudaEventSynchronize(ctx->ev[stage][view][1]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
-        if (cudaEventElapsedTime(&ms, ctx->ev[stage][view][0], ctx->ev[stage][view][1]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+        if (cudaEventSynchronize(p[1]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+        if (cudaEventElapsedTime(&ms, p[0], p[1]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
         total += ms;
     }
+    return total;
+}
+
+// completed pairs -> accumulators (wait: also the ones still running)
+extern "C++" void s3_ev_harvest(s3dmst_ctx* ctx, int stage, int view, bool wait) {
+    for (int sl = 0; sl < S3_EV_SLOTS; sl++) {
+        if (!ctx->ev_state[stage][view][sl]) continue;
+        cudaEvent_t* p = ctx->ev[stage][view][sl];
+        const cudaError_t q = wait ? cudaEventSynchronize(p[1]) : cudaEventQuery(p[1]);
+        if (q != cudaSuccess) { cudaGetLastError(); continue; }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p[0], p[1]) == cudaSuccess) { ctx->ev_acc_ms[stage] += ms; ctx->ev_acc_n[stage]++; }
+        else cudaGetLastError();
+        ctx->ev_state[stage][view][sl] = 0;
+    }
+}
+
+double s3dmst_stage_total_ms(s3dmst_ctx* ctx, int stage, int* samples, int reset) {
+    if (!ctx || stage < 0 || stage >= S3DMST_T_COUNT) return -1.0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+    for (int view = 0; view < 2; view++) s3_ev_harvest(ctx, stage, view, true);
+    const double total = ctx->ev_acc_ms[stage];
+    if (samples) *samples = ctx->ev_acc_n[stage];
+    if (reset) { ctx->ev_acc_ms[stage] = 0.0; ctx->ev_acc_n[stage] = 0; ctx->ev_lost[stage] = 0; }
     return total;
 }
 

@@ -24,6 +24,8 @@ struct __align__(16) NodeUp {
     uint32_t cw01, cw23;  // integer edge weights of children 0..3, 16 bits each
 };
 
+#define S3_EV_SLOTS 4   // stage-timer samples that may be in flight per (stage, view)
+
 struct View {
     // ---- image stage
     uint8_t* bgr = nullptr;    // [N*3] tightly packed copy of the input
@@ -114,8 +116,14 @@ struct s3dmst_ctx {
     double* lut_w2 = nullptr;  // [S3_NUM_W] 1 - w*w
     float* lut_wf = nullptr;   // fp32 copies for the fast path
     float* lut_w2f = nullptr;
-    cudaEvent_t ev[S3DMST_T_COUNT][2][2];  // [stage][view][begin/end]
-    bool ev_set[S3DMST_T_COUNT][2];
+    // Stage timers: a small ring of event pairs per (stage, view), so that a caller that queues call after call without
+    // synchronising still gets every sample: a pair is harvested into the accumulators once its end event has completed.
+    cudaEvent_t ev[S3DMST_T_COUNT][2][S3_EV_SLOTS][2];  // [stage][view][slot][begin/end]
+    int ev_slot[S3DMST_T_COUNT][2];                     // slot of the latest pair
+    unsigned char ev_state[S3DMST_T_COUNT][2][S3_EV_SLOTS];  // 0 = free / harvested, 1 = recorded, waiting to be harvested
+    bool ev_set[S3DMST_T_COUNT][2];                     // the latest pair belongs to the current call (s3dmst_stage_ms)
+    double ev_acc_ms[S3DMST_T_COUNT];                   // accumulated since the last reset (s3dmst_stage_total_ms)
+    int ev_acc_n[S3DMST_T_COUNT], ev_lost[S3DMST_T_COUNT];
     long long launches = 0;
     int fused_D = 0;           // > 0: the last dense run computed its matching cost in the aggregation kernel for this D (no volume yet)
     std::string err;
@@ -176,11 +184,21 @@ int s3_fail(s3dmst_ctx* c, int code, const char* fmt, ...);
         if (e__ != cudaSuccess)                                                                         \
             return s3_fail(ctx, S3DMST_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
     } while (0)
-#define S3_EV_BEGIN(stage, view) S3_CUDA(cudaEventRecord(ctx->ev[stage][view][0], ctx->stream))
-#define S3_EV_END(stage, view)                                              \
-    do {                                                                   \
-        S3_CUDA(cudaEventRecord(ctx->ev[stage][view][1], ctx->stream));    \
-        ctx->ev_set[stage][view] = true;                                   \
+void s3_ev_harvest(s3dmst_ctx* ctx, int stage, int view, bool wait);   // api.cu
+#define S3_EV_BEGIN(stage, view)                                                                          \
+    do {                                                                                                  \
+        s3_ev_harvest(ctx, stage, view, false);                                                           \
+        const int sl__ = (ctx->ev_slot[stage][view] + 1) % S3_EV_SLOTS;                                   \
+        if (ctx->ev_state[stage][view][sl__]) ctx->ev_lost[stage]++; /* still running: overwritten */     \
+        ctx->ev_state[stage][view][sl__] = 0;                                                             \
+        ctx->ev_slot[stage][view] = sl__;                                                                 \
+        S3_CUDA(cudaEventRecord(ctx->ev[stage][view][sl__][0], ctx->stream));                             \
+    } while (0)
+#define S3_EV_END(stage, view)                                                                            \
+    do {                                                                                                  \
+        S3_CUDA(cudaEventRecord(ctx->ev[stage][view][ctx->ev_slot[stage][view]][1], ctx->stream));        \
+        ctx->ev_state[stage][view][ctx->ev_slot[stage][view]] = 1;                                        \
+        ctx->ev_set[stage][view] = true;                                                                  \
     } while (0)
 #define S3_TRY(call)            \
     do {                        \

@@ -626,6 +626,15 @@ def test_run_dense_batch_matches_single_frames(api, oracle):
     for k in range(2):
         for (dl, dr), (bl, br) in zip(outs if k == 0 else outs[::-1], bufs[k]):
             assert np.array_equal(bits(dl), bits(bl)) and np.array_equal(bits(dr), bits(br))
+    # ... and the library's stage timers kept every sample of the calls queued without synchronisation in between
+    for e in engs:
+        e.stage_total_ms(api.T_AGG, reset=True); e.stage_total_ms(api.T_FOREST, reset=True)
+    for k in range(3):
+        api.run_dense_batch(engs, D, fill=True, fetch=False)
+    tot, n = engs[0].stage_total_ms(api.T_AGG)
+    assert n == 3 and tot > 0.0
+    assert all(e.stage_total_ms(api.T_FOREST)[1] == 3 for e in engs)
+    assert abs(engs[0].stage_ms(api.T_AGG) - tot / 3) < tot   # the latest sample is still readable
     for e, (L, R, _) in zip(engs, frames):
         e.set_images(L, R)
     # a second batch on the same contexts (state reuse) with D not a multiple of the slice width
