@@ -514,9 +514,9 @@ def run_gpu(args):
     ev0.record()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        step()           # queued back to back: no host synchronisation between the steps
-    for e in engs:
-        e.sync()
+        step()
+        for e in engs:   # (queueing the steps back to back is 2 % slower: the next forests then start inside this step's aggregation tail)
+            e.sync()
     ev1.record()
     barrier()
     t_wall = (time.perf_counter() - t_wall) * 1e3
