@@ -66,6 +66,9 @@ typedef struct s3dmst_params {
                            0 / 1 = the aggregation kernel computes the matching cost itself and no volume is built
                            (s3dmst_get_cost_volume / s3dmst_aggregate_dense build it on demand afterwards); -1 = build the
                            volume first.  Results are bit-identical either way.                                      */
+    int comm_p2p;       /* label sharding: 0 / 1 = the MIN-LOC runs as ONE kernel over peer memory (every rank's result buffers
+                           mapped through CUDA IPC, NVLink loads and stores) when all ranks can map each other, else over
+                           NCCL; -1 = always the two NCCL all-reduces                                                 */
     int fh_cluster;     /* 0: the forest kernel is a cooperative grid with a software barrier per view; 8 or 16: every view gets one
                            thread-block cluster of that many CTAs and the hardware cluster barrier                      */
     int pms_cost_mode;  /* data term of the 3D-label (PatchMatch) search: 0 = compute3DLabelCost on the cost volume (the

@@ -33,7 +33,7 @@ class S3Params(C.Structure):
                 ("cost_cap", C.c_float), ("cost_offset", C.c_float), ("cost_scale", C.c_float), ("oob_cost", C.c_float),
                 ("num_iter", C.c_int), ("refine_floor", C.c_float), ("exact", C.c_int), ("keep_aggregated", C.c_int),
                 ("agg_threads", C.c_int), ("agg_cache_nodes", C.c_int), ("agg_ring_nodes", C.c_int), ("agg_kernel", C.c_int),
-                ("fh_ctas", C.c_int), ("fh_threads", C.c_int), ("fuse_cost", C.c_int), ("fh_cluster", C.c_int), ("pms_cost_mode", C.c_int), ("pm_alpha", C.c_float), ("pm_tau_c", C.c_float),
+                ("fh_ctas", C.c_int), ("fh_threads", C.c_int), ("fuse_cost", C.c_int), ("comm_p2p", C.c_int), ("fh_cluster", C.c_int), ("pms_cost_mode", C.c_int), ("pm_alpha", C.c_float), ("pm_tau_c", C.c_float),
                 ("pm_tau_g", C.c_float), ("agg_cluster_nodes", C.c_int)]
 
 

@@ -116,6 +116,7 @@ static int alloc_view(s3dmst_ctx* ctx, View& V, int N) {
 static int set_size(s3dmst_ctx* ctx, int W, int H) {
     if (W < 1 || H < 1 || (long long)W * H > (1ll << 27)) return s3_fail(ctx, S3DMST_E_ARG, "image size %dx%d unsupported", W, H);
     if (ctx->W == W && ctx->H == H) return 0;
+    S3_TRY(s3_comm_before_free(ctx));  // result buffers mapped into the other ranks: they let go of them first (collective)
     for (int i = 0; i < 2; i++) free_view(ctx->v[i]);
     ctx->W = ctx->H = ctx->N = 0;
     ctx->forest_pending = 0;
@@ -153,6 +154,7 @@ void s3dmst_default_params(s3dmst_params* p) {
     p->fh_threads = 0;
     p->agg_cluster_nodes = 0;
     p->fuse_cost = 0;
+    p->comm_p2p = 0;
     p->fh_cluster = 0;
     p->pms_cost_mode = 0;
     p->pm_alpha = 0.9f;
@@ -179,6 +181,9 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
     memset(ctx->ev_acc_ms, 0, sizeof ctx->ev_acc_ms);
     memset(ctx->ev_acc_n, 0, sizeof ctx->ev_acc_n);
     memset(ctx->ev_lost, 0, sizeof ctx->ev_lost);
+    memset(ctx->p2p_best, 0, sizeof ctx->p2p_best);
+    memset(ctx->p2p_disp, 0, sizeof ctx->p2p_disp);
+    memset(ctx->p2p_flags, 0, sizeof ctx->p2p_flags);
     bool ok = cudaSetDevice(device) == cudaSuccess;
     cudaDeviceProp prop;
     ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;

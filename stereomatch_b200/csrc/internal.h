@@ -24,6 +24,7 @@ struct __align__(16) NodeUp {
     uint32_t cw01, cw23;  // integer edge weights of children 0..3, 16 bits each
 };
 
+#define S3_P2P_MAX 16   // ranks of a label-sharded communicator that can use the peer-memory MIN-LOC
 #define S3_EV_SLOTS 4   // stage-timer samples that may be in flight per (stage, view)
 
 struct View {
@@ -149,6 +150,17 @@ struct s3dmst_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_comm[2] = {nullptr, nullptr}, ev_comm_t[4] = {nullptr, nullptr, nullptr, nullptr};
     bool comm_timed = false;
+    // MIN-LOC over peer memory (comm.cu): every rank's (best, disparity) buffers and flag array mapped into this process
+    // through CUDA IPC; rank r reduces pixel slice r reading all ranks over NVLink and writes the result to all of them
+    bool p2p_tried = false, p2p_ok = false;
+    int p2p_N = 0, p2p_epoch = 0;
+    double* p2p_best[2][S3_P2P_MAX];
+    int32_t* p2p_disp[2][S3_P2P_MAX];
+    int* p2p_flags[S3_P2P_MAX];          // p2p_flags[comm_rank] = this rank's own array (cudaMalloc)
+    int* p2p_counter = nullptr;          // CTAs of this rank that finished their share
+    int* p2p_err_host = nullptr;         // mapped pinned: set by a kernel whose wait for the peers timed out
+    int* p2p_err_dev = nullptr;
+    void* p2p_xbuf = nullptr;
     double* gmin = nullptr;
     size_t gmin_cap = 0;
     float* abc_init = nullptr;      // the reference's random plane initialisation for (abc_init_w x abc_init_h, abc_init_d), kept on the device
@@ -221,6 +233,7 @@ int s3_set_rectify_maps(s3dmst_ctx* ctx, int view, const int16_t* map_xy, const 
 int s3_remap_raw_pair(s3dmst_ctx* ctx, const uint8_t* left_raw, const uint8_t* right_raw, int sw, int sh, int stride);
 void s3_rectify_free(s3dmst_ctx* ctx);
 void s3_remap_table(int16_t* tab);  // [1024][4]
+int s3_comm_before_free(s3dmst_ctx* ctx);                         // comm.cu: peers unmap this rank's result buffers (collective; no-op without them)
 int s3_cost_adgrad(s3dmst_ctx* ctx, int D, int apply_ingest);     // cost.cu
 int s3_cost_from_dmajor(s3dmst_ctx* ctx, int view, const float* dev_dmajor, int D, int apply_ingest);
 int s3_cost_to_dmajor(s3dmst_ctx* ctx, int view, float* dev_dmajor);
