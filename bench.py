@@ -375,7 +375,7 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
 
     eng = api.Stereo3DMST(device=local, **eng_kw())
     parallel.comm_init_from_torch(eng)
-    out = {"ranks": world, "collective": "2 x ncclAllReduce(MIN) + mask kernel per view, on the library's communicator (csrc/comm.cu)"}
+    out = {"ranks": world, "collective": "per-pixel MIN-LOC of (best cost f64, disparity i32), lowest disparity on ties (csrc/comm.cu)"}
     # ---- (a) small pair, bit-exact against the CPU oracle's full-range result, on every rank
     cw, ch, cd = 480, 270, 96
     L, R, _ = synth.make_pair(cw, ch, cd, seed=synth.BASE_SEED + 100)
@@ -394,6 +394,8 @@ def bench_label_sharded(api, parallel, synth, dist, torch, local, rank, world, s
         disp, best = eng.get_dense_result(view)
         ok &= bool(np.array_equal(disp, do) and np.array_equal(best.view(np.uint64), bo.view(np.uint64)))
     out["check"] = allmin_flag(ok)
+    out["transport"] = {1: "one kernel over peer memory (CUDA IPC mappings of every rank's result buffers, NVLink loads/stores)",
+                        0: "two ncclAllReduce(MIN) + mask kernel per view"}.get(eng.comm_transport(), "none")
     out["check_case"] = f"{cw}x{ch} D={cd}: every rank's reduced (disparity, best cost) == the oracle's full-range result, bit for bit"
     # ---- (b) the C5 shape: 3840x2160, D = 512
     w5, h5, d5 = 3840, 2160, 512

@@ -176,6 +176,11 @@ int s3dmst_comm_destroy(s3dmst_ctx* ctx);
 int s3dmst_comm_label_range(const s3dmst_ctx* ctx, int D, int* d0, int* d1);
 int s3dmst_reduce_minloc(s3dmst_ctx* ctx, int view);
 int s3dmst_aggregate_dense_sharded(s3dmst_ctx* ctx, int D);
+/* How the MIN-LOC of the sharded calls travels: 1 = one kernel over peer memory (every rank's result buffers mapped through
+ * CUDA IPC; decided collectively at the first s3dmst_aggregate_dense_sharded, params.comm_p2p), 0 = two NCCL all-reduces,
+ * -1 = no communicator.  While the mapping is live, changing the image size (s3dmst_set_images with another W x H) and
+ * s3dmst_comm_destroy / s3dmst_destroy are collective: every rank's buffers are unmapped everywhere before one is freed. */
+int s3dmst_comm_transport(const s3dmst_ctx* ctx);
 double s3dmst_comm_minloc_ms(s3dmst_ctx* ctx);
 
 /* Dense disparity (int) -> float disparity map used by the LR check. */

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "s3dmst_set_cost_volume", "s3dmst_get_cost_volume", "s3dmst_aggregate_dense", "s3dmst_get_aggregated",
     "s3dmst_dense_result_dev", "s3dmst_minloc_mask", "s3dmst_dense_to_disparity", "s3dmst_set_labels", "s3dmst_get_labels",
     "s3dmst_reset_min_cost", "s3dmst_get_min_cost", "s3dmst_pms_apply", "s3dmst_label_to_disp", "s3dmst_set_disparity",
-    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_run_dense_batch_async", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_stage_ms", "s3dmst_stage_total_ms", "s3dmst_launch_count",
+    "s3dmst_get_disparity", "s3dmst_lr_check", "s3dmst_init_labels", "s3dmst_pms_iterate", "s3dmst_run", "s3dmst_run_dense", "s3dmst_run_dense_batch", "s3dmst_run_dense_batch_async", "s3dmst_batch_front", "s3dmst_batch_back", "s3dmst_reproject_to_3d", "s3dmst_comm_transport", "s3dmst_stage_ms", "s3dmst_stage_total_ms", "s3dmst_launch_count",
     "s3dmst_comm_unique_id", "s3dmst_comm_init", "s3dmst_comm_destroy", "s3dmst_comm_label_range", "s3dmst_reduce_minloc", "s3dmst_aggregate_dense_sharded",
     "s3dmst_comm_minloc_ms", "s3dmst_get_lr_mask", "s3dmst_weighted_median", "s3dmst_wmf_table", "s3dmst_norm_factor",
     "s3dmst_prepare_plane_cost", "s3dmst_get_plane_gradients",
@@ -122,6 +122,7 @@ def load_library():
     L.s3dmst_batch_back.argtypes = [C.POINTER(c_p), C.c_int, C.c_int, C.c_int, C.POINTER(c_p), C.POINTER(c_p)]
     L.s3dmst_stage_ms.argtypes = [c_p, C.c_int]
     L.s3dmst_stage_ms.restype = C.c_double
+    L.s3dmst_comm_transport.argtypes = [c_p]
     L.s3dmst_stage_total_ms.argtypes = [c_p, C.c_int, C.POINTER(C.c_int), C.c_int]
     L.s3dmst_stage_total_ms.restype = C.c_double
     L.s3dmst_launch_count.argtypes = [c_p]
@@ -486,6 +487,10 @@ class Stereo3DMST:
 
     def stage_ms(self, stage):
         return self.L.s3dmst_stage_ms(self.h, stage)
+
+    def comm_transport(self):
+        """1 = MIN-LOC over peer memory, 0 = NCCL all-reduces, -1 = no communicator (s3dmst_comm_transport)."""
+        return self.L.s3dmst_comm_transport(self.h)
 
     def stage_total_ms(self, stage, reset=False):
         """(accumulated ms, samples) of a stage over every call since the last reset (s3dmst_stage_total_ms)."""

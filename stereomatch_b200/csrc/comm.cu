@@ -439,6 +439,8 @@ int s3dmst_aggregate_dense_sharded(s3dmst_ctx* ctx, int D) {
     return 0;
 }
 
+int s3dmst_comm_transport(const s3dmst_ctx* ctx) { return !ctx || !ctx->comm ? -1 : (ctx->p2p_ok ? 1 : 0); }
+
 double s3dmst_comm_minloc_ms(s3dmst_ctx* ctx) {
     if (!ctx->comm_timed) return -1.0;
     double total = 0.0;
