@@ -3,7 +3,9 @@
 // exchange is a per-pixel MIN-LOC of (aggregated cost, disparity) — the reduction that replaces the serial
 // `if (agg < min_cost)` over ascending labels of the reference (Stereo3DMST.cpp:173-185; dense mode: SURVEY A13).
 //
-// NCCL has no MINLOC and the exact-mode cost is fp64, so it is two all-reduces on the context's communication stream:
+// Default: ONE kernel over peer memory (k_minloc_p2p below: every rank's result buffers mapped through CUDA IPC).  The
+// fall-back, and the transport of s3dmst_reduce_minloc before the first sharded call, is NCCL — which has no MINLOC, and
+// the exact-mode cost is fp64, so it is two all-reduces on the context's communication stream:
 //   1. ncclAllReduce(MIN, f64) of the best cost                       -> global minimum per pixel
 //   2. disparity := INT32_MAX where local cost != global minimum      (k_minloc_mask)
 //      ncclAllReduce(MIN, i32) of the disparity                       -> lowest d attaining the minimum

@@ -741,16 +741,30 @@ def test_label_sharded_reduce_partial_ranges(api, oracle):
     eng.close()
     # s3dmst_aggregate_dense_sharded without any cost volume (the aggregation kernel computes the matching cost) == with one
     res = []
-    for prebuilt in (False, True):
-        e = api.Stereo3DMST()
+    for prebuilt, p2p in ((False, 0), (True, 0), (False, -1)):
+        # comm_p2p: 0 = the MIN-LOC as one kernel over peer memory when the ranks can map each other (one rank: itself),
+        # -1 = the two NCCL all-reduces
+        e = api.Stereo3DMST(comm_p2p=p2p)
         e.comm_init(e.comm_unique_id(), 0, 1)
+        assert e.comm_transport() == 0   # decided at the first sharded call
         e.set_images(L, R)
         e.build_forest(0); e.build_forest(1)
         if prebuilt:
             e.build_cost_volume(D)
         e.aggregate_dense_sharded(D)
         e.sync()
+        assert e.comm_transport() in ((0,) if p2p < 0 else (0, 1))
         res.append([e.get_dense_result(v) for v in (0, 1)])
+        if p2p == 0 and not prebuilt:   # another image size on a live mapping: the buffers are re-mapped
+            L2, R2, _ = make(96, 64, 16, 3, 0)
+            e.set_images(L2, R2)
+            e.build_forest(0); e.build_forest(1)
+            e.aggregate_dense_sharded(16)
+            e.sync()
+            lv2, _ = oracle.cost_adgrad(L2, R2, 16)
+            do2, bo2, _ = oracle.aggregate_dense(oracle.forest(L2), lv2)
+            d2, b2 = e.get_dense_result(0)
+            assert np.array_equal(d2, do2) and np.array_equal(bits(b2), bits(bo2))
         e.close()
     _, rv = oracle.cost_adgrad(L, R, D)
     for v, (img, vol) in enumerate(((L, lv), (R, rv))):
