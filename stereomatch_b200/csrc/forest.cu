@@ -590,11 +590,10 @@ __device__ long long g_dummy;
 // One node of one BFS level: decode the frontier word, fetch the adjacency record, drop the parent's entry.
 // Returns the child count; k0..k3 = the child entries in order, 0xFFFF-padded (kept in four registers: every use below
 // is straight-line code — the per-level instruction count of ONE warp is what bounds this kernel).
-__device__ __forceinline__ int bfs_expand(uint32_t fw, const unsigned long long* __restrict__ adjw, int& pix, uint32_t& k0, uint32_t& k1, uint32_t& k2,
+__device__ __forceinline__ int bfs_expand(uint32_t fw, unsigned long long rec, int& pix, uint32_t& k0, uint32_t& k1, uint32_t& k2,
                                           uint32_t& k3) {
     pix = (int)(fw & 0x0FFFFFFFu);
     const uint32_t pdir = (fw >> 28) & 7u;  // 4 = no parent (root); bit 31: the parent is S3_AGG_NEAR or more nodes back
-    const unsigned long long rec = __ldg(adjw + pix);
     const uint32_t lo = (uint32_t)rec, hi = (uint32_t)(rec >> 32);
     const uint32_t e0 = lo & 0xFFFFu, e1 = lo >> 16, e2 = hi & 0xFFFFu, e3 = hi >> 16;
     // f_k: the parent's entry sits at a position <= k; the list without it is e_k below it and e_{k+1} from there on
@@ -630,6 +629,10 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
     __shared__ int s_total;
     __shared__ int s_state[4];
     __shared__ uint32_t s_front[2][BFS_FRONT];
+    // the adjacency records of the frontier, fetched by the lane that DISCOVERS a node: the load (an L2 round trip, ~700
+    // cycles — an L1 prefetch did not shorten it) flies while that lane writes the node's records, and the level that
+    // expands the node finds its record in shared memory
+    __shared__ unsigned long long s_rec[2][BFS_FRONT];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     for (int u = bid; u < T; u += nb) {
@@ -642,6 +645,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
             node_dn[base] = make_int4(base, 0, 0, rp);
             lvl[0] = base;
             s_front[0][0] = (uint32_t)rp | (4u << 28);  // direction 4 = no parent
+            s_rec[0][0] = __ldg(adjw + rp);
         }
         __syncthreads();
         int a = base, b = base + 1, L = 0, cur = 0;
@@ -650,18 +654,22 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
 #endif
         // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record
         // one child of node g: frontier word, pixel -> node, root->leaf record, warm-up of its own children's lines
-        auto emit_child = [&](int g, int pix, uint32_t en, int h, int bnext, int Lc, int curc) {
+        auto emit_child = [&](int g, int pix, uint32_t en, int h, int bnext, int Lc, int curc) -> unsigned long long {
             const int dir = (int)(en & 7u);
             const int q = pix + ((dir & 2) ? 1 : -1) * ((dir == 0 || dir == 3) ? W : 1);  // 0 up, 1 left, 2 right, 3 down
             const uint32_t fw = (uint32_t)q | ((uint32_t)(3 - dir) << 28) | (h - g >= S3_AGG_NEAR ? 0x80000000u : 0u);  // the parent lies in the opposite direction
-            if (h - bnext < BFS_FRONT) s_front[curc ^ 1][h - bnext] = fw;
+            const bool in_smem = h - bnext < BFS_FRONT;
+            unsigned long long rec = 0ull;
+            if (in_smem) rec = __ldg(adjw + q);  // in flight during the stores below
+            if (in_smem) s_front[curc ^ 1][h - bnext] = fw;
             else front[h] = fw;
             pixel_node[q] = h;
             node_dn[h] = make_int4(g, (int)(en >> 3), Lc + 1, q);
             {  // q's possible children: rows above and below (q +- 1 share q's line)
-                if (q >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q - W));
-                if (q + W < NN) asm volatile("prefetch.global.L1 [%0];" ::"l"(adjw + q + W));
+                if (q >= W) asm volatile("prefetch.global.L2 [%0];" ::"l"(adjw + q - W));
+                if (q + W < NN) asm volatile("prefetch.global.L2 [%0];" ::"l"(adjw + q + W));
             }
+            return rec;
         };
         // emits the children of node g (child slots cb..cb+cc-1 of level L+1) and g's leaf->root record; `active` is false
         // for lanes without a node (they only take part in the warp-uniform votes)
@@ -676,15 +684,24 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                 if (cc == 0) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_LEAF;
                 else if (cb + cc - 1 - g >= S3_AGG_NEAR) reinterpret_cast<int*>(node_dn + g)[2] = Lc | S3_ND_FAR;
             }
+            unsigned long long r0 = 0ull, r1 = 0ull, r2 = 0ull, r3 = 0ull;
             if (__any_sync(0xffffffffu, active && cc > 0)) {
-                if (active && cc > 0) emit_child(g, pix, k0, cb, bnext, Lc, curc);
+                if (active && cc > 0) r0 = emit_child(g, pix, k0, cb, bnext, Lc, curc);
                 if (__any_sync(0xffffffffu, active && cc > 1)) {
-                    if (active && cc > 1) emit_child(g, pix, k1, cb + 1, bnext, Lc, curc);
+                    if (active && cc > 1) r1 = emit_child(g, pix, k1, cb + 1, bnext, Lc, curc);
                     if (__any_sync(0xffffffffu, active && cc > 2)) {
-                        if (active && cc > 2) emit_child(g, pix, k2, cb + 2, bnext, Lc, curc);
-                        if (active && cc > 3) emit_child(g, pix, k3, cb + 3, bnext, Lc, curc);
+                        if (active && cc > 2) r2 = emit_child(g, pix, k2, cb + 2, bnext, Lc, curc);
+                        if (active && cc > 3) r3 = emit_child(g, pix, k3, cb + 3, bnext, Lc, curc);
                     }
                 }
+            }
+            // the children's records, once they have arrived (every other store of the level is already on its way)
+            if (active) {
+                const int s0 = cb - bnext;
+                if (cc > 0 && s0 < BFS_FRONT) s_rec[curc ^ 1][s0] = r0;
+                if (cc > 1 && s0 + 1 < BFS_FRONT) s_rec[curc ^ 1][s0 + 1] = r1;
+                if (cc > 2 && s0 + 2 < BFS_FRONT) s_rec[curc ^ 1][s0 + 2] = r2;
+                if (cc > 3 && s0 + 3 < BFS_FRONT) s_rec[curc ^ 1][s0 + 3] = r3;
             }
         };
         while (true) {
@@ -695,7 +712,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                     uint32_t k0 = 0xFFFFu, k1 = 0xFFFFu, k2 = 0xFFFFu, k3 = 0xFFFFu;
                     const int g = a + lane;
                     uint32_t fwg = 0;
-                    if (g < b) { fwg = s_front[cur][lane]; cc = bfs_expand(fwg, adjw, pix, k0, k1, k2, k3); }
+                    if (g < b) { fwg = s_front[cur][lane]; cc = bfs_expand(fwg, s_rec[cur][lane], pix, k0, k1, k2, k3); }
                     BFS_CLK(q_load);
                     // exclusive prefix of cc (0..4) from three independent ballots
                     const uint32_t b0 = __ballot_sync(0xffffffffu, cc & 1), b1 = __ballot_sync(0xffffffffu, cc & 2), b2 = __ballot_sync(0xffffffffu, cc & 4);
@@ -724,7 +741,11 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(BfsArgs2 AA) {
                 int cc = 0, pix = 0;
                 uint32_t k0 = 0xFFFFu, k1 = 0xFFFFu, k2 = 0xFFFFu, k3 = 0xFFFFu;
                 uint32_t fwg = 0;
-                if (g < b) { fwg = g - a < BFS_FRONT ? s_front[cur][g - a] : front[g]; cc = bfs_expand(fwg, adjw, pix, k0, k1, k2, k3); }
+                if (g < b) {
+                    const bool in_smem = g - a < BFS_FRONT;
+                    fwg = in_smem ? s_front[cur][g - a] : front[g];
+                    cc = bfs_expand(fwg, in_smem ? s_rec[cur][g - a] : __ldg(adjw + (fwg & 0x0FFFFFFFu)), pix, k0, k1, k2, k3);
+                }
                 int incl = cc;
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, incl, o);
