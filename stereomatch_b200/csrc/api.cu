@@ -199,8 +199,15 @@ int s3dmst_create(s3dmst_ctx** out, int device, const s3dmst_params* params, voi
         for (int i = 0; ok && i < S3DMST_T_COUNT * 2 * S3_EV_SLOTS * 2; i++) ok = cudaEventCreate(&evs[i]) == cudaSuccess;
     }
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_xctx, cudaEventDisableTiming) == cudaSuccess;
-    if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) == cudaSuccess;
-    if (ok) ok = cudaStreamCreateWithFlags(&ctx->stream_big, cudaStreamNonBlocking) == cudaSuccess;
+    {
+        // the launches of the large trees (clusters, 32-warp CTAs) are a launch set's critical path: their CTAs go first
+        // when they compete with the small trees' launch for SMs (without it the FLIR pair's aggregation is 6.6 or 8.1 ms
+        // from run to run, depending on which launch the block scheduler happens to serve first)
+        int prio_lo = 0, prio_hi = 0;
+        if (ok) ok = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess;
+        if (ok) ok = cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        if (ok) ok = cudaStreamCreateWithPriority(&ctx->stream_big, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    }
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_join_big, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
