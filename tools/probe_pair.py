@@ -24,6 +24,7 @@ t0 = time.perf_counter()
 for _ in range(reps):
     eng.run_dense(D, fill=True, fetch=False); eng.sync()
     st += [eng.stage_ms(i) for i in range(4)]
+    if os.environ.get("PROBE_VERBOSE"): print("rep", [round(eng.stage_ms(i), 3) for i in range(4)], flush=True)
 dt = (time.perf_counter() - t0) / reps * 1e3
 print(json.dumps({"case": case, "cl": cl, "fh_cluster": fhc, "env": {k: v for k, v in os.environ.items() if k.startswith("S3_")}, "ms_per_pair": round(dt, 3),
                   "forest": round(st[0] / reps, 3), "cost": round(st[1] / reps, 3), "aggregate": round(st[2] / reps, 3), "post": round(st[3] / reps, 3)}), flush=True)
